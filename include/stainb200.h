@@ -1,0 +1,141 @@
+/* stainb200.h -- C ABI of libstainb200.so: the B200 (sm_100a) stain-processing hot path.
+ *
+ * The reference (sebastianffx/stainlib) has no FFI: its boundary is the Python class API of
+ * stainlib/extraction, stainlib/normalization and stainlib/augmentation.  Each entry point below replaces the body of
+ * one of those reference functions (cited per function, paths relative to the reference checkout); the Python mirror
+ * in stainlib_b200/ binds them with ctypes (stainlib_b200/_native.py) and keeps the reference's class/method names.
+ *
+ * Conventions
+ *   - plain C types only; no exceptions cross the boundary; every function returns 0 on success or a negative
+ *     sb_error code (sb_error_string() describes it; CUDA failures map to SB_ERR_CUDA, text via sb_last_cuda_error()).
+ *   - all image / matrix pointers are DEVICE pointers unless the function name ends in _host.
+ *   - images are uint8, C-contiguous [B,H,W,3] RGB; "tile" = one [H,W,3] image; N = H*W.
+ *   - stain matrices are double [B,2,3] (rows = stains, H first), maxC / scale / alpha / beta are double [B,2].
+ *   - work is stream-ordered on `stream` (a cudaStream_t passed as void*); nothing synchronises unless stated.
+ *   - the caller owns every buffer; the library allocates only inside sb_create / the *_host staging.
+ *   - per-tile int32 status word instead of raising mid-batch (bits below); outputs of flagged tiles are defined
+ *     as documented per function.
+ */
+#ifndef STAINB200_H
+#define STAINB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sb_handle sb_handle;
+
+enum sb_error {
+    SB_OK = 0,
+    SB_ERR_ARG = -1,        /* null pointer, non-positive shape, unknown method ...            */
+    SB_ERR_CUDA = -2,       /* a CUDA runtime call failed; see sb_last_cuda_error()             */
+    SB_ERR_UNSUPPORTED = -3,/* valid request the kernels do not implement (e.g. N > 2^24)       */
+    SB_ERR_NO_DEVICE = -4   /* no CUDA device / not an sm_100 part                              */
+};
+
+/* per-tile status bits */
+#define SB_STATUS_EMPTY_MASK   1  /* no tissue pixel: reference raises TissueMaskException (stain_utils.py:46-47)   */
+#define SB_STATUS_FEW_TISSUE   2  /* < 2 tissue pixels: np.cov is NaN, reference raises LinAlgError                 */
+#define SB_STATUS_ZERO_MAXC    4  /* a 99th-percentile concentration is 0 / non-finite: reference divides by zero   */
+#define SB_STATUS_DEGENERATE   8  /* non-finite stain matrix (e.g. zero covariance)                                 */
+
+enum sb_method { SB_METHOD_MACENKO = 0, SB_METHOD_VAHADANE = 1 };
+
+/* Parameters shared by the extract / fit / normalize entry points.  Defaults = the reference's keyword defaults. */
+typedef struct sb_params {
+    int    method;               /* sb_method                                                                      */
+    double luminosity_threshold; /* 0.8   stain_utils.py:32                                                        */
+    double angular_percentile;   /* 99    macenko_stain_extractor.py:7                                             */
+    double lasso_lambda;         /* 0.01  stain_utils.py:69 (get_concentrations regularizer)                       */
+    double conc_percentile;      /* 99    normalizer.py:36,47                                                      */
+    double dl_lambda;            /* 0.1   vahadane_stain_extractor.py:19 (trainDL lambda1)                         */
+    int    dl_iters;             /* full-batch dictionary-learning iterations (reference: 1 s wall-clock budget)   */
+    int    cluster_size;         /* CTAs cooperating on one tile: 0 = auto, else 1/2/4/8                            */
+} sb_params;
+
+void sb_default_params(sb_params* p);
+
+int  sb_create(int device, sb_handle** out);
+int  sb_destroy(sb_handle* h);
+const char* sb_error_string(int code);
+const char* sb_last_cuda_error(void);
+int  sb_version(void);
+/* number of kernel launches issued through this handle since creation (bench.py's gpu_launches) */
+long long sb_launch_count(const sb_handle* h);
+
+/* LuminosityThresholdTissueLocator.get_tissue_mask -- stainlib/utils/stain_utils.py:32-48.
+ * mask: uint8 [B,H,W] (1 = tissue).  status bit SB_STATUS_EMPTY_MASK where the reference would raise. */
+int sb_tissue_mask(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold,
+                   uint8_t* mask, int32_t* status, void* stream);
+
+/* MacenkoStainExtractor.get_stain_matrix -- stainlib/extraction/macenko_stain_extractor.py:7-44  (method MACENKO)
+ * VahadaneStainExtractor.get_stain_matrix -- stainlib/extraction/vahadane_stain_extractor.py:19-43 (method VAHADANE)
+ * M: double [B,2,3].  Flagged tiles get NaN matrices. */
+int sb_extract(sb_handle* h, const uint8_t* rgb, int B, int H, int W, const sb_params* p,
+               double* M, int32_t* status, void* stream);
+
+/* ExtractiveStainNormalizer.fit -- stainlib/normalization/normalizer.py:27-36, batched over tiles:
+ * M = get_stain_matrix(tile); maxC = percentile(get_concentrations(tile, M), 99, axis=0). */
+int sb_fit(sb_handle* h, const uint8_t* rgb, int B, int H, int W, const sb_params* p,
+           double* M, double* maxC, int32_t* status, void* stream);
+
+/* ExtractiveStainNormalizer.transform -- stainlib/normalization/normalizer.py:39-50, one fused pass sequence per
+ * tile.  M_target double[2,3], maxC_target double[2] live on the DEVICE (outputs of sb_fit).  M_src / maxC_src are
+ * optional outputs (may be NULL).  Output is NOT clipped (wraps modulo 256 like the reference's astype(uint8)).
+ * Flagged tiles: EMPTY_MASK / FEW_TISSUE / DEGENERATE -> input copied through; ZERO_MAXC -> zeros (as the reference). */
+int sb_normalize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const sb_params* p,
+                 const double* M_target, const double* maxC_target, double* M_src, double* maxC_src,
+                 int32_t* status, void* stream);
+
+/* Same as sb_normalize but rgb_in / rgb_out / status are HOST buffers (pinned for full speed): the call streams
+ * tile chunks H2D -> kernels -> D2H on internal streams with double buffering and returns after the last byte has
+ * landed in rgb_out (synchronous).  M_target / maxC_target are HOST doubles here. */
+int sb_normalize_host(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const sb_params* p,
+                      const double* M_target, const double* maxC_target, int32_t* status, int chunk_tiles);
+
+/* get_concentrations -- stainlib/utils/stain_utils.py:69-78.  C: float [B,N,2]. */
+int sb_concentrations(sb_handle* h, const uint8_t* rgb, int B, int H, int W, const double* M, double lasso_lambda,
+                      float* C, void* stream);
+
+/* Lines normalizer.py:46,48-50 alone (the fused OD+recombine kernel): out = uint8(255*exp(-(C*scale) @ M_target)),
+ * C = get_concentrations(tile, M_src[b]).  M_src [B,2,3], scale [B,2], M_target [2,3], all device doubles. */
+int sb_recombine(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const double* M_src,
+                 const double* scale, const double* M_target, double lasso_lambda, void* stream);
+
+/* StainAugmentor.pop -- stainlib/augmentation/augmenter.py:428-449 for given draws: concentrations under M[b],
+ * alpha*C+beta on tissue pixels (all pixels if augment_background), recombined with the tile's own M, clipped. */
+int sb_stain_augment(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const double* M,
+                     const double* alpha, const double* beta, int augment_background, double luminosity_threshold,
+                     double lasso_lambda, void* stream);
+
+/* ReinhardStainNormalizer.fit -- normalizer.py:64-68 (+ standardize_brightness stain_utils.py:188-194, lab_split
+ * :146-158, get_mean_std :174-186).  means/stds: double [B,3] of the brightness-standardised tile in LAB. */
+int sb_reinhard_stats(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double* means, double* stds,
+                      void* stream);
+
+/* ReinhardStainNormalizer.transform -- normalizer.py:70-94.  target_means/target_stds: device double[3]. */
+int sb_reinhard_transform(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W,
+                          const double* target_means, const double* target_stds, int mask_background,
+                          double luminosity_threshold, int32_t* status, void* stream);
+
+/* LuminosityStandardizer.standardize -- stain_utils.py:53-67. */
+int sb_luminosity_standardize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W,
+                              double percentile, void* stream);
+
+/* HedColorAugmenter.transform -- augmenter.py:276-331 for given draws.  sigma/bias: device double [B,3] (H,E,D);
+ * tiles whose mean/255 lies outside [cutoff_lo, cutoff_hi] are copied through (status bit 0 set to 1 = skipped).
+ * log_base: 10 = scikit-image 0.16-0.17 (pinned by the reference's environment.yml), e = <= 0.15. */
+int sb_hed_augment(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const double* sigma,
+                   const double* bias, double cutoff_lo, double cutoff_hi, double log_base, int32_t* status,
+                   void* stream);
+
+/* GrayscaleAugmentor.pop -- augmenter.py:390-401 for given draws alpha/beta: device double [B]. */
+int sb_grayscale_augment(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W,
+                         const double* alpha, const double* beta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAINB200_H */

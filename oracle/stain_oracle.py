@@ -1,0 +1,441 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle, never imported by the product path.
+
+Numpy (float64) restatement of the stainlib hot path, function by function, each citing the reference lines it
+follows (paths relative to the reference checkout).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+CPU-baseline legs may import this module; the product (``stainlib_b200``) must never do so.
+
+What is restated and how it is pinned
+-------------------------------------
+* Everything that the reference computes with numpy / OpenCV is restated with the *same* numpy / OpenCV calls
+  (``np.cov``, ``np.linalg.eigh``, ``np.percentile``, ``cv2.cvtColor`` ...).  It is pinned by golden fixtures produced
+  by running the reference's own, unmodified code in the build container (``oracle/gen_golden.py`` ->
+  ``tests/golden/*.npz``; checked by ``tests/test_oracle_golden.py``).
+* ``spams.lasso`` (SPAMS 2.6.2.5, ``stainlib/utils/environment.yml:148``; call site ``stain_utils.py:78``) is absent
+  from this image.  It is restated as the exact closed-form solution of the 2-atom non-negative LASSO
+  (``lasso_pos2``) and cross-checked against ``sklearn.linear_model.Lasso(positive=True)`` in
+  ``tests/test_oracle_lasso.py``.  PARITY UNPINNED against SPAMS itself: no SPAMS binary and no golden vector exist.
+* ``spams.trainDL`` (call site ``vahadane_stain_extractor.py:35-36``) is restated two ways: ``train_dl_online``
+  (Mairal et al., JMLR 2010, Alg. 1-2, seeded, fixed iteration count) and ``train_dl_fullbatch`` (deterministic
+  alternating minimisation of the same objective -- the algorithm the CUDA path runs).  PARITY UNPINNED against
+  SPAMS: the reference call is itself irreproducible (random init, 1-second time budget).
+* ``skimage.color.rgb2hed / hed2rgb / rgb2gray`` (scikit-image 0.17.2, ``environment.yml:107``; call sites
+  ``augmenter.py:295,319,397``) are restated from the published 0.17 formulas.  PARITY UNPINNED against skimage.
+"""
+import copy
+
+import cv2 as cv
+import numpy as np
+
+
+class TissueMaskException(Exception):
+    """Mirror of ``stainlib/utils/excepts.py:22-23``."""
+
+
+# ----------------------------------------------------------------------------------------------------- pixel utilities
+def is_uint8_image(I):
+    """``stain_utils.py:126-144``."""
+    return isinstance(I, np.ndarray) and I.ndim == 3 and I.dtype == np.uint8
+
+
+def get_tissue_mask(I, luminosity_threshold=0.8):
+    """``LuminosityThresholdTissueLocator.get_tissue_mask`` -- ``stain_utils.py:32-48``."""
+    assert is_uint8_image(I), "Image should be RGB uint8."
+    I_LAB = cv.cvtColor(I, cv.COLOR_RGB2LAB)
+    L = I_LAB[:, :, 0] / 255.0
+    mask = L < luminosity_threshold
+    if mask.sum() == 0:
+        raise TissueMaskException("Empty tissue mask computed")
+    return mask
+
+
+def convert_RGB_to_OD(I):
+    """``stain_utils.py:101-112``: zeros -> 1, OD = max(-ln(I/255), 1e-6)."""
+    I_masked = np.where(I == 0, 1, I).astype(I.dtype)
+    return np.maximum(-1 * np.log(I_masked / 255), 1e-6)
+
+
+def od_lut():
+    """The 256 values ``convert_RGB_to_OD`` can produce (float64)."""
+    return convert_RGB_to_OD(np.arange(256, dtype=np.uint8).reshape(1, 256, 1)).reshape(256)
+
+
+def convert_OD_to_RGB(OD):
+    """``stain_utils.py:114-124``."""
+    assert OD.min() >= 0, "Negative optical density."
+    OD = np.maximum(OD, 1e-6)
+    return (255 * np.exp(-1 * OD)).astype(np.uint8)
+
+
+def normalize_matrix_rows(A):
+    """``stain_utils.py:93-99``."""
+    return A / np.linalg.norm(A, axis=1)[:, None]
+
+
+def lasso_pos2(X, D, lam):
+    """Closed form of ``spams.lasso(X, D, mode=2, lambda1=lam, pos=True)`` for a 2-atom dictionary.
+
+    Solves, per column x of X (m x n):  min_{a >= 0}  0.5*||x - D a||^2 + lam*||a||_1 ,  D: m x 2.
+    Call site: ``stain_utils.py:78`` (lam = 0.01) and the sparse-coding step of ``spams.trainDL`` (lam = 0.1).
+    Returns a (2 x n) dense array (the reference densifies the CSC result with ``.toarray()``).
+
+    KKT case analysis with G = D^T D, u = D^T x - lam:
+      both active   a = G^-1 u                      if both components > 0
+      only atom 0   (u0/G00, 0)                     if u0 > 0 and u1 - G01*u0/G00 <= 0
+      only atom 1   (0, u1/G11)                     if u1 > 0 and u0 - G01*u1/G11 <= 0
+      none          (0, 0)
+    """
+    X = np.asarray(X, dtype=np.float64)
+    D = np.asarray(D, dtype=np.float64)
+    G = D.T @ D
+    u = D.T @ X - lam
+    u0, u1 = u[0], u[1]
+    det = G[0, 0] * G[1, 1] - G[0, 1] * G[0, 1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a0 = (G[1, 1] * u0 - G[0, 1] * u1) / det
+        a1 = (G[0, 0] * u1 - G[0, 1] * u0) / det
+    both = (a0 > 0) & (a1 > 0) & np.isfinite(a0) & np.isfinite(a1)
+    c0 = np.maximum(u0, 0) / G[0, 0]
+    c1 = np.maximum(u1, 0) / G[1, 1]
+    only0 = ~both & (c0 > 0) & (u1 - G[0, 1] * c0 <= 0)
+    only1 = ~both & ~only0 & (c1 > 0) & (u0 - G[0, 1] * c1 <= 0)
+    out = np.zeros((2, X.shape[1]), dtype=np.float64)
+    out[0] = np.where(both, a0, np.where(only0, c0, 0.0))
+    out[1] = np.where(both, a1, np.where(only1, c1, 0.0))
+    return out
+
+
+def get_concentrations(I, stain_matrix, regularizer=0.01):
+    """``stain_utils.py:69-78``: N x 2 concentrations of ALL pixels (background included)."""
+    OD = convert_RGB_to_OD(I).reshape((-1, 3))
+    return lasso_pos2(OD.T, np.asarray(stain_matrix).T, regularizer).T
+
+
+# ------------------------------------------------------------------------------------------------------ Macenko (a3)
+def macenko_stain_matrix(I, luminosity_threshold=0.8, angular_percentile=99):
+    """``MacenkoStainExtractor.get_stain_matrix`` -- ``macenko_stain_extractor.py:7-44``."""
+    assert is_uint8_image(I), "Image should be RGB uint8."
+    tissue_mask = get_tissue_mask(I, luminosity_threshold=luminosity_threshold).reshape((-1,))
+    OD = convert_RGB_to_OD(I).reshape((-1, 3))
+    OD = OD[tissue_mask]
+    _, V = np.linalg.eigh(np.cov(OD, rowvar=False))
+    V = V[:, [2, 1]]
+    if V[0, 0] < 0:
+        V[:, 0] *= -1
+    if V[0, 1] < 0:
+        V[:, 1] *= -1
+    That = np.dot(OD, V)
+    phi = np.arctan2(That[:, 1], That[:, 0])
+    minPhi = np.percentile(phi, 100 - angular_percentile)
+    maxPhi = np.percentile(phi, angular_percentile)
+    v1 = np.dot(V, np.array([np.cos(minPhi), np.sin(minPhi)]))
+    v2 = np.dot(V, np.array([np.cos(maxPhi), np.sin(maxPhi)]))
+    if v1[0] > v2[0]:
+        HE = np.array([v1, v2])
+    else:
+        HE = np.array([v2, v1])
+    return normalize_matrix_rows(HE)
+
+
+# ----------------------------------------------------------------------------------------------------- Vahadane (a6)
+RUIFROK_HE = np.array([[0.65, 0.70, 0.29], [0.07, 0.99, 0.11]], dtype=np.float64)
+
+
+def dl_objective(X, D, lam):
+    """(1/n) sum_i min_{a>=0} 0.5||x_i - D a||^2 + lam||a||_1 -- the quantity ``spams.trainDL`` (mode=2) minimises.
+    X: m x n, D: m x 2."""
+    A = lasso_pos2(X, D, lam)
+    R = X - D @ A
+    return float((0.5 * (R * R).sum(axis=0) + lam * A.sum(axis=0)).mean())
+
+
+def _dict_update(D, A, Bm, n_sweeps=1):
+    """Mairal et al. 2010, Alg. 2 (block-coordinate dictionary update) with the non-negativity projection of
+    ``posD=True`` and the unit-ball constraint of ``modeD=0``.  D: m x K (columns = atoms), A: K x K, Bm: m x K."""
+    D = D.copy()
+    K = D.shape[1]
+    for _ in range(n_sweeps):
+        for j in range(K):
+            if A[j, j] > 1e-12:
+                u = (Bm[:, j] - D @ A[:, j]) / A[j, j] + D[:, j]
+                u = np.maximum(u, 0.0)
+                D[:, j] = u / max(np.linalg.norm(u), 1.0)
+    return D
+
+
+def train_dl_fullbatch(X, lam=0.1, n_iter=50, D0=None):
+    """Deterministic full-batch alternating minimisation of the trainDL objective (K = 2, posAlpha, posD, modeD=0).
+
+    Each iteration: sparse-code every column with the current dictionary (``lasso_pos2``), accumulate
+    A = sum a a^T and B = sum x a^T over all columns, then one block-coordinate sweep of the dictionary update.
+    This is the algorithm the CUDA path runs (one pass over the tile per iteration).  X: m x n.  Returns m x 2.
+    """
+    D = normalize_matrix_rows(RUIFROK_HE).T.copy() if D0 is None else np.array(D0, dtype=np.float64)
+    for _ in range(n_iter):
+        Al = lasso_pos2(X, D, lam)
+        A = Al @ Al.T
+        Bm = X @ Al.T
+        D = _dict_update(D, A, Bm)
+    return D
+
+
+def train_dl_online(X, lam=0.1, n_iter=1000, batchsize=512, seed=0):
+    """Seeded restatement of SPAMS' online dictionary learning (Mairal et al. 2010, Alg. 1) as the reference calls it
+    (``vahadane_stain_extractor.py:35-36``: K=2, mode=2, modeD=0, posAlpha, posD, D=None -> random data columns).
+    The reference's 1-second time budget (iter=-1) is replaced by a fixed iteration count."""
+    rng = np.random.default_rng(seed)
+    m, n = X.shape
+    idx = rng.choice(n, size=2, replace=False)
+    D = X[:, idx].copy()
+    D = D / np.maximum(np.linalg.norm(D, axis=0), 1e-12)
+    A = np.zeros((2, 2))
+    Bm = np.zeros((m, 2))
+    t0 = 1e-5
+    for t in range(1, n_iter + 1):
+        cols = rng.integers(0, n, size=min(batchsize, n))
+        x = X[:, cols]
+        al = lasso_pos2(x, D, lam)
+        # SPAMS rescales the past information with a forgetting factor; rho = 1 here (pure averaging)
+        beta = 1.0 if t == 1 else (1.0 - 1.0 / t) ** 1.0
+        A = beta * A + (al @ al.T) / x.shape[1]
+        Bm = beta * Bm + (x @ al.T) / x.shape[1]
+        D = _dict_update(D, A + t0 * np.eye(2), Bm + t0 * D)
+    return D
+
+
+def vahadane_finish(dictionary):
+    """Row ordering and normalisation of ``vahadane_stain_extractor.py:38-43`` (dictionary: 2 x 3, rows = stains)."""
+    dictionary = np.array(dictionary, dtype=np.float64)
+    if dictionary[0, 0] < dictionary[1, 0]:
+        dictionary = dictionary[[1, 0], :]
+    return normalize_matrix_rows(dictionary)
+
+
+def vahadane_stain_matrix(I, luminosity_threshold=0.8, regularizer=0.1, n_iter=50, solver="fullbatch", seed=0):
+    """``VahadaneStainExtractor.get_stain_matrix`` -- ``vahadane_stain_extractor.py:19-43`` with ``spams.trainDL``
+    replaced by one of the two restatements above."""
+    assert is_uint8_image(I), "Image should be RGB uint8."
+    tissue_mask = get_tissue_mask(I, luminosity_threshold=luminosity_threshold).reshape((-1,))
+    OD = convert_RGB_to_OD(I).reshape((-1, 3))
+    OD = OD[tissue_mask]
+    if solver == "fullbatch":
+        D = train_dl_fullbatch(OD.T, lam=regularizer, n_iter=n_iter)
+    else:
+        D = train_dl_online(OD.T, lam=regularizer, n_iter=n_iter, seed=seed)
+    return vahadane_finish(D.T)
+
+
+# ------------------------------------------------------------------------------------------- extractive normaliser (a5)
+class ExtractiveStainNormalizer(object):
+    """``normalizer.py:16-50``."""
+
+    def __init__(self, method, **extractor_kwargs):
+        if method.lower() == "macenko":
+            self.get_stain_matrix = macenko_stain_matrix
+        elif method.lower() == "vahadane":
+            self.get_stain_matrix = lambda I: vahadane_stain_matrix(I, **extractor_kwargs)
+        else:
+            raise Exception("Method not recognized.")
+
+    def fit(self, target):
+        self.stain_matrix_target = self.get_stain_matrix(target)
+        self.target_concentrations = get_concentrations(target, self.stain_matrix_target)
+        self.maxC_target = np.percentile(self.target_concentrations, 99, axis=0).reshape((1, 2))
+
+    def transform(self, I):
+        stain_matrix_source = self.get_stain_matrix(I)
+        source_concentrations = get_concentrations(I, stain_matrix_source)
+        maxC_source = np.percentile(source_concentrations, 99, axis=0).reshape((1, 2))
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            source_concentrations *= (self.maxC_target / maxC_source)
+            tmp = 255 * np.exp(-1 * np.dot(source_concentrations, self.stain_matrix_target))
+            return tmp.reshape(I.shape).astype(np.uint8)  # NOTE: no clip -- wraps modulo 256 like the reference
+
+
+def recombine(I, stain_matrix_source, scale, stain_matrix_target, regularizer=0.01):
+    """Lines ``normalizer.py:46,48-50`` in isolation (the fused OD+recombine kernel's job): concentrations of I under
+    ``stain_matrix_source``, multiplied by ``scale`` (1x2), recombined with ``stain_matrix_target``; unclipped cast."""
+    C = get_concentrations(I, stain_matrix_source, regularizer)
+    C = C * np.asarray(scale, dtype=np.float64).reshape(1, 2)
+    with np.errstate(over="ignore", invalid="ignore"):
+        tmp = 255 * np.exp(-1 * np.dot(C, stain_matrix_target))
+        return tmp.reshape(I.shape).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------------ Reinhard (a7)
+def standardize_brightness(I):
+    """``stain_utils.py:188-194``."""
+    p = np.percentile(I, 90)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.clip(I * 255.0 / p, 0, 255).astype(np.uint8)
+
+
+def lab_split(I):
+    """``stain_utils.py:146-158``."""
+    I = cv.cvtColor(I, cv.COLOR_RGB2LAB)
+    I = I.astype(np.float32)
+    I1, I2, I3 = cv.split(I)
+    I1 /= 2.55
+    I2 -= 128.0
+    I3 -= 128.0
+    return I1, I2, I3
+
+
+def merge_back(I1, I2, I3):
+    """``stain_utils.py:160-172``."""
+    I1 = I1 * 2.55
+    I2 = I2 + 128.0
+    I3 = I3 + 128.0
+    I = np.clip(cv.merge((I1, I2, I3)), 0, 255).astype(np.uint8)
+    return cv.cvtColor(I, cv.COLOR_LAB2RGB)
+
+
+def get_mean_std(I):
+    """``stain_utils.py:174-186``."""
+    I1, I2, I3 = lab_split(I)
+    m1, sd1 = cv.meanStdDev(I1)
+    m2, sd2 = cv.meanStdDev(I2)
+    m3, sd3 = cv.meanStdDev(I3)
+    return (m1, m2, m3), (sd1, sd2, sd3)
+
+
+class ReinhardStainNormalizer(object):
+    """``normalizer.py:54-94``."""
+
+    def __init__(self, target_means=0, target_stds=0):
+        self.target_means = target_means
+        self.target_stds = target_stds
+
+    def fit(self, target):
+        target = standardize_brightness(target)
+        self.target_means, self.target_stds = get_mean_std(target)
+
+    def transform(self, I, mask_background=False, luminosity_threshold=0.8):
+        I = standardize_brightness(I)
+        I1, I2, I3 = lab_split(I)
+        means, stds = get_mean_std(I)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            norm1 = ((I1 - means[0]) * (self.target_stds[0] / stds[0])) + self.target_means[0]
+            norm2 = ((I2 - means[1]) * (self.target_stds[1] / stds[1])) + self.target_means[1]
+            norm3 = ((I3 - means[2]) * (self.target_stds[2] / stds[2])) + self.target_means[2]
+        if mask_background:
+            tissue_mask = get_tissue_mask(I, luminosity_threshold=luminosity_threshold)
+            background = np.array(~tissue_mask * 254).astype(np.uint8)
+            norm1, norm2, norm3 = (np.multiply(tissue_mask, norm1), np.multiply(tissue_mask, norm2),
+                                   np.multiply(tissue_mask, norm3))
+            return merge_back(background + norm1, norm2, norm3)
+        return merge_back(norm1, norm2, norm3)
+
+
+# --------------------------------------------------------------------------------------- luminosity standardiser (f1)
+def luminosity_standardize(I, percentile=95):
+    """``LuminosityStandardizer.standardize`` -- ``stain_utils.py:53-67``."""
+    assert is_uint8_image(I), "Image should be RGB uint8."
+    I_LAB = cv.cvtColor(I, cv.COLOR_RGB2LAB)
+    L_float = I_LAB[:, :, 0].astype(float)
+    p = np.percentile(L_float, percentile)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        I_LAB[:, :, 0] = np.clip(255 * L_float / p, 0, 255).astype(np.uint8)
+    return cv.cvtColor(I_LAB, cv.COLOR_LAB2RGB)
+
+
+# ------------------------------------------------------------------------------------------------- HED (a8, a10)
+# scikit-image 0.17.2 colour deconvolution (skimage/color/colorconv.py: rgb_from_hed, separate_stains, combine_stains)
+RGB_FROM_HED = np.array([[0.65, 0.70, 0.29], [0.07, 0.99, 0.11], [0.27, 0.57, 0.78]])
+HED_FROM_RGB = np.linalg.inv(RGB_FROM_HED)
+
+
+def rgb2hed(rgb, log_base=10.0):
+    """skimage 0.17 ``separate_stains(rgb, hed_from_rgb)``: ``x = img_as_float(rgb) + 2; -(log(x)/log(b)) @ conv``
+    (b = 10 in 0.16-0.17).  uint8 input is scaled by 1/255, float input is taken as is."""
+    x = rgb.astype(np.float64) / 255.0 if rgb.dtype.kind != "f" else rgb.astype(np.float64)
+    x = x + 2.0
+    stains = np.reshape(-np.log(x) / np.log(log_base), (-1, 3)) @ HED_FROM_RGB
+    return np.reshape(stains, rgb.shape)
+
+
+def hed2rgb(hed, log_base=10.0):
+    """skimage 0.17 ``combine_stains(hed, rgb_from_hed)``: ``rescale_intensity(b ** (-(hed @ conv)) - 2,
+    in_range=(-1, 1))`` -> clip to [-1, 1] then map linearly to [0, 1]."""
+    logrgb2 = -np.reshape(hed.astype(np.float64), (-1, 3)) @ RGB_FROM_HED
+    rgb2 = np.power(log_base, logrgb2)
+    out = np.reshape(rgb2 - 2.0, hed.shape)
+    out = np.clip(out, -1.0, 1.0)
+    return (out + 1.0) / 2.0
+
+
+def hed_augment(patch, sigmas, biases, cutoff_range=(0.05, 0.95), log_base=10.0):
+    """``HedColorAugmenter.transform`` -- ``augmenter.py:276-331`` for a fixed draw of (sigmas, biases)."""
+    if patch.dtype.kind == "f":
+        patch_mean = np.mean(a=patch)
+    else:
+        patch_mean = np.mean(a=patch.astype(dtype=np.float32)) / 255.0
+    if cutoff_range[0] <= patch_mean <= cutoff_range[1]:
+        patch_hed = rgb2hed(patch, log_base)
+        for k in range(3):
+            if sigmas[k] != 0.0:
+                patch_hed[:, :, k] *= 1.0 + sigmas[k]
+            if biases[k] != 0.0:
+                patch_hed[:, :, k] += biases[k]
+        patch_rgb = hed2rgb(patch_hed, log_base)
+        patch_transformed = np.clip(a=patch_rgb, a_min=0.0, a_max=1.0)
+        if patch.dtype.kind != "f":
+            patch_transformed *= 255.0
+            patch_transformed = patch_transformed.astype(dtype=np.uint8)
+        return patch_transformed
+    return patch
+
+
+def rgb2gray(rgb):
+    """skimage 0.17 ``rgb2gray``: float image @ [0.2125, 0.7154, 0.0721]."""
+    x = rgb.astype(np.float64) / 255.0 if rgb.dtype.kind != "f" else rgb.astype(np.float64)
+    return x @ np.array([0.2125, 0.7154, 0.0721])
+
+
+def grayscale_augment(I, alpha, beta):
+    """``GrayscaleAugmentor.pop`` -- ``augmenter.py:390-401`` for a fixed draw (alpha, beta)."""
+    g = rgb2gray(I)
+    g = np.clip((g * alpha) + beta, 0, 1)
+    g3 = np.stack([g, g, g], axis=2)
+    return np.clip(g3 * 255, 0, 255).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------- StainAugmentor (a11)
+class StainAugmentor(object):
+    """``augmenter.py:403-449``.  ``pop`` takes the draws explicitly (``alphas``, ``betas``: length-2) or, when they are
+    ``None``, draws them from numpy's global RNG in the reference's order (alpha0, beta0, alpha1, beta1)."""
+
+    def __init__(self, method, sigma1=0.2, sigma2=0.2, augment_background=False, **extractor_kwargs):
+        if method.lower() == "macenko":
+            self.get_stain_matrix = macenko_stain_matrix
+        elif method.lower() == "vahadane":
+            self.get_stain_matrix = lambda I: vahadane_stain_matrix(I, **extractor_kwargs)
+        else:
+            raise Exception("Method not recognized.")
+        self.sigma1 = sigma1
+        self.sigma2 = sigma2
+        self.augment_background = augment_background
+
+    def fit(self, I):
+        self.image_shape = I.shape
+        self.stain_matrix = self.get_stain_matrix(I)
+        self.source_concentrations = get_concentrations(I, self.stain_matrix)
+        self.n_stains = self.source_concentrations.shape[1]
+        self.tissue_mask = get_tissue_mask(I).ravel()
+
+    def pop(self, alphas=None, betas=None):
+        augmented = copy.deepcopy(self.source_concentrations)
+        for i in range(self.n_stains):
+            if alphas is None:
+                alpha = np.random.uniform(1 - self.sigma1, 1 + self.sigma1)
+                beta = np.random.uniform(-self.sigma2, self.sigma2)
+            else:
+                alpha, beta = alphas[i], betas[i]
+            if self.augment_background:
+                augmented[:, i] *= alpha
+                augmented[:, i] += beta
+            else:
+                augmented[self.tissue_mask, i] *= alpha
+                augmented[self.tissue_mask, i] += beta
+        I_aug = 255 * np.exp(-1 * np.dot(augmented, self.stain_matrix))
+        I_aug = I_aug.reshape(self.image_shape)
+        return np.clip(I_aug, 0, 255).astype(np.uint8)

@@ -1,0 +1,358 @@
+// sb_api.cu -- the extern "C" boundary declared in include/stainb200.h.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sb_kernels.h"
+#include "sb_tables.inc"
+
+namespace {
+
+thread_local std::string g_last_cuda_error;
+
+int cuda_fail(cudaError_t e, const char* what) {
+    g_last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return SB_ERR_CUDA;
+}
+#define SB_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);      \
+    } while (0)
+
+}  // namespace
+
+struct sb_handle {
+    int device = 0;
+    int num_sms = 0;
+    long long launches = 0;
+    sb::Tables tab{};
+    void* table_mem = nullptr;
+    // host-streaming state (sb_normalize_host)
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    static constexpr int NSLOT = 3;
+    uint8_t* slot_in[NSLOT] = {nullptr, nullptr, nullptr};
+    uint8_t* slot_out[NSLOT] = {nullptr, nullptr, nullptr};
+    size_t slot_bytes = 0;
+    cudaEvent_t ev_in[NSLOT] = {}, ev_comp[NSLOT] = {}, ev_out[NSLOT] = {};
+    double* d_target = nullptr;   // [6 + 2]
+    int32_t* d_status = nullptr;
+    size_t status_cap = 0;
+};
+
+namespace {
+
+// Largest luminance table index whose L satisfies L/255.0 < thr (float64), -1 if none.  L is monotone in the index.
+int mask_y_bound(double thr) {
+    int best = -1;
+    for (int i = 0; i < 3072; ++i) {
+        long long L = ((long long)SB_LAB_LSCALE * SB_CBRT_TAB[i] + SB_LAB_LSHIFT + (1 << 14)) >> 15;
+        if (L < 0) L = 0;
+        if (L > 255) L = 255;
+        if ((double)L / 255.0 < thr) best = i;
+    }
+    return best;
+}
+float mask_ybound_f(double thr) {
+    const int yb = mask_y_bound(thr);
+    return (float)((double)(yb + 1) * 4096.0 - 2048.0);
+}
+
+int check_image_args(const sb_handle* h, const void* rgb, int B, int H, int W) {
+    if (!h || !rgb || B <= 0 || H <= 0 || W <= 0) return SB_ERR_ARG;
+    if ((long long)H * W > (1LL << 24)) return SB_ERR_UNSUPPORTED;   // histogram counters / rank arithmetic are 32-bit
+    return SB_OK;
+}
+int is_aligned(const void* a, const void* b, int npx) {
+    return (((uintptr_t)a | (uintptr_t)b) % 16 == 0) && (((size_t)npx * 3) % 16 == 0);
+}
+int pick_cluster(const sb_handle* h, int B, int npx, int requested) {
+    if (requested == 1 || requested == 2 || requested == 4 || requested == 8) return requested;
+    // auto: keep ~<=128k pixels per CTA and enough clusters to fill the SMs when the batch is small
+    int S = 1;
+    while (S < 8 && ((long long)npx / S > 160 * 1024 || (long long)B * S * 1 < h->num_sms)) S *= 2;
+    if (npx / S < 16 * sb::NT) { while (S > 1 && npx / S < 16 * sb::NT) S /= 2; }
+    return S;
+}
+
+int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B, int H, int W, const sb_params* p,
+                 const double* Mt, const double* maxCt, double* M, double* maxC, int32_t* status, cudaStream_t stream) {
+    if (!p) return SB_ERR_ARG;
+    if (p->method != SB_METHOD_MACENKO && p->method != SB_METHOD_VAHADANE) return SB_ERR_ARG;
+    sb::PipeArgs a{};
+    a.in = in; a.out = out; a.B = B; a.npx = H * W;
+    a.aligned = is_aligned(in, out, a.npx);
+    a.tab = h->tab;
+    a.mode = mode; a.method = p->method;
+    a.cluster_size = pick_cluster(h, B, a.npx, p->cluster_size);
+    a.ybound = mask_ybound_f(p->luminosity_threshold);
+    a.ang_pct = p->angular_percentile; a.lasso_lambda = p->lasso_lambda; a.conc_pct = p->conc_percentile;
+    a.dl_lambda = p->dl_lambda; a.dl_iters = p->dl_iters;
+    a.Mt = Mt; a.maxCt = maxCt; a.M_out = M; a.maxC_out = maxC; a.status = status;
+    cudaError_t e = (cudaError_t)sb::launch_tile_pipeline(a, h->num_sms, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tile_pipeline launch");
+    h->launches += 1;
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void sb_default_params(sb_params* p) {
+    if (!p) return;
+    p->method = SB_METHOD_MACENKO;
+    p->luminosity_threshold = 0.8;
+    p->angular_percentile = 99.0;
+    p->lasso_lambda = 0.01;
+    p->conc_percentile = 99.0;
+    p->dl_lambda = 0.1;
+    p->dl_iters = 50;
+    p->cluster_size = 0;
+}
+
+int sb_version(void) { return 100; }
+
+const char* sb_error_string(int code) {
+    switch (code) {
+        case SB_OK: return "ok";
+        case SB_ERR_ARG: return "invalid argument";
+        case SB_ERR_CUDA: return "CUDA error";
+        case SB_ERR_UNSUPPORTED: return "unsupported request";
+        case SB_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+        default: return "unknown error";
+    }
+}
+const char* sb_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+long long sb_launch_count(const sb_handle* h) { return h ? h->launches : 0; }
+
+int sb_create(int device, sb_handle** out) {
+    if (!out) return SB_ERR_ARG;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return SB_ERR_NO_DEVICE;
+    SB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return SB_ERR_NO_DEVICE;   // kernels are built for sm_100a only
+    sb_handle* h = new sb_handle();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+
+    // ---- constant tables, one allocation
+    std::vector<float> od32(256), gy(768);
+    for (int i = 0; i < 256; ++i) od32[i] = (float)SB_OD_TAB[i];
+    for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < 256; ++i) gy[c * 256 + i] = (float)(SB_RGB2LAB_COEFFS[3 + c] * (int)SB_GAMMA_TAB[i]);
+    size_t off = 0;
+    auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_od = place(256 * 4), o_gy = place(768 * 4), o_od64 = place(256 * 8), o_gam = place(256 * 2),
+                 o_cb = place(3072 * 2), o_yf = place(512 * 4), o_ig = place(4096);
+    SB_CUDA(cudaMalloc(&h->table_mem, off));
+    char* base = (char*)h->table_mem;
+    SB_CUDA(cudaMemcpy(base + o_od, od32.data(), 256 * 4, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(base + o_gy, gy.data(), 768 * 4, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(base + o_od64, SB_OD_TAB, 256 * 8, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(base + o_gam, SB_GAMMA_TAB, 256 * 2, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(base + o_cb, SB_CBRT_TAB, 3072 * 2, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(base + o_yf, SB_LAB2YF_TAB, 512 * 4, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(base + o_ig, SB_INVGAMMA_TAB, 4096, cudaMemcpyHostToDevice));
+    h->tab.od = (const float*)(base + o_od);
+    h->tab.gy = (const float*)(base + o_gy);
+    h->tab.od64 = (const double*)(base + o_od64);
+    h->tab.gamma = (const unsigned short*)(base + o_gam);
+    h->tab.cbrt = (const unsigned short*)(base + o_cb);
+    h->tab.lab2yf = (const int*)(base + o_yf);
+    h->tab.invgamma = (const unsigned char*)(base + o_ig);
+    *out = h;
+    return SB_OK;
+}
+
+int sb_destroy(sb_handle* h) {
+    if (!h) return SB_ERR_ARG;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < sb_handle::NSLOT; ++i) {
+        if (h->slot_in[i]) cudaFree(h->slot_in[i]);
+        if (h->slot_out[i]) cudaFree(h->slot_out[i]);
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    if (h->d_target) cudaFree(h->d_target);
+    if (h->d_status) cudaFree(h->d_status);
+    if (h->table_mem) cudaFree(h->table_mem);
+    delete h;
+    return SB_OK;
+}
+
+int sb_tissue_mask(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold, uint8_t* mask,
+                   int32_t* status, void* stream) {
+    int rc = check_image_args(h, rgb, B, H, W);
+    if (rc) return rc;
+    if (!mask) return SB_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    sb::PointArgs a{};
+    a.in = rgb; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb, mask, a.npx) && (a.npx % 16 == 0);
+    a.tab = h->tab; a.ybound = mask_ybound_f(luminosity_threshold); a.mask_out = mask; a.status = status;
+    if (status) {
+        // preset every tile to EMPTY_MASK (int32 value 1); the kernel clears the bit when it sees tissue
+        std::vector<int32_t> ones((size_t)B, SB_STATUS_EMPTY_MASK);
+        SB_CUDA(cudaMemcpyAsync(status, ones.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaStreamSynchronize(st));   // `ones` is pageable host memory
+    }
+    cudaError_t e = (cudaError_t)sb::launch_mask(a, h->num_sms, st);
+    if (e != cudaSuccess) return cuda_fail(e, "mask launch");
+    h->launches += 1;
+    return SB_OK;
+}
+
+int sb_extract(sb_handle* h, const uint8_t* rgb, int B, int H, int W, const sb_params* p, double* M, int32_t* status,
+               void* stream) {
+    int rc = check_image_args(h, rgb, B, H, W);
+    if (rc) return rc;
+    if (!M) return SB_ERR_ARG;
+    return run_pipeline(h, sb::PIPE_EXTRACT, rgb, nullptr, B, H, W, p, nullptr, nullptr, M, nullptr, status, (cudaStream_t)stream);
+}
+
+int sb_fit(sb_handle* h, const uint8_t* rgb, int B, int H, int W, const sb_params* p, double* M, double* maxC,
+           int32_t* status, void* stream) {
+    int rc = check_image_args(h, rgb, B, H, W);
+    if (rc) return rc;
+    if (!M || !maxC) return SB_ERR_ARG;
+    return run_pipeline(h, sb::PIPE_FIT, rgb, nullptr, B, H, W, p, nullptr, nullptr, M, maxC, status, (cudaStream_t)stream);
+}
+
+int sb_normalize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const sb_params* p,
+                 const double* M_target, const double* maxC_target, double* M_src, double* maxC_src, int32_t* status,
+                 void* stream) {
+    int rc = check_image_args(h, rgb_in, B, H, W);
+    if (rc) return rc;
+    if (!rgb_out || !M_target || !maxC_target || rgb_in == rgb_out) return SB_ERR_ARG;
+    return run_pipeline(h, sb::PIPE_NORMALIZE, rgb_in, rgb_out, B, H, W, p, M_target, maxC_target, M_src, maxC_src, status,
+                        (cudaStream_t)stream);
+}
+
+int sb_normalize_host(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const sb_params* p,
+                      const double* M_target, const double* maxC_target, int32_t* status, int chunk_tiles) {
+    int rc = check_image_args(h, rgb_in, B, H, W);
+    if (rc) return rc;
+    if (!rgb_out || !M_target || !maxC_target || !p) return SB_ERR_ARG;
+    SB_CUDA(cudaSetDevice(h->device));
+    const size_t tile_bytes = (size_t)H * W * 3;
+    if (chunk_tiles <= 0) {
+        chunk_tiles = (int)(((size_t)48 << 20) / tile_bytes);
+        if (chunk_tiles < 1) chunk_tiles = 1;
+    }
+    if (chunk_tiles > B) chunk_tiles = B;
+    const size_t need = (size_t)chunk_tiles * tile_bytes;
+    if (!h->s_in) {
+        SB_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        SB_CUDA(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+        SB_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < sb_handle::NSLOT; ++i) {
+            SB_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            SB_CUDA(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+            SB_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+        }
+        SB_CUDA(cudaMalloc(&h->d_target, 8 * sizeof(double)));
+    }
+    if (h->slot_bytes < need) {
+        for (int i = 0; i < sb_handle::NSLOT; ++i) {
+            if (h->slot_in[i]) cudaFree(h->slot_in[i]);
+            if (h->slot_out[i]) cudaFree(h->slot_out[i]);
+            SB_CUDA(cudaMalloc(&h->slot_in[i], need));
+            SB_CUDA(cudaMalloc(&h->slot_out[i], need));
+        }
+        h->slot_bytes = need;
+    }
+    if (h->status_cap < (size_t)B) {
+        if (h->d_status) cudaFree(h->d_status);
+        SB_CUDA(cudaMalloc(&h->d_status, (size_t)B * 4));
+        h->status_cap = (size_t)B;
+    }
+    double tgt[8];
+    std::memcpy(tgt, M_target, 6 * sizeof(double));
+    std::memcpy(tgt + 6, maxC_target, 2 * sizeof(double));
+    SB_CUDA(cudaMemcpyAsync(h->d_target, tgt, sizeof(tgt), cudaMemcpyHostToDevice, h->s_comp));
+    SB_CUDA(cudaStreamSynchronize(h->s_comp));
+
+    const int nchunks = (B + chunk_tiles - 1) / chunk_tiles;
+    for (int c = 0; c < nchunks; ++c) {
+        const int slot = c % sb_handle::NSLOT;
+        const int t0 = c * chunk_tiles, nt = (B - t0 < chunk_tiles) ? (B - t0) : chunk_tiles;
+        const size_t bytes = (size_t)nt * tile_bytes;
+        // the slot's previous occupant must have been consumed by compute (input) and copied out (output)
+        if (c >= sb_handle::NSLOT) {
+            SB_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_comp[slot], 0));
+            SB_CUDA(cudaStreamWaitEvent(h->s_comp, h->ev_out[slot], 0));
+        }
+        SB_CUDA(cudaMemcpyAsync(h->slot_in[slot], rgb_in + (size_t)t0 * tile_bytes, bytes, cudaMemcpyHostToDevice, h->s_in));
+        SB_CUDA(cudaEventRecord(h->ev_in[slot], h->s_in));
+        SB_CUDA(cudaStreamWaitEvent(h->s_comp, h->ev_in[slot], 0));
+        rc = run_pipeline(h, sb::PIPE_NORMALIZE, h->slot_in[slot], h->slot_out[slot], nt, H, W, p, h->d_target, h->d_target + 6,
+                          nullptr, nullptr, h->d_status + t0, h->s_comp);
+        if (rc) return rc;
+        SB_CUDA(cudaEventRecord(h->ev_comp[slot], h->s_comp));
+        SB_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
+        SB_CUDA(cudaMemcpyAsync(rgb_out + (size_t)t0 * tile_bytes, h->slot_out[slot], bytes, cudaMemcpyDeviceToHost, h->s_out));
+        SB_CUDA(cudaEventRecord(h->ev_out[slot], h->s_out));
+    }
+    SB_CUDA(cudaStreamSynchronize(h->s_out));
+    if (status) {
+        SB_CUDA(cudaMemcpyAsync(status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, h->s_out));
+        SB_CUDA(cudaStreamSynchronize(h->s_out));
+    }
+    SB_CUDA(cudaStreamSynchronize(h->s_comp));
+    return SB_OK;
+}
+
+int sb_concentrations(sb_handle* h, const uint8_t* rgb, int B, int H, int W, const double* M, double lasso_lambda,
+                      float* C, void* stream) {
+    int rc = check_image_args(h, rgb, B, H, W);
+    if (rc) return rc;
+    if (!M || !C) return SB_ERR_ARG;
+    sb::PointArgs a{};
+    a.in = rgb; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb, rgb, a.npx);
+    a.tab = h->tab; a.M = M; a.lasso_lambda = lasso_lambda; a.conc_out = C;
+    cudaError_t e = (cudaError_t)sb::launch_concentrations(a, h->num_sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "concentrations launch");
+    h->launches += 1;
+    return SB_OK;
+}
+
+int sb_recombine(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const double* M_src,
+                 const double* scale, const double* M_target, double lasso_lambda, void* stream) {
+    int rc = check_image_args(h, rgb_in, B, H, W);
+    if (rc) return rc;
+    if (!rgb_out || !M_src || !scale || !M_target) return SB_ERR_ARG;
+    sb::PointArgs a{};
+    a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb_in, rgb_out, a.npx);
+    a.tab = h->tab; a.M = M_src; a.scale = scale; a.Mt = M_target; a.lasso_lambda = lasso_lambda;
+    cudaError_t e = (cudaError_t)sb::launch_recombine(a, h->num_sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "recombine launch");
+    h->launches += 1;
+    return SB_OK;
+}
+
+int sb_stain_augment(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const double* M,
+                     const double* alpha, const double* beta, int augment_background, double luminosity_threshold,
+                     double lasso_lambda, void* stream) {
+    int rc = check_image_args(h, rgb_in, B, H, W);
+    if (rc) return rc;
+    if (!rgb_out || !M || !alpha || !beta) return SB_ERR_ARG;
+    sb::PointArgs a{};
+    a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb_in, rgb_out, a.npx);
+    a.tab = h->tab; a.M = M; a.scale = alpha; a.beta = beta; a.lasso_lambda = lasso_lambda;
+    a.augment_background = augment_background; a.ybound = mask_ybound_f(luminosity_threshold);
+    cudaError_t e = (cudaError_t)sb::launch_stain_augment(a, h->num_sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "stain_augment launch");
+    h->launches += 1;
+    return SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,261 @@
+// sb_device.cuh -- device-side building blocks shared by the stain kernels (sm_100a).
+//
+// Per-pixel arithmetic is fp32 on 256-entry LUTs (OD is a function of a uint8: stain_utils.py:101-112); per-tile
+// reductions are fp64 in a fixed order (deterministic); order statistics are exact selections on 23-bit monotone keys.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace sb {
+
+constexpr int NT = 512;             // threads per CTA for the tile kernels
+constexpr int NWARP = NT / 32;
+constexpr int GROUP_PX = 16;        // pixels per thread-iteration: 48 B = 3 x 16-byte vectors
+constexpr int KEY_BITS = 23;
+constexpr int L1_BITS = 12, L1_BINS = 1 << L1_BITS;   // level-1 histogram: top 12 bits of the key
+constexpr int L2_BITS = 11, L2_BINS = 1 << L2_BITS;   // level-2 histogram: low 11 bits
+constexpr float CONC_KEY_K = 2.0f;  // concentration key: t = 2 - K/(C+K) in [1,2)
+
+// ------------------------------------------------------------------------------------------------ tables (device)
+struct Tables {
+    const float* od;        // [256]   OD LUT, fp32
+    const float* gy;        // [3*256] pre-weighted luminance terms: coeffY[c] * gamma[v] (exact integers < 2^24)
+    const double* od64;     // [256]
+    const unsigned short* gamma;   // [256]
+    const unsigned short* cbrt;    // [3072]
+    const int* lab2yf;             // [512]
+    const unsigned char* invgamma; // [4096]
+};
+
+// ------------------------------------------------------------------------------------------------ memory helpers
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_keep(const uint4* p) { return __ldg(p); }
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0u, 0x4440u + i); }
+
+// Loads pixel group g (16 px = 12 words) of a tile. Full + 16B-aligned groups use three 16-byte loads; the ragged
+// tail (or an unaligned tile) is assembled bytewise and padded with 255 (white = background).
+template <bool KEEP>
+__device__ __forceinline__ void load_group(const uint8_t* __restrict__ tile, int npx, int g, bool aligned, uint32_t (&w)[12], int& nvalid) {
+    const int p0 = g * GROUP_PX;
+    nvalid = min(GROUP_PX, npx - p0);
+    const uint8_t* src = tile + (size_t)p0 * 3;
+    if (aligned && nvalid == GROUP_PX) {
+        const uint4* v = reinterpret_cast<const uint4*>(src);
+        uint4 a = KEEP ? ldg_keep(v) : ldg_stream(v), b = KEEP ? ldg_keep(v + 1) : ldg_stream(v + 1), c = KEEP ? ldg_keep(v + 2) : ldg_stream(v + 2);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+    } else {
+        const int nbytes = nvalid * 3;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int k = i * 4 + j;
+                uint32_t byte = k < nbytes ? (uint32_t)src[k] : 255u;
+                x |= byte << (8 * j);
+            }
+            w[i] = x;
+        }
+    }
+}
+
+__device__ __forceinline__ void store_group(uint8_t* __restrict__ tile, int npx, int g, bool aligned, const uint32_t (&w)[12]) {
+    const int p0 = g * GROUP_PX;
+    const int nvalid = min(GROUP_PX, npx - p0);
+    uint8_t* dst = tile + (size_t)p0 * 3;
+    if (aligned && nvalid == GROUP_PX) {
+        uint4* v = reinterpret_cast<uint4*>(dst);
+        stg_stream(v, make_uint4(w[0], w[1], w[2], w[3]));
+        stg_stream(v + 1, make_uint4(w[4], w[5], w[6], w[7]));
+        stg_stream(v + 2, make_uint4(w[8], w[9], w[10], w[11]));
+    } else {
+        const int nbytes = nvalid * 3;
+        for (int k = 0; k < nbytes; ++k) dst[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    }
+}
+
+// Calls f(pixel_index_in_group, r, g, b) for the 16 pixels of a group.
+template <class F>
+__device__ __forceinline__ void for_each_px(const uint32_t (&w)[12], F&& f) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        f(4 * q + 0, byte_of(a, 0), byte_of(a, 1), byte_of(a, 2));
+        f(4 * q + 1, byte_of(a, 3), byte_of(b, 0), byte_of(b, 1));
+        f(4 * q + 2, byte_of(b, 2), byte_of(b, 3), byte_of(c, 0));
+        f(4 * q + 3, byte_of(c, 1), byte_of(c, 2), byte_of(c, 3));
+    }
+}
+
+// Packs four values (each already reduced to its low byte inside a 32-bit word) into one word.
+__device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+    return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+}
+
+// ------------------------------------------------------------------------------------------------ per-pixel math
+// 2-atom non-negative LASSO in closed form (oracle: lasso_pos2; reference call site stain_utils.py:78).
+struct LassoK {
+    float m00, m01, m02, m10, m11, m12;  // dictionary rows (stain vectors)
+    float lam;
+    float i00, i01, i11;                 // inverse Gram matrix
+    float rg00, rg11, g01;               // 1/G00, 1/G11, G01
+};
+
+__device__ __forceinline__ void lasso2(const LassoK& k, float o0, float o1, float o2, float& c0, float& c1) {
+    const float u0 = fmaf(k.m02, o2, fmaf(k.m01, o1, fmaf(k.m00, o0, -k.lam)));
+    const float u1 = fmaf(k.m12, o2, fmaf(k.m11, o1, fmaf(k.m10, o0, -k.lam)));
+    const float a0 = fmaf(k.i01, u1, k.i00 * u0);
+    const float a1 = fmaf(k.i11, u1, k.i01 * u0);
+    const bool both = (a0 > 0.f) & (a1 > 0.f);
+    const float p0 = fmaxf(u0, 0.f) * k.rg00, p1 = fmaxf(u1, 0.f) * k.rg11;
+    const bool only0 = (p0 > 0.f) & (fmaf(-k.g01, p0, u1) <= 0.f);
+    const bool only1 = (p1 > 0.f) & (fmaf(-k.g01, p1, u0) <= 0.f);
+    c0 = both ? a0 : (only0 ? p0 : 0.f);
+    c1 = both ? a1 : ((!only0 & only1) ? p1 : 0.f);
+}
+
+__host__ __device__ inline void make_lasso_consts(const double M[6], double lam, LassoK& k) {
+    const double g00 = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
+    const double g11 = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
+    const double g01 = M[0] * M[3] + M[1] * M[4] + M[2] * M[5];
+    const double det = g00 * g11 - g01 * g01;
+    k.m00 = (float)M[0]; k.m01 = (float)M[1]; k.m02 = (float)M[2];
+    k.m10 = (float)M[3]; k.m11 = (float)M[4]; k.m12 = (float)M[5];
+    k.lam = (float)lam;
+    k.i00 = (float)(g11 / det); k.i01 = (float)(-g01 / det); k.i11 = (float)(g00 / det);
+    k.rg00 = (float)(1.0 / g00); k.rg11 = (float)(1.0 / g11); k.g01 = (float)g01;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// uint8(x) exactly as numpy's astype(np.uint8) does on x86-64 for x >= 0: truncate via int32, keep the low byte;
+// out of int32 range / inf / NaN -> 0 (normalizer.py:50 does not clip).  Returns a word whose LOW BYTE is the value.
+__device__ __forceinline__ uint32_t wrap_u8_bits(float x) {
+    if (x < 8388608.f) return __float_as_uint(__fadd_rd(x, 8388608.f));  // mantissa = floor(x); low byte = floor(x) & 255
+    if (x < 2147483648.f) return (uint32_t)__float2int_rz(x);
+    return 0u;
+}
+// uint8(clip(x, 0, 255)) for x >= 0 or NaN (augmenter.py:447).
+__device__ __forceinline__ uint32_t clip_u8_bits(float x) {
+    return __float_as_uint(__fadd_rd(fminf(x, 255.f), 8388608.f));
+}
+
+// ------------------------------------------------------------------------------------------------ selection keys
+// Monotone 23-bit key of the angle atan2(y, x): the "diamond angle" d in [-2,2] mapped to t = d/4 + 1.5 in [1,2];
+// key = mantissa bits of t.  Exact order statistics of the key give the order statistics of the angle.
+__device__ __forceinline__ uint32_t angle_key(float x, float y) {
+    const float s = fabsf(x) + fabsf(y);
+    float r = y * rcp_approx(s);
+    if (!(s > 0.f)) r = 0.f;
+    const float d = (x >= 0.f) ? r : ((y >= 0.f) ? 2.f - r : -2.f - r);
+    const float t = fmaf(d, 0.25f, 1.5f);
+    const uint32_t k = __float_as_uint(t) - 0x3F800000u;
+    return min(k, (1u << KEY_BITS) - 1u);
+}
+__device__ inline double angle_from_key(uint32_t key) {
+    const double t = 1.0 + (double)key * (1.0 / 8388608.0);
+    const double d = (t - 1.5) * 4.0;
+    if (d > 1.0) return atan2(2.0 - d, -(d - 1.0));
+    if (d < -1.0) return atan2(-2.0 - d, -(-1.0 - d));
+    return atan2(d, 1.0 - fabs(d));
+}
+// Monotone 23-bit key of a concentration C >= 0: t = 2 - K/(C+K).
+__device__ __forceinline__ uint32_t conc_key(float c) {
+    const float t = fmaf(-CONC_KEY_K, rcp_approx(c + CONC_KEY_K), 2.f);
+    const uint32_t k = __float_as_uint(t) - 0x3F800000u;
+    return (c > 0.f) ? min(k, (1u << KEY_BITS) - 1u) : 0u;
+}
+__device__ inline double conc_from_key(uint32_t key) {
+    if (key == 0) return 0.0;
+    const double t = 1.0 + (double)key * (1.0 / 8388608.0);
+    return (double)CONC_KEY_K * (t - 1.0) / (2.0 - t);
+}
+
+// numpy.percentile (linear): virtual index (n-1)*q/100; returns lo index and the interpolation weight.
+__device__ inline void percentile_index(unsigned n, double pct, unsigned& lo, unsigned& hi, double& frac) {
+    const double vi = (double)(n - 1) * (pct / 100.0);
+    double fl = floor(vi);
+    if (fl < 0) fl = 0;
+    if (fl > (double)(n - 1)) fl = (double)(n - 1);
+    lo = (unsigned)fl;
+    hi = min(lo + 1u, n - 1u);
+    frac = vi - fl;
+}
+__device__ inline double lerp_np(double a, double b, double t) {
+    // numpy's _lerp: a + (b-a)*t, computed from the far end when t >= 0.5
+    const double d = b - a;
+    return t >= 0.5 ? b - d * (1.0 - t) : a + d * t;
+}
+
+// ------------------------------------------------------------------------------------------------ 3x3 symmetric eig
+// Cyclic Jacobi in fp64 (single thread).  a = {a00,a01,a02,a11,a12,a22}.  Outputs eigenvalues w[3] (unsorted) and
+// eigenvectors as columns of v[3][3] (v[r][c]).
+__device__ inline void jacobi_eig3(const double a_in[6], double w[3], double v[3][3]) {
+    double a[3][3] = {{a_in[0], a_in[1], a_in[2]}, {a_in[1], a_in[3], a_in[4]}, {a_in[2], a_in[4], a_in[5]}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        const double diag = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]);
+        if (off <= 1e-300 || off <= 1e-22 * diag) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                const double apq = a[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                const int r = 3 - p - q;
+                const double app = a[p][p], aqq = a[q][q], arp = a[r][p], arq = a[r][q];
+                a[p][p] = app - t * apq;
+                a[q][q] = aqq + t * apq;
+                a[p][q] = a[q][p] = 0.0;
+                a[r][p] = a[p][r] = c * arp - s * arq;
+                a[r][q] = a[q][r] = s * arp + c * arq;
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = c * vkp - s * vkq;
+                    v[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    w[0] = a[0][0]; w[1] = a[1][1]; w[2] = a[2][2];
+}
+
+// ------------------------------------------------------------------------------------------------ block reductions
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ unsigned warp_incl_scan(unsigned x) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    return x;
+}
+
+}  // namespace sb

@@ -1,0 +1,51 @@
+// sb_kernels.h -- internal interface between the C-ABI layer (sb_api.cu) and the kernel translation units.
+#pragma once
+#include "sb_device.cuh"
+#include "../../include/stainb200.h"
+
+namespace sb {
+
+enum PipeMode { PIPE_EXTRACT = 0, PIPE_FIT = 1, PIPE_NORMALIZE = 2 };
+
+struct PipeArgs {
+    const uint8_t* in;
+    uint8_t* out;
+    int B, npx;
+    int aligned;          // tile base addresses and tile size are multiples of 16 bytes
+    Tables tab;
+    int mode, method, cluster_size;
+    float ybound;         // tissue <=> sum_c gy[c][v_c] < ybound
+    double ang_pct, lasso_lambda, conc_pct, dl_lambda;
+    int dl_iters;
+    const double* Mt;     // [2,3] device
+    const double* maxCt;  // [2]   device
+    double* M_out;        // [B,2,3] or null
+    double* maxC_out;     // [B,2] or null
+    int32_t* status;      // [B] or null
+};
+
+int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream);
+
+// ---- pointwise kernels (sb_pointwise.cu)
+struct PointArgs {
+    const uint8_t* in;
+    uint8_t* out;
+    int B, npx, aligned;
+    Tables tab;
+    float ybound;
+    const double* M;       // [B,2,3] per-tile source matrices
+    const double* scale;   // [B,2]   (recombine)  /  alpha (augment)
+    const double* beta;    // [B,2]   (augment)
+    const double* Mt;      // [2,3]   (recombine)
+    double lasso_lambda;
+    int augment_background;
+    float* conc_out;       // [B,N,2] (concentrations)
+    uint8_t* mask_out;     // [B,N]   (mask)
+    int32_t* status;
+};
+int launch_mask(const PointArgs& a, int num_sms, cudaStream_t stream);
+int launch_recombine(const PointArgs& a, int num_sms, cudaStream_t stream);
+int launch_stain_augment(const PointArgs& a, int num_sms, cudaStream_t stream);
+int launch_concentrations(const PointArgs& a, int num_sms, cudaStream_t stream);
+
+}  // namespace sb

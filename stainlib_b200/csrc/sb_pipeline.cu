@@ -1,0 +1,569 @@
+// sb_pipeline.cu -- fused per-tile stain pipeline for sm_100a.
+//
+// One thread-block cluster (1, 2, 4 or 8 CTAs) owns one tile and runs the whole dependency chain of
+//   ExtractiveStainNormalizer.transform  (stainlib/normalization/normalizer.py:39-50)
+// on it without leaving the kernel; clusters are persistent and stride over the batch:
+//
+//   Macenko (macenko_stain_extractor.py:7-44)
+//     A   tissue mask + masked OD moments (n, sum od, sum od x od)      -> 3x3 covariance, fp64 Jacobi eigenvectors
+//     B1  angle keys of tissue pixels -> 4096-bin histogram              -> bins holding the two angular percentiles
+//     B2  11-bit refinement inside those bins                             -> exact order statistics -> stain matrix
+//   Vahadane (vahadane_stain_extractor.py:19-43; spams.trainDL restated as deterministic full-batch learning)
+//     V x T  sparse-code tissue pixels with the current dictionary, accumulate A = sum aa^T, B = sum xa^T, update D
+//   common (stain_utils.py:69-78, normalizer.py:46-50)
+//     C1  closed-form non-negative LASSO concentrations of ALL pixels -> two 4096-bin histograms
+//     C2  11-bit refinement                                              -> exact 99th percentiles (maxC)
+//     D   recombine with the target matrix, 255*exp(.), unclipped uint8 wrap, 16-byte stores
+//
+// Every pass re-reads the tile with 16-byte vector loads; the working set of all in-flight tiles is sized to stay in
+// the 126 MB L2 (cluster size is chosen by the host), so HBM sees ~3 B/px in and 3 B/px out.  Cross-CTA reductions
+// (moments, histograms) go through distributed shared memory; every CTA of a cluster redundantly evaluates the small
+// serial steps (eigenvectors, selections) so no broadcast is needed and results are bit-identical.
+#include "sb_kernels.h"
+
+namespace sb {
+
+struct __align__(16) PipeShared {
+    unsigned hist[2 * L1_BINS];      // 32 KB: 2 x 4096 (level 1) or 4 x 2048 (level 2)
+    float od[256];
+    float gy[3 * 256];
+    double red[NWARP][10];
+    double part[2][12];              // this CTA's partial sums (double-buffered; read by cluster peers)
+    double tot[12];
+    unsigned wtot[NWARP];
+    unsigned q_rank[4], q_bin[4], q_rem[4], q_key[4], q_hist[4], q_tmp[4];
+    unsigned d_bin[4], d_src[4];     // distinct level-2 histograms: level-1 bin and key source (0/1)
+    int n_distinct;
+    float V[6];
+    LassoK lk;
+    float A[6];
+    float need_check;
+    int flags;
+    double D[6];                     // Vahadane dictionary, rows = atoms
+    double Msrc[6];
+    double maxC[2];
+};
+
+__device__ __forceinline__ void tile_sync(int S) {
+    if (S > 1) cg::this_cluster().sync(); else __syncthreads();
+}
+
+// Sums 9 doubles + a count over the block (fixed order) into sh->part[buf].
+__device__ __forceinline__ void block_reduce10(PipeShared* sh, int buf, double (&acc)[9], unsigned cnt) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc[i] = warp_sum(acc[i]);
+    double c = warp_sum((double)cnt);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sh->red[warp][i] = acc[i];
+        sh->red[warp][9] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        double s = 0.0;
+        for (int w = 0; w < NWARP; ++w) s += sh->red[w][threadIdx.x];
+        sh->part[buf][threadIdx.x] = s;
+    }
+}
+
+// After tile_sync: every CTA sums the partials of all cluster ranks in rank order -> sh->tot (identical everywhere).
+__device__ __forceinline__ void cluster_total10(PipeShared* sh, int buf, int S) {
+    if (threadIdx.x < 10) {
+        double s = 0.0;
+        if (S > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            for (int r = 0; r < S; ++r) s += cluster.map_shared_rank(&sh->part[buf][0], r)[threadIdx.x];
+        } else {
+            s = sh->part[buf][threadIdx.x];
+        }
+        sh->tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// Finds, for nq target ranks, the bin of the (cluster-wide) histogram that contains each rank and the rank inside it.
+template <int NB>
+__device__ __forceinline__ void select_ranks(PipeShared* sh, const unsigned* hist, int S, const unsigned* ranks, int nq,
+                                             unsigned* out_bin, unsigned* out_rem) {
+    constexpr int PER = NB / NT;
+    static_assert(PER == 4 || PER == 8, "bins per thread");
+    unsigned v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) v[i] = 0;
+    for (int r = 0; r < S; ++r) {
+        const unsigned* hs = hist;
+        if (S > 1) hs = cg::this_cluster().map_shared_rank(hist, r);
+        const uint4* p = reinterpret_cast<const uint4*>(hs + threadIdx.x * PER);
+#pragma unroll
+        for (int i = 0; i < PER / 4; ++i) {
+            uint4 x = p[i];
+            v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+        }
+    }
+    unsigned sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) sum += v[i];
+    const unsigned incl = warp_incl_scan(sum);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 31) sh->wtot[warp] = incl;
+    __syncthreads();
+    unsigned base = 0;
+    for (int w = 0; w < warp; ++w) base += sh->wtot[w];
+    const unsigned excl = base + incl - sum;
+    for (int q = 0; q < nq; ++q) {
+        const unsigned r = ranks[q];
+        if (r >= excl && r < excl + sum) {
+            unsigned c = excl;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                if (r >= c && r < c + v[i]) { out_bin[q] = threadIdx.x * PER + i; out_rem[q] = r - c; }
+                c += v[i];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void zero_hist(PipeShared* sh) {
+    uint4* h = reinterpret_cast<uint4*>(sh->hist);
+    for (int i = threadIdx.x; i < 2 * L1_BINS / 4; i += NT) h[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+}
+
+// Level-2 bookkeeping (thread 0): queries q (level-1 bin q_bin[q], key source src[q]) -> distinct histograms.
+__device__ inline void plan_level2(PipeShared* sh, const unsigned src[4]) {
+    int nd = 0;
+    for (int q = 0; q < 4; ++q) {
+        int found = -1;
+        for (int d = 0; d < nd; ++d)
+            if (sh->d_bin[d] == sh->q_bin[q] && sh->d_src[d] == src[q]) found = d;
+        if (found < 0) { found = nd; sh->d_bin[nd] = sh->q_bin[q]; sh->d_src[nd] = src[q]; ++nd; }
+        sh->q_hist[q] = found;
+    }
+    sh->n_distinct = nd;
+}
+
+// Runs f over this CTA's share of the tile.  f(w, nvalid, g) sees the raw 12 words of one 16-pixel group.
+template <class F>
+__device__ __forceinline__ void for_each_group(const uint8_t* __restrict__ tile, int npx, int gb, int ge, bool aligned, F&& f) {
+    for (int g = gb + threadIdx.x; g < ge; g += NT) {
+        uint32_t w[12];
+        int nvalid;
+        load_group<true>(tile, npx, g, aligned, w, nvalid);
+        f(w, nvalid, g);
+    }
+}
+
+__global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PipeShared* sh = reinterpret_cast<PipeShared*>(smem_raw);
+    const int S = a.cluster_size;
+    const int crank = S > 1 ? (int)cg::this_cluster().block_rank() : 0;
+    const int cluster_id = blockIdx.x / S, n_clusters = gridDim.x / S;
+    const int npx = a.npx;
+    const int G = (npx + GROUP_PX - 1) / GROUP_PX;
+    const int gb = (int)(((long long)G * crank) / S), ge = (int)(((long long)G * (crank + 1)) / S);
+    const size_t tile_bytes = (size_t)npx * 3;
+    const bool aligned = a.aligned != 0;
+    const float ybound = a.ybound;
+
+    for (int i = threadIdx.x; i < 256; i += NT) sh->od[i] = a.tab.od[i];
+    for (int i = threadIdx.x; i < 768; i += NT) sh->gy[i] = a.tab.gy[i];
+    __syncthreads();
+    const float* od = sh->od;
+    const float* gyR = sh->gy, *gyG = sh->gy + 256, *gyB = sh->gy + 512;
+    int pbuf = 0;   // parity of sh->part
+
+    for (int tile = cluster_id; tile < a.B; tile += n_clusters) {
+        const uint8_t* __restrict__ tin = a.in + (size_t)tile * tile_bytes;
+        unsigned n_tissue = 0;
+        if (threadIdx.x == 0) { sh->flags = 0; }
+
+        if (a.method == SB_METHOD_MACENKO) {
+            // ------------------------------------------------------------------ A: mask + moments
+            double acc[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+            unsigned cnt = 0;
+            for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
+                float f[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) f[i] = 0.f;
+                for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
+                    const float y = gyR[r] + gyG[g] + gyB[b];
+                    const bool m = (y < ybound) & (i < nvalid);
+                    const float o0 = m ? od[r] : 0.f, o1 = m ? od[g] : 0.f, o2 = m ? od[b] : 0.f;
+                    cnt += m ? 1u : 0u;
+                    f[0] += o0; f[1] += o1; f[2] += o2;
+                    f[3] = fmaf(o0, o0, f[3]); f[4] = fmaf(o0, o1, f[4]); f[5] = fmaf(o0, o2, f[5]);
+                    f[6] = fmaf(o1, o1, f[6]); f[7] = fmaf(o1, o2, f[7]); f[8] = fmaf(o2, o2, f[8]);
+                });
+#pragma unroll
+                for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
+            });
+            block_reduce10(sh, pbuf, acc, cnt);
+            tile_sync(S);
+            cluster_total10(sh, pbuf, S);
+            pbuf ^= 1;
+            n_tissue = (unsigned)sh->tot[9];
+            if (threadIdx.x == 0) {
+                const double n = sh->tot[9];
+                int flags = 0;
+                if (n < 1.0) flags |= SB_STATUS_EMPTY_MASK;
+                else if (n < 2.0) flags |= SB_STATUS_FEW_TISSUE;
+                if (!flags) {
+                    const double* t = sh->tot;
+                    const double inv = 1.0 / (n - 1.0);
+                    double c[6];
+                    c[0] = (t[3] - t[0] * t[0] / n) * inv; c[1] = (t[4] - t[0] * t[1] / n) * inv; c[2] = (t[5] - t[0] * t[2] / n) * inv;
+                    c[3] = (t[6] - t[1] * t[1] / n) * inv; c[4] = (t[7] - t[1] * t[2] / n) * inv; c[5] = (t[8] - t[2] * t[2] / n) * inv;
+                    double wv[3], v[3][3];
+                    jacobi_eig3(c, wv, v);
+                    int i1 = 0;
+                    if (wv[1] > wv[i1]) i1 = 1;
+                    if (wv[2] > wv[i1]) i1 = 2;
+                    int i2 = -1;
+                    for (int k = 0; k < 3; ++k) if (k != i1 && (i2 < 0 || wv[k] > wv[i2])) i2 = k;
+                    const double s1 = v[0][i1] < 0 ? -1.0 : 1.0, s2 = v[0][i2] < 0 ? -1.0 : 1.0;
+                    bool ok = true;
+                    for (int k = 0; k < 3; ++k) {
+                        const double x1 = s1 * v[k][i1], x2 = s2 * v[k][i2];
+                        sh->V[k] = (float)x1; sh->V[3 + k] = (float)x2;
+                        sh->D[k] = x1; sh->D[3 + k] = x2;        // keep the fp64 eigenvectors
+                        ok = ok && isfinite(x1) && isfinite(x2);
+                    }
+                    if (!ok) flags |= SB_STATUS_DEGENERATE;
+                }
+                sh->flags = flags;
+            }
+            __syncthreads();
+            if (sh->flags == 0) {
+                // -------------------------------------------------------------- B1: angle histogram (tissue pixels)
+                zero_hist(sh);
+                const float v00 = sh->V[0], v01 = sh->V[1], v02 = sh->V[2], v10 = sh->V[3], v11 = sh->V[4], v12 = sh->V[5];
+                for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
+                    for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
+                        const float y = gyR[r] + gyG[g] + gyB[b];
+                        const bool m = (y < ybound) & (i < nvalid);
+                        const float o0 = od[r], o1 = od[g], o2 = od[b];
+                        const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
+                        const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
+                        const uint32_t key = angle_key(px, py);
+                        if (m) atomicAdd(&sh->hist[key >> L2_BITS], 1u);
+                    });
+                });
+                if (threadIdx.x == 0) {
+                    unsigned lo, hi; double fr;
+                    percentile_index(n_tissue, 100.0 - a.ang_pct, lo, hi, fr);
+                    sh->q_rank[0] = lo; sh->q_rank[1] = hi;
+                    percentile_index(n_tissue, a.ang_pct, lo, hi, fr);
+                    sh->q_rank[2] = lo; sh->q_rank[3] = hi;
+                    for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
+                }
+                __syncthreads();
+                tile_sync(S);
+                select_ranks<L1_BINS>(sh, sh->hist, S, sh->q_rank, 4, sh->q_bin, sh->q_rem);
+                if (threadIdx.x == 0) { const unsigned src[4] = {0, 0, 0, 0}; plan_level2(sh, src); }
+                tile_sync(S);
+                // -------------------------------------------------------------- B2: 11-bit refinement
+                zero_hist(sh);
+                {
+                    const int nd = sh->n_distinct;
+                    const unsigned b0 = sh->d_bin[0], b1 = sh->d_bin[1], b2 = sh->d_bin[2], b3 = sh->d_bin[3];
+                    for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
+                        for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
+                            const float y = gyR[r] + gyG[g] + gyB[b];
+                            const bool m = (y < ybound) & (i < nvalid);
+                            const float o0 = od[r], o1 = od[g], o2 = od[b];
+                            const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
+                            const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
+                            const uint32_t key = angle_key(px, py);
+                            const uint32_t bin = key >> L2_BITS, low = key & (L2_BINS - 1);
+                            if (m) {
+                                if (bin == b0) atomicAdd(&sh->hist[low], 1u);
+                                if (nd > 1 && bin == b1) atomicAdd(&sh->hist[L2_BINS + low], 1u);
+                                if (nd > 2 && bin == b2) atomicAdd(&sh->hist[2 * L2_BINS + low], 1u);
+                                if (nd > 3 && bin == b3) atomicAdd(&sh->hist[3 * L2_BINS + low], 1u);
+                            }
+                        });
+                    });
+                }
+                __syncthreads();
+                tile_sync(S);
+                for (int q = 0; q < 4; ++q)
+                    select_ranks<L2_BINS>(sh, sh->hist + sh->q_hist[q] * L2_BINS, S, &sh->q_rem[q], 1, &sh->q_key[q], &sh->q_tmp[q]);
+                if (threadIdx.x == 0) {
+                    double ang[4];
+                    for (int q = 0; q < 4; ++q) ang[q] = angle_from_key((sh->q_bin[q] << L2_BITS) | sh->q_key[q]);
+                    unsigned lo, hi; double fr_lo, fr_hi;
+                    percentile_index(n_tissue, 100.0 - a.ang_pct, lo, hi, fr_lo);
+                    percentile_index(n_tissue, a.ang_pct, lo, hi, fr_hi);
+                    const double min_phi = lerp_np(ang[0], ang[1], fr_lo), max_phi = lerp_np(ang[2], ang[3], fr_hi);
+                    const double c1 = cos(min_phi), s1 = sin(min_phi), c2 = cos(max_phi), s2 = sin(max_phi);
+                    double v1[3], v2[3];
+                    for (int k = 0; k < 3; ++k) {
+                        v1[k] = sh->D[k] * c1 + sh->D[3 + k] * s1;
+                        v2[k] = sh->D[k] * c2 + sh->D[3 + k] * s2;
+                    }
+                    const bool first = v1[0] > v2[0];
+                    const double* h = first ? v1 : v2;
+                    const double* e = first ? v2 : v1;
+                    const double nh = sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]), ne = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+                    bool ok = true;
+                    for (int k = 0; k < 3; ++k) {
+                        sh->Msrc[k] = h[k] / nh; sh->Msrc[3 + k] = e[k] / ne;
+                        ok = ok && isfinite(sh->Msrc[k]) && isfinite(sh->Msrc[3 + k]);
+                    }
+                    if (!ok) sh->flags |= SB_STATUS_DEGENERATE;
+                }
+                tile_sync(S);
+            }
+        } else {
+            // ------------------------------------------------------------------ Vahadane: full-batch dictionary learning
+            if (threadIdx.x == 0) {
+                const double r0[3] = {0.65, 0.70, 0.29}, r1[3] = {0.07, 0.99, 0.11};
+                const double n0 = sqrt(r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]), n1 = sqrt(r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
+                for (int k = 0; k < 3; ++k) { sh->D[k] = r0[k] / n0; sh->D[3 + k] = r1[k] / n1; }
+                make_lasso_consts(sh->D, a.dl_lambda, sh->lk);
+            }
+            __syncthreads();
+            for (int it = 0; it < a.dl_iters; ++it) {
+                const LassoK lk = sh->lk;
+                double acc[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+                unsigned cnt = 0;
+                for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
+                    float f[9];
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) f[i] = 0.f;
+                    for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
+                        const float y = gyR[r] + gyG[g] + gyB[b];
+                        const bool m = (y < ybound) & (i < nvalid);
+                        const float o0 = od[r], o1 = od[g], o2 = od[b];
+                        float c0, c1;
+                        lasso2(lk, o0, o1, o2, c0, c1);
+                        c0 = m ? c0 : 0.f; c1 = m ? c1 : 0.f;
+                        cnt += m ? 1u : 0u;
+                        f[0] = fmaf(c0, c0, f[0]); f[1] = fmaf(c0, c1, f[1]); f[2] = fmaf(c1, c1, f[2]);
+                        f[3] = fmaf(o0, c0, f[3]); f[4] = fmaf(o1, c0, f[4]); f[5] = fmaf(o2, c0, f[5]);
+                        f[6] = fmaf(o0, c1, f[6]); f[7] = fmaf(o1, c1, f[7]); f[8] = fmaf(o2, c1, f[8]);
+                    });
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
+                });
+                block_reduce10(sh, pbuf, acc, cnt);
+                tile_sync(S);
+                cluster_total10(sh, pbuf, S);
+                pbuf ^= 1;
+                n_tissue = (unsigned)sh->tot[9];
+                if (threadIdx.x == 0) {
+                    const double* t = sh->tot;
+                    if (t[9] < 1.0) sh->flags |= SB_STATUS_EMPTY_MASK;
+                    // Mairal et al. 2010 Alg. 2, one block-coordinate sweep; D rows = atoms.
+                    const double Aj[2][2] = {{t[0], t[1]}, {t[1], t[2]}};
+                    for (int j = 0; j < 2; ++j) {
+                        if (Aj[j][j] > 1e-12) {
+                            double u[3], nrm = 0.0;
+                            for (int k = 0; k < 3; ++k) {
+                                const double Da = sh->D[k] * Aj[0][j] + sh->D[3 + k] * Aj[1][j];
+                                u[k] = (t[3 + 3 * j + k] - Da) / Aj[j][j] + sh->D[3 * j + k];
+                                u[k] = u[k] > 0.0 ? u[k] : 0.0;
+                                nrm += u[k] * u[k];
+                            }
+                            nrm = sqrt(nrm);
+                            const double sc = 1.0 / (nrm > 1.0 ? nrm : 1.0);
+                            for (int k = 0; k < 3; ++k) sh->D[3 * j + k] = u[k] * sc;
+                        }
+                    }
+                    make_lasso_consts(sh->D, a.dl_lambda, sh->lk);
+                }
+                __syncthreads();
+                if (sh->flags) break;
+            }
+            if (threadIdx.x == 0 && sh->flags == 0) {
+                // vahadane_stain_extractor.py:38-43: H first, rows normalised
+                const bool swap = sh->D[0] < sh->D[3];
+                const double* h = swap ? sh->D + 3 : sh->D;
+                const double* e = swap ? sh->D : sh->D + 3;
+                const double nh = sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]), ne = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+                double m[6];
+                bool ok = true;
+                for (int k = 0; k < 3; ++k) { m[k] = h[k] / nh; m[3 + k] = e[k] / ne; ok = ok && isfinite(m[k]) && isfinite(m[3 + k]); }
+                for (int k = 0; k < 6; ++k) sh->Msrc[k] = m[k];
+                if (!ok) sh->flags |= SB_STATUS_DEGENERATE;
+            }
+            tile_sync(S);
+        }
+
+        // stain matrix out
+        if (threadIdx.x == 0 && crank == 0 && a.M_out) {
+            for (int k = 0; k < 6; ++k) a.M_out[(size_t)tile * 6 + k] = sh->flags ? __longlong_as_double(0x7ff8000000000000LL) : sh->Msrc[k];
+        }
+
+        if (a.mode >= PIPE_FIT && sh->flags == 0) {
+            // ------------------------------------------------------------------ C1: concentration histograms (all pixels)
+            if (threadIdx.x == 0) make_lasso_consts(sh->Msrc, a.lasso_lambda, sh->lk);
+            zero_hist(sh);
+            const LassoK lk = sh->lk;
+            for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
+                for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
+                    float c0, c1;
+                    lasso2(lk, od[r], od[g], od[b], c0, c1);
+                    if (i < nvalid) {
+                        atomicAdd(&sh->hist[conc_key(c0) >> L2_BITS], 1u);
+                        atomicAdd(&sh->hist[L1_BINS + (conc_key(c1) >> L2_BITS)], 1u);
+                    }
+                });
+            });
+            if (threadIdx.x == 0) {
+                unsigned lo, hi; double fr;
+                percentile_index((unsigned)npx, a.conc_pct, lo, hi, fr);
+                sh->q_rank[0] = lo; sh->q_rank[1] = hi; sh->q_rank[2] = lo; sh->q_rank[3] = hi;
+                for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
+            }
+            __syncthreads();
+            tile_sync(S);
+            select_ranks<L1_BINS>(sh, sh->hist, S, sh->q_rank, 2, sh->q_bin, sh->q_rem);
+            select_ranks<L1_BINS>(sh, sh->hist + L1_BINS, S, sh->q_rank + 2, 2, sh->q_bin + 2, sh->q_rem + 2);
+            if (threadIdx.x == 0) { const unsigned src[4] = {0, 0, 1, 1}; plan_level2(sh, src); }
+            tile_sync(S);
+            // ------------------------------------------------------------------ C2: refinement
+            zero_hist(sh);
+            {
+                const int nd = sh->n_distinct;
+                const unsigned b0 = sh->d_bin[0], b1 = sh->d_bin[1], b2 = sh->d_bin[2], b3 = sh->d_bin[3];
+                const unsigned s0 = sh->d_src[0], s1 = sh->d_src[1], s2 = sh->d_src[2], s3 = sh->d_src[3];
+                for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
+                    for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
+                        float c0, c1;
+                        lasso2(lk, od[r], od[g], od[b], c0, c1);
+                        const uint32_t k0 = conc_key(c0), k1 = conc_key(c1);
+                        if (i < nvalid) {
+                            { const uint32_t k = s0 ? k1 : k0; if ((k >> L2_BITS) == b0) atomicAdd(&sh->hist[k & (L2_BINS - 1)], 1u); }
+                            if (nd > 1) { const uint32_t k = s1 ? k1 : k0; if ((k >> L2_BITS) == b1) atomicAdd(&sh->hist[L2_BINS + (k & (L2_BINS - 1))], 1u); }
+                            if (nd > 2) { const uint32_t k = s2 ? k1 : k0; if ((k >> L2_BITS) == b2) atomicAdd(&sh->hist[2 * L2_BINS + (k & (L2_BINS - 1))], 1u); }
+                            if (nd > 3) { const uint32_t k = s3 ? k1 : k0; if ((k >> L2_BITS) == b3) atomicAdd(&sh->hist[3 * L2_BINS + (k & (L2_BINS - 1))], 1u); }
+                        }
+                    });
+                });
+            }
+            __syncthreads();
+            tile_sync(S);
+            for (int q = 0; q < 4; ++q)
+                select_ranks<L2_BINS>(sh, sh->hist + sh->q_hist[q] * L2_BINS, S, &sh->q_rem[q], 1, &sh->q_key[q], &sh->q_tmp[q]);
+            if (threadIdx.x == 0) {
+                double cv[4];
+                for (int q = 0; q < 4; ++q) cv[q] = conc_from_key((sh->q_bin[q] << L2_BITS) | sh->q_key[q]);
+                unsigned lo, hi; double fr;
+                percentile_index((unsigned)npx, a.conc_pct, lo, hi, fr);
+                sh->maxC[0] = lerp_np(cv[0], cv[1], fr);
+                sh->maxC[1] = lerp_np(cv[2], cv[3], fr);
+                if (crank == 0 && a.maxC_out) { a.maxC_out[(size_t)tile * 2] = sh->maxC[0]; a.maxC_out[(size_t)tile * 2 + 1] = sh->maxC[1]; }
+            }
+            tile_sync(S);
+        } else if (a.mode >= PIPE_FIT && threadIdx.x == 0 && crank == 0 && a.maxC_out) {
+            a.maxC_out[(size_t)tile * 2] = a.maxC_out[(size_t)tile * 2 + 1] = __longlong_as_double(0x7ff8000000000000LL);
+        }
+
+        if (a.mode == PIPE_NORMALIZE) {
+            // ------------------------------------------------------------------ D: recombine + store
+            uint8_t* __restrict__ tout = a.out + (size_t)tile * tile_bytes;
+            if (threadIdx.x == 0 && sh->flags == 0) {
+                const double LOG2E = 1.4426950408889634;
+                float need = 0.f;
+                bool finite = true;
+                for (int j = 0; j < 2; ++j) {
+                    const double s = a.maxCt[j] / sh->maxC[j];
+                    finite = finite && isfinite(s);
+                    for (int k = 0; k < 3; ++k) {
+                        const double v = -s * a.Mt[3 * j + k] * LOG2E;
+                        sh->A[3 * j + k] = (float)v;
+                        if (v > 0.0) need = 1.f;
+                    }
+                }
+                sh->need_check = need;
+                if (!finite) sh->flags |= SB_STATUS_ZERO_MAXC;
+            }
+            __syncthreads();
+            const int flags = sh->flags;
+            if (flags == 0) {
+                const LassoK lk = sh->lk;
+                const float a00 = sh->A[0], a01 = sh->A[1], a02 = sh->A[2], a10 = sh->A[3], a11 = sh->A[4], a12 = sh->A[5];
+                const float L255 = 7.994353436858858f;  // log2(255)
+                for (int g = gb + threadIdx.x; g < ge; g += NT) {
+                    uint32_t w[12], o[12];
+                    int nvalid;
+                    load_group<false>(tin, npx, g, aligned, w, nvalid);
+                    uint32_t bits[12];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
+                        const uint32_t rr[4] = {byte_of(wa, 0), byte_of(wa, 3), byte_of(wb, 2), byte_of(wc, 1)};
+                        const uint32_t gg[4] = {byte_of(wa, 1), byte_of(wb, 0), byte_of(wb, 3), byte_of(wc, 2)};
+                        const uint32_t bb[4] = {byte_of(wa, 2), byte_of(wb, 1), byte_of(wc, 0), byte_of(wc, 3)};
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            float c0, c1;
+                            lasso2(lk, od[rr[p]], od[gg[p]], od[bb[p]], c0, c1);
+                            const float e0 = fmaf(c1, a10, fmaf(c0, a00, L255));
+                            const float e1 = fmaf(c1, a11, fmaf(c0, a01, L255));
+                            const float e2 = fmaf(c1, a12, fmaf(c0, a02, L255));
+                            bits[3 * p] = wrap_u8_bits(ex2_approx(e0));
+                            bits[3 * p + 1] = wrap_u8_bits(ex2_approx(e1));
+                            bits[3 * p + 2] = wrap_u8_bits(ex2_approx(e2));
+                        }
+                        o[3 * q] = pack4(bits[0], bits[1], bits[2], bits[3]);
+                        o[3 * q + 1] = pack4(bits[4], bits[5], bits[6], bits[7]);
+                        o[3 * q + 2] = pack4(bits[8], bits[9], bits[10], bits[11]);
+                    }
+                    store_group(tout, npx, g, aligned, o);
+                }
+            } else {
+                // flagged tile: zeros where the reference divides by zero, otherwise the input is passed through
+                const bool zeros = (flags & SB_STATUS_ZERO_MAXC) != 0 && (flags & ~SB_STATUS_ZERO_MAXC) == 0;
+                for (int g = gb + threadIdx.x; g < ge; g += NT) {
+                    uint32_t w[12];
+                    int nvalid;
+                    load_group<false>(tin, npx, g, aligned, w, nvalid);
+                    if (zeros) {
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) w[i] = 0;
+                    }
+                    store_group(tout, npx, g, aligned, w);
+                }
+            }
+        }
+        if (threadIdx.x == 0 && crank == 0 && a.status) a.status[tile] = sh->flags;
+        tile_sync(S);   // protects sh->flags / histograms of the next tile from slow peers
+    }
+}
+
+int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(PipeShared);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tile_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int S = a.cluster_size;
+    int ctas_per_sm = 2;
+    int n_clusters = (num_sms * ctas_per_sm) / S;
+    if (n_clusters > a.B) n_clusters = a.B;
+    if (n_clusters < 1) n_clusters = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_clusters * S);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, tile_pipeline_kernel, a);
+}
+
+}  // namespace sb

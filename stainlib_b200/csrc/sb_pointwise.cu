@@ -1,0 +1,231 @@
+// sb_pointwise.cu -- per-pixel kernels that need no per-tile reduction (sm_100a).
+//
+//   mask_kernel            LuminosityThresholdTissueLocator.get_tissue_mask   stain_utils.py:32-48
+//   recombine_kernel (K4)  normalizer.py:46,48-50: OD LUT -> closed-form LASSO -> scale -> 2x3 mat-vec -> 255*exp -> u8
+//   stain_augment_kernel   StainAugmentor.pop                                  augmenter.py:428-449
+//   concentrations_kernel  get_concentrations                                  stain_utils.py:69-78
+//
+// Work unit = one 16-pixel group (48 B, three 16-byte vectors); a tile is a whole number of CTA-sized spans so the
+// per-tile constants are block-uniform.  grid = (spans_per_tile, B).
+#include "sb_kernels.h"
+
+namespace sb {
+
+constexpr int PT = 256;   // threads per CTA for the pointwise kernels
+
+struct __align__(16) PointShared {
+    float od[256];
+    float gy[768];
+    LassoK lk;
+    float A[6];
+    float alpha[2], beta[2];
+    int zero_out;
+};
+
+__device__ __forceinline__ void load_tables(PointShared* sh, const Tables& t, bool with_gy) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh->od[i] = t.od[i];
+    if (with_gy)
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) sh->gy[i] = t.gy[i];
+}
+
+__global__ void __launch_bounds__(PT) mask_kernel(PointArgs a) {
+    __shared__ PointShared sh;
+    load_tables(&sh, a.tab, true);
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    const int tile = blockIdx.x;
+    const uint8_t* tin = a.in + (size_t)tile * a.npx * 3;
+    uint8_t* mout = a.mask_out + (size_t)tile * a.npx;
+    const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
+    const float* gyR = sh.gy, *gyG = sh.gy + 256, *gyB = sh.gy + 512;
+    int found = 0;
+    for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < G; g += gridDim.y * blockDim.x) {
+        uint32_t w[12];
+        int nvalid;
+        load_group<false>(tin, a.npx, g, a.aligned != 0, w, nvalid);
+        uint32_t m[16];
+        for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
+            m[i] = (gyR[r] + gyG[gg] + gyB[b] < a.ybound) ? 1u : 0u;
+            found |= (i < nvalid) ? m[i] : 0u;
+        });
+        uint8_t* dst = mout + (size_t)g * GROUP_PX;
+        if (nvalid == GROUP_PX && (a.npx % 16) == 0) {
+            uint4 v;
+            v.x = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
+            v.y = m[4] | (m[5] << 8) | (m[6] << 16) | (m[7] << 24);
+            v.z = m[8] | (m[9] << 8) | (m[10] << 16) | (m[11] << 24);
+            v.w = m[12] | (m[13] << 8) | (m[14] << 16) | (m[15] << 24);
+            *reinterpret_cast<uint4*>(dst) = v;
+        } else {
+            for (int i = 0; i < nvalid; ++i) dst[i] = (uint8_t)m[i];
+        }
+    }
+    if (found) any = 1;
+    __syncthreads();
+    // status was preset to EMPTY_MASK by the host; any CTA that saw tissue clears it
+    if (threadIdx.x == 0 && any && a.status) atomicAnd(&a.status[tile], ~SB_STATUS_EMPTY_MASK);
+}
+
+__global__ void __launch_bounds__(PT, 4) recombine_kernel(PointArgs a) {
+    __shared__ PointShared sh;
+    load_tables(&sh, a.tab, false);
+    const int tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        double M[6];
+        for (int k = 0; k < 6; ++k) M[k] = a.M[(size_t)tile * 6 + k];
+        make_lasso_consts(M, a.lasso_lambda, sh.lk);
+        const double LOG2E = 1.4426950408889634;
+        bool finite = true;
+        for (int j = 0; j < 2; ++j) {
+            const double s = a.scale[(size_t)tile * 2 + j];
+            finite = finite && isfinite(s);
+            for (int k = 0; k < 3; ++k) sh.A[3 * j + k] = (float)(-s * a.Mt[3 * j + k] * LOG2E);
+        }
+        sh.zero_out = finite ? 0 : 1;
+    }
+    __syncthreads();
+    const uint8_t* tin = a.in + (size_t)tile * a.npx * 3;
+    uint8_t* tout = a.out + (size_t)tile * a.npx * 3;
+    const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
+    const LassoK lk = sh.lk;
+    const float a00 = sh.A[0], a01 = sh.A[1], a02 = sh.A[2], a10 = sh.A[3], a11 = sh.A[4], a12 = sh.A[5];
+    const float L255 = 7.994353436858858f;
+    const bool zero_out = sh.zero_out != 0;
+    const float* od = sh.od;
+    for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < G; g += gridDim.y * blockDim.x) {
+        uint32_t w[12], o[12];
+        int nvalid;
+        load_group<false>(tin, a.npx, g, a.aligned != 0, w, nvalid);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
+            const uint32_t rr[4] = {byte_of(wa, 0), byte_of(wa, 3), byte_of(wb, 2), byte_of(wc, 1)};
+            const uint32_t gg[4] = {byte_of(wa, 1), byte_of(wb, 0), byte_of(wb, 3), byte_of(wc, 2)};
+            const uint32_t bb[4] = {byte_of(wa, 2), byte_of(wb, 1), byte_of(wc, 0), byte_of(wc, 3)};
+            uint32_t bits[12];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                float c0, c1;
+                lasso2(lk, od[rr[p]], od[gg[p]], od[bb[p]], c0, c1);
+                bits[3 * p] = wrap_u8_bits(ex2_approx(fmaf(c1, a10, fmaf(c0, a00, L255))));
+                bits[3 * p + 1] = wrap_u8_bits(ex2_approx(fmaf(c1, a11, fmaf(c0, a01, L255))));
+                bits[3 * p + 2] = wrap_u8_bits(ex2_approx(fmaf(c1, a12, fmaf(c0, a02, L255))));
+            }
+            o[3 * q] = zero_out ? 0u : pack4(bits[0], bits[1], bits[2], bits[3]);
+            o[3 * q + 1] = zero_out ? 0u : pack4(bits[4], bits[5], bits[6], bits[7]);
+            o[3 * q + 2] = zero_out ? 0u : pack4(bits[8], bits[9], bits[10], bits[11]);
+        }
+        store_group(tout, a.npx, g, a.aligned != 0, o);
+    }
+}
+
+__global__ void __launch_bounds__(PT, 4) stain_augment_kernel(PointArgs a) {
+    __shared__ PointShared sh;
+    load_tables(&sh, a.tab, true);
+    const int tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        double M[6];
+        for (int k = 0; k < 6; ++k) M[k] = a.M[(size_t)tile * 6 + k];
+        make_lasso_consts(M, a.lasso_lambda, sh.lk);
+        const double LOG2E = 1.4426950408889634;
+        for (int k = 0; k < 6; ++k) sh.A[k] = (float)(-M[k] * LOG2E);
+        for (int j = 0; j < 2; ++j) { sh.alpha[j] = (float)a.scale[(size_t)tile * 2 + j]; sh.beta[j] = (float)a.beta[(size_t)tile * 2 + j]; }
+    }
+    __syncthreads();
+    const uint8_t* tin = a.in + (size_t)tile * a.npx * 3;
+    uint8_t* tout = a.out + (size_t)tile * a.npx * 3;
+    const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
+    const LassoK lk = sh.lk;
+    const float a00 = sh.A[0], a01 = sh.A[1], a02 = sh.A[2], a10 = sh.A[3], a11 = sh.A[4], a12 = sh.A[5];
+    const float al0 = sh.alpha[0], al1 = sh.alpha[1], be0 = sh.beta[0], be1 = sh.beta[1];
+    const float L255 = 7.994353436858858f;
+    const bool all_px = a.augment_background != 0;
+    const float ybound = a.ybound;
+    const float* od = sh.od;
+    const float* gyR = sh.gy, *gyG = sh.gy + 256, *gyB = sh.gy + 512;
+    for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < G; g += gridDim.y * blockDim.x) {
+        uint32_t w[12], o[12];
+        int nvalid;
+        load_group<false>(tin, a.npx, g, a.aligned != 0, w, nvalid);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
+            const uint32_t rr[4] = {byte_of(wa, 0), byte_of(wa, 3), byte_of(wb, 2), byte_of(wc, 1)};
+            const uint32_t gg[4] = {byte_of(wa, 1), byte_of(wb, 0), byte_of(wb, 3), byte_of(wc, 2)};
+            const uint32_t bb[4] = {byte_of(wa, 2), byte_of(wb, 1), byte_of(wc, 0), byte_of(wc, 3)};
+            uint32_t bits[12];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                float c0, c1;
+                lasso2(lk, od[rr[p]], od[gg[p]], od[bb[p]], c0, c1);
+                const bool m = all_px | (gyR[rr[p]] + gyG[gg[p]] + gyB[bb[p]] < ybound);
+                c0 = m ? fmaf(c0, al0, be0) : c0;
+                c1 = m ? fmaf(c1, al1, be1) : c1;
+                bits[3 * p] = clip_u8_bits(ex2_approx(fmaf(c1, a10, fmaf(c0, a00, L255))));
+                bits[3 * p + 1] = clip_u8_bits(ex2_approx(fmaf(c1, a11, fmaf(c0, a01, L255))));
+                bits[3 * p + 2] = clip_u8_bits(ex2_approx(fmaf(c1, a12, fmaf(c0, a02, L255))));
+            }
+            o[3 * q] = pack4(bits[0], bits[1], bits[2], bits[3]);
+            o[3 * q + 1] = pack4(bits[4], bits[5], bits[6], bits[7]);
+            o[3 * q + 2] = pack4(bits[8], bits[9], bits[10], bits[11]);
+        }
+        store_group(tout, a.npx, g, a.aligned != 0, o);
+    }
+}
+
+__global__ void __launch_bounds__(PT) concentrations_kernel(PointArgs a) {
+    __shared__ PointShared sh;
+    load_tables(&sh, a.tab, false);
+    const int tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        double M[6];
+        for (int k = 0; k < 6; ++k) M[k] = a.M[(size_t)tile * 6 + k];
+        make_lasso_consts(M, a.lasso_lambda, sh.lk);
+    }
+    __syncthreads();
+    const uint8_t* tin = a.in + (size_t)tile * a.npx * 3;
+    float2* cout = reinterpret_cast<float2*>(a.conc_out) + (size_t)tile * a.npx;
+    const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
+    const LassoK lk = sh.lk;
+    const float* od = sh.od;
+    for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < G; g += gridDim.y * blockDim.x) {
+        uint32_t w[12];
+        int nvalid;
+        load_group<false>(tin, a.npx, g, a.aligned != 0, w, nvalid);
+        for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
+            float c0, c1;
+            lasso2(lk, od[r], od[gg], od[b], c0, c1);
+            if (i < nvalid) cout[(size_t)g * GROUP_PX + i] = make_float2(c0, c1);
+        });
+    }
+}
+
+static dim3 point_grid(const PointArgs& a, int num_sms, int ctas_per_sm) {
+    const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
+    int spans = (G + PT - 1) / PT;
+    // keep the grid near (SMs x resident CTAs) x a few waves when B is large; never more spans than work
+    int want = (num_sms * ctas_per_sm * 4 + a.B - 1) / a.B;
+    if (want < 1) want = 1;
+    if (spans > want) spans = want;
+    return dim3(a.B, spans);
+}
+
+int launch_mask(const PointArgs& a, int num_sms, cudaStream_t stream) {
+    mask_kernel<<<point_grid(a, num_sms, 8), PT, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+int launch_recombine(const PointArgs& a, int num_sms, cudaStream_t stream) {
+    recombine_kernel<<<point_grid(a, num_sms, 4), PT, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+int launch_stain_augment(const PointArgs& a, int num_sms, cudaStream_t stream) {
+    stain_augment_kernel<<<point_grid(a, num_sms, 4), PT, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+int launch_concentrations(const PointArgs& a, int num_sms, cudaStream_t stream) {
+    concentrations_kernel<<<point_grid(a, num_sms, 8), PT, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace sb

@@ -1,0 +1,149 @@
+"""Host-side mirror of stainlib/utils/stain_utils.py: same names and argument meaning, CUDA kernels underneath.
+
+Every function accepts what the reference accepts (one ``np.uint8 [H,W,3]`` image) and returns what the reference
+returns; as an extension it also accepts ``torch.uint8 [B,H,W,3]`` batches (CPU/pinned or CUDA) and then returns a
+tensor of the same kind with a leading batch dimension.
+"""
+import ctypes
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from stainlib_b200 import _native as nv
+from stainlib_b200.utils.excepts import TissueMaskException
+
+
+class ABCStainExtractor(ABC):
+    """stain_utils.py:8-17."""
+
+    @staticmethod
+    @abstractmethod
+    def get_stain_matrix(I):
+        """Estimate the stain matrix given an image."""
+
+
+class ABCTissueLocator(ABC):
+    """stain_utils.py:19-27."""
+
+    @staticmethod
+    @abstractmethod
+    def get_tissue_mask(I):
+        """Get a boolean tissue mask."""
+
+
+def is_image(I):
+    """stain_utils.py:126-134 (numpy) -- extended to torch tensors."""
+    if isinstance(I, torch.Tensor):
+        return I.dim() in (3, 4)
+    if not isinstance(I, np.ndarray):
+        return False
+    return I.ndim == 3
+
+
+def is_uint8_image(I):
+    """stain_utils.py:136-144.  Unlike the reference, a channel count other than 3 is rejected."""
+    if not is_image(I):
+        return False
+    if isinstance(I, torch.Tensor):
+        return I.dtype == torch.uint8 and I.shape[-1] == 3
+    return I.dtype == np.uint8 and I.shape[2] == 3
+
+
+def raise_for_status(status, single):
+    """Reference error behaviour for single-tile calls (stain_utils.py:46-47; np.linalg.eigh on a NaN covariance)."""
+    if not single:
+        return
+    s = int(status[0])
+    if s & nv.SB_STATUS_EMPTY_MASK:
+        raise TissueMaskException("Empty tissue mask computed")
+    if s & (nv.SB_STATUS_FEW_TISSUE | nv.SB_STATUS_DEGENERATE):
+        raise np.linalg.LinAlgError("Eigenvalues did not converge")
+
+
+class LuminosityThresholdTissueLocator(ABCTissueLocator):
+    """stain_utils.py:29-48."""
+
+    @staticmethod
+    def get_tissue_mask(I, luminosity_threshold=0.8):
+        assert is_uint8_image(I), "Image should be RGB uint8."
+        b = nv.Batch(I)
+        mask = b.dev_tensor((b.B, b.H, b.W), torch.uint8)
+        status = b.dev_tensor((b.B,), torch.int32)
+        nv.check(nv.load_library().sb_tissue_mask(b.handle, nv.ptr(b.dev), b.B, b.H, b.W, float(luminosity_threshold),
+                                                  nv.ptr(mask), nv.ptr(status), nv.stream_ptr(b.idx)))
+        st = status.cpu()
+        LuminosityThresholdTissueLocator.last_status = st
+        raise_for_status(st, b.single)
+        return b.give_back(mask.bool())
+
+
+class LuminosityStandardizer(object):
+    """stain_utils.py:50-67."""
+
+    @staticmethod
+    def standardize(I, percentile=95):
+        assert is_uint8_image(I), "Image should be RGB uint8."
+        b = nv.Batch(I)
+        out = b.new_like()
+        nv.check(nv.load_library().sb_luminosity_standardize(b.handle, nv.ptr(b.dev), nv.ptr(out), b.B, b.H, b.W,
+                                                             float(percentile), nv.stream_ptr(b.idx)))
+        return b.give_back(out)
+
+
+def _matrices_to_device(M, b):
+    """[2,3] or [B,2,3] (numpy / tensor) -> float64 CUDA tensor [B,2,3]."""
+    Mt = torch.as_tensor(np.asarray(M.detach().cpu()) if isinstance(M, torch.Tensor) else np.asarray(M), dtype=torch.float64)
+    if Mt.dim() == 2:
+        Mt = Mt[None].expand(b.B, 2, 3)
+    return Mt.contiguous().to(b.dev.device)
+
+
+def get_concentrations(I, stain_matrix, regularizer=0.01):
+    """stain_utils.py:69-78.  Returns N x 2 (float64 for numpy input, as the reference; float32 tensors for batches:
+    [B,N,2])."""
+    b = nv.Batch(I)
+    M = _matrices_to_device(stain_matrix, b)
+    C = b.dev_tensor((b.B, b.H * b.W, 2), torch.float32)
+    nv.check(nv.load_library().sb_concentrations(b.handle, nv.ptr(b.dev), b.B, b.H, b.W, nv.ptr(M), float(regularizer),
+                                                 nv.ptr(C), nv.stream_ptr(b.idx)))
+    out = b.give_back(C)
+    return out.astype(np.float64) if isinstance(out, np.ndarray) else out
+
+
+def get_sign(x):
+    """stain_utils.py:80-91."""
+    if x > 0:
+        return +1
+    elif x < 0:
+        return -1
+    elif x == 0:
+        return 0
+
+
+def normalize_matrix_rows(A):
+    """stain_utils.py:93-99."""
+    if isinstance(A, torch.Tensor):
+        return A / torch.linalg.norm(A, dim=-1, keepdim=True)
+    return A / np.linalg.norm(A, axis=1)[:, None]
+
+
+_OD_LUT = np.maximum(-1 * np.log(np.maximum(np.arange(256), 1) / 255), 1e-6)
+
+
+def convert_RGB_to_OD(I):
+    """stain_utils.py:101-112: OD = max(-ln(max(I,1)/255), 1e-6) -- a 256-entry table lookup (float64).
+    Convenience export only; the kernels apply the same table inline."""
+    if isinstance(I, torch.Tensor):
+        return torch.as_tensor(_OD_LUT, device=I.device)[I.long()]
+    return _OD_LUT[I]
+
+
+def convert_OD_to_RGB(OD):
+    """stain_utils.py:114-124."""
+    if isinstance(OD, torch.Tensor):
+        assert OD.min() >= 0, "Negative optical density."
+        return (255 * torch.exp(-1 * torch.clamp(OD, min=1e-6))).to(torch.uint8)
+    assert OD.min() >= 0, "Negative optical density."
+    OD = np.maximum(OD, 1e-6)
+    return (255 * np.exp(-1 * OD)).astype(np.uint8)
