@@ -18,6 +18,9 @@ constexpr int KEY_BITS = 23;
 constexpr int L1_BITS = 12, L1_BINS = 1 << L1_BITS;   // level-1 histogram: top 12 bits of the key
 constexpr int L2_BITS = 11, L2_BINS = 1 << L2_BITS;   // level-2 histogram: low 11 bits
 constexpr float CONC_KEY_K = 2.0f;  // concentration key: t = 2 - K/(C+K) in [1,2)
+// log2(255) rounded UP by one float step (2^x = 255 * (1 + 5.6e-7)): a pixel with zero concentrations must come out
+// as exactly 255 like the reference's 255*exp(0), even when ex2.approx errs low by its 2^-22 bound.
+constexpr float LOG2_255_UP = 7.994354248046875f;
 
 // ------------------------------------------------------------------------------------------------ tables (device)
 struct Tables {

@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
             if (flags == 0) {
                 const LassoK lk = sh->lk;
                 const float a00 = sh->A[0], a01 = sh->A[1], a02 = sh->A[2], a10 = sh->A[3], a11 = sh->A[4], a12 = sh->A[5];
-                const float L255 = 7.994353436858858f;  // log2(255)
+                const float L255 = LOG2_255_UP;
                 for (int g = gb + threadIdx.x; g < ge; g += NT) {
                     uint32_t w[12], o[12];
                     int nvalid;

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(PT, 4) recombine_kernel(PointArgs a) {
     const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
     const LassoK lk = sh.lk;
     const float a00 = sh.A[0], a01 = sh.A[1], a02 = sh.A[2], a10 = sh.A[3], a11 = sh.A[4], a12 = sh.A[5];
-    const float L255 = 7.994353436858858f;
+    const float L255 = LOG2_255_UP;
     const bool zero_out = sh.zero_out != 0;
     const float* od = sh.od;
     for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < G; g += gridDim.y * blockDim.x) {
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(PT, 4) stain_augment_kernel(PointArgs a) {
     const LassoK lk = sh.lk;
     const float a00 = sh.A[0], a01 = sh.A[1], a02 = sh.A[2], a10 = sh.A[3], a11 = sh.A[4], a12 = sh.A[5];
     const float al0 = sh.alpha[0], al1 = sh.alpha[1], be0 = sh.beta[0], be1 = sh.beta[1];
-    const float L255 = 7.994353436858858f;
+    const float L255 = LOG2_255_UP;
     const bool all_px = a.augment_background != 0;
     const float ybound = a.ybound;
     const float* od = sh.od;
