@@ -355,12 +355,12 @@ def rgb2hed(rgb, log_base=10.0):
 
 def hed2rgb(hed, log_base=10.0):
     """skimage 0.17 ``combine_stains(hed, rgb_from_hed)``: ``rescale_intensity(b ** (-(hed @ conv)) - 2,
-    in_range=(-1, 1))`` -> clip to [-1, 1] then map linearly to [0, 1]."""
+    in_range=(-1, 1))``.  For a float image ``rescale_intensity`` maps in_range onto the float dtype range, which is
+    (-1, 1) when the lower input bound is negative (``clip_negative=False``) -- i.e. it is a plain clip to [-1, 1]."""
     logrgb2 = -np.reshape(hed.astype(np.float64), (-1, 3)) @ RGB_FROM_HED
     rgb2 = np.power(log_base, logrgb2)
     out = np.reshape(rgb2 - 2.0, hed.shape)
-    out = np.clip(out, -1.0, 1.0)
-    return (out + 1.0) / 2.0
+    return np.clip(out, -1.0, 1.0)
 
 
 def hed_augment(patch, sigmas, biases, cutoff_range=(0.05, 0.95), log_base=10.0):

@@ -25,23 +25,6 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 }  // namespace
 
-struct sb_handle {
-    int device = 0;
-    int num_sms = 0;
-    long long launches = 0;
-    sb::Tables tab{};
-    void* table_mem = nullptr;
-    // host-streaming state (sb_normalize_host)
-    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-    static constexpr int NSLOT = 3;
-    uint8_t* slot_in[NSLOT] = {nullptr, nullptr, nullptr};
-    uint8_t* slot_out[NSLOT] = {nullptr, nullptr, nullptr};
-    size_t slot_bytes = 0;
-    cudaEvent_t ev_in[NSLOT] = {}, ev_comp[NSLOT] = {}, ev_out[NSLOT] = {};
-    double* d_target = nullptr;   // [6 + 2]
-    int32_t* d_status = nullptr;
-    size_t status_cap = 0;
-};
 
 namespace {
 

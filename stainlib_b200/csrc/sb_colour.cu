@@ -1,9 +1,480 @@
-// sb_colour.cu -- Reinhard / luminosity standardiser / HED / grayscale entry points (placeholder until implemented).
+// sb_colour.cu -- LAB-space and HED-space kernels (sm_100a).
+//
+//   lab_tile_kernel   one CTA per tile, persistent over the batch; three uses:
+//       REINHARD_STATS      ReinhardStainNormalizer.fit         normalizer.py:64-68
+//       REINHARD_TRANSFORM  ReinhardStainNormalizer.transform   normalizer.py:70-94
+//       LUM_STANDARDIZE     LuminosityStandardizer.standardize  stain_utils.py:53-67
+//     All arithmetic on pixels is the integer 8-bit sRGB<->CIELAB path of OpenCV (oracle/cv_lab.py, verified on all
+//     2^24 colours); every per-channel floating-point step of the reference is a function of one uint8, so it is
+//     evaluated ONCE per tile in fp64 into 256-entry tables (brightness standardisation, the three Reinhard affine
+//     maps, the luminosity rescale) -- the per-pixel work is table lookups and integer multiply-adds, bit-exact.
+//     Percentiles of uint8-valued data come from exact 256-bin histograms.
+//   hed_kernel        HedColorAugmenter.transform  augmenter.py:276-331  (skimage 0.17 colour deconvolution collapsed
+//                     to  rgb' = b^(log_b(rgb/255+2) . A - c) - 2  with a per-tile 3x3 A and 3-vector c)
+//   gray_kernel       GrayscaleAugmentor.pop       augmenter.py:390-401
 #include "sb_kernels.h"
-extern "C" {
-int sb_reinhard_stats(sb_handle*, const uint8_t*, int, int, int, double*, double*, void*) { return SB_ERR_UNSUPPORTED; }
-int sb_reinhard_transform(sb_handle*, const uint8_t*, uint8_t*, int, int, int, const double*, const double*, int, double, int32_t*, void*) { return SB_ERR_UNSUPPORTED; }
-int sb_luminosity_standardize(sb_handle*, const uint8_t*, uint8_t*, int, int, int, double, void*) { return SB_ERR_UNSUPPORTED; }
-int sb_hed_augment(sb_handle*, const uint8_t*, uint8_t*, int, int, int, const double*, const double*, double, double, double, int32_t*, void*) { return SB_ERR_UNSUPPORTED; }
-int sb_grayscale_augment(sb_handle*, const uint8_t*, uint8_t*, int, int, int, const double*, const double*, void*) { return SB_ERR_UNSUPPORTED; }
+#include "sb_tables.inc"
+
+namespace sb {
+
+enum LabMode { REINHARD_STATS = 0, REINHARD_TRANSFORM = 1, LUM_STANDARDIZE = 2 };
+
+struct LabArgs {
+    const uint8_t* in;
+    uint8_t* out;
+    int B, npx, aligned, mode;
+    Tables tab;
+    const double* tmeans;   // [3] device (transform)
+    const double* tstds;    // [3]
+    double* means_out;      // [B,3] (stats)
+    double* stds_out;       // [B,3]
+    int mask_background;
+    int lmax;               // tissue <=> L <= lmax (L of the standardised image)
+    double percentile;      // LUM_STANDARDIZE
+    int32_t* status;
+};
+
+struct __align__(16) LabShared {
+    unsigned hist[3][256];
+    unsigned short gamma[256];
+    unsigned short cbrt[3072];
+    int yf[512];
+    unsigned char invg[4096];
+    unsigned char smap[256];        // brightness standardisation  v -> trunc(clip(v*255/p))
+    unsigned char cmap[3][256];     // per-channel LAB maps
+    double stat[6];                 // means (3), stds (3)
+    double p;
+    unsigned warp_any[NWARP];
+    int any_tissue;
+};
+
+__device__ __forceinline__ void lab_forward(const LabShared* sh, int r, int g, int b, int& L, int& A, int& Bc) {
+    const int R = sh->gamma[r], G = sh->gamma[g], Bl = sh->gamma[b];
+    const int fX = sh->cbrt[(R * 1777 + G * 1541 + Bl * 778 + 2048) >> 12];
+    const int fY = sh->cbrt[(R * 871 + G * 2929 + Bl * 296 + 2048) >> 12];
+    const int fZ = sh->cbrt[(R * 73 + G * 448 + Bl * 3575 + 2048) >> 12];
+    L = (SB_LAB_LSCALE * fY + SB_LAB_LSHIFT + 16384) >> 15;
+    A = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
+    Bc = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
+    L = min(max(L, 0), 255); A = min(max(A, 0), 255); Bc = min(max(Bc, 0), 255);
 }
+
+__device__ __forceinline__ int ab_to_xz(int t) {
+    // inverse companding in fixed point, C truncating division
+    return t <= 3390 ? (t * 108) / 841 - 290 : (((t * t) / 16384) * t) / 16384;
+}
+
+__device__ __forceinline__ void lab_inverse(const LabShared* sh, int L, int A, int Bc, int& r, int& g, int& b) {
+    const int y = sh->yf[2 * L], ify = sh->yf[2 * L + 1];
+    const int adiv = ((5 * A * 53687 + 128) >> 13) - 128 * 16384 / 500;
+    const int bdiv = ((Bc * 41943 + 16) >> 9) - 128 * 16384 / 200 + 1;
+    const int x = ab_to_xz(ify + adiv), z = ab_to_xz(ify - bdiv);
+    int ro = (12615 * x - 6296 * y - 2223 * z + 8192) >> 14;
+    int go = (-3773 * x + 7684 * y + 185 * z + 8192) >> 14;
+    int bo = (217 * x - 836 * y + 4715 * z + 8192) >> 14;
+    r = sh->invg[min(max(ro, 0), 4095)];
+    g = sh->invg[min(max(go, 0), 4095)];
+    b = sh->invg[min(max(bo, 0), 4095)];
+}
+
+// numpy.percentile (linear) of uint8-valued data given its exact histogram (n values), evaluated by one thread.
+__device__ inline double hist_percentile(const unsigned* h, unsigned long long n, double pct) {
+    const double vi = (double)(n - 1) * (pct / 100.0);
+    unsigned long long lo = (unsigned long long)floor(vi);
+    if (lo > n - 1) lo = n - 1;
+    const unsigned long long hi = lo + 1 < n ? lo + 1 : n - 1;
+    const double frac = vi - (double)lo;
+    unsigned long long c = 0;
+    int vlo = 255, vhi = 255;
+    bool flo = false, fhi = false;
+    for (int v = 0; v < 256; ++v) {
+        c += h[v];
+        if (!flo && c > lo) { vlo = v; flo = true; }
+        if (!fhi && c > hi) { vhi = v; fhi = true; }
+    }
+    return lerp_np((double)vlo, (double)vhi, frac);
+}
+
+__device__ inline unsigned char trunc_clip_u8(double x) {
+    // np.clip(x, 0, 255).astype(np.uint8); NaN -> 0
+    if (!(x == x)) return 0;
+    if (x <= 0.0) return 0;
+    if (x >= 255.0) return 255;
+    return (unsigned char)(int)x;
+}
+
+__global__ void __launch_bounds__(NT, 2) lab_tile_kernel(LabArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LabShared* sh = reinterpret_cast<LabShared*>(smem_raw);
+    for (int i = threadIdx.x; i < 256; i += NT) sh->gamma[i] = a.tab.gamma[i];
+    for (int i = threadIdx.x; i < 3072; i += NT) sh->cbrt[i] = a.tab.cbrt[i];
+    for (int i = threadIdx.x; i < 512; i += NT) sh->yf[i] = a.tab.lab2yf[i];
+    for (int i = threadIdx.x; i < 4096; i += NT) sh->invg[i] = a.tab.invgamma[i];
+    __syncthreads();
+    const int npx = a.npx;
+    const int G = (npx + GROUP_PX - 1) / GROUP_PX;
+    const bool aligned = a.aligned != 0;
+    const bool reinhard = a.mode != LUM_STANDARDIZE;
+
+    for (int tile = blockIdx.x; tile < a.B; tile += gridDim.x) {
+        const uint8_t* __restrict__ tin = a.in + (size_t)tile * npx * 3;
+        for (int i = threadIdx.x; i < 768; i += NT) (&sh->hist[0][0])[i] = 0;
+        if (threadIdx.x == 0) sh->any_tissue = 0;
+        __syncthreads();
+        if (reinhard) {
+            // ---- pass 1: histogram of all 3N channel bytes -> 90th percentile -> brightness table (stain_utils.py:188-194)
+            for (int g = threadIdx.x; g < G; g += NT) {
+                uint32_t w[12]; int nvalid;
+                load_group<true>(tin, npx, g, aligned, w, nvalid);
+                for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
+                    if (i < nvalid) { atomicAdd(&sh->hist[0][r], 1u); atomicAdd(&sh->hist[0][gg], 1u); atomicAdd(&sh->hist[0][b], 1u); }
+                });
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) sh->p = hist_percentile(sh->hist[0], 3ull * (unsigned long long)npx, 90.0);
+            __syncthreads();
+            if (threadIdx.x < 256) sh->smap[threadIdx.x] = trunc_clip_u8((double)threadIdx.x * 255.0 / sh->p);
+            __syncthreads();
+            for (int i = threadIdx.x; i < 256; i += NT) sh->hist[0][i] = 0;
+            __syncthreads();
+        }
+        // ---- pass 2: LAB histograms of the (standardised) tile
+        for (int g = threadIdx.x; g < G; g += NT) {
+            uint32_t w[12]; int nvalid;
+            load_group<true>(tin, npx, g, aligned, w, nvalid);
+            for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
+                if (reinhard) { r = sh->smap[r]; gg = sh->smap[gg]; b = sh->smap[b]; }
+                int L, A, Bc;
+                lab_forward(sh, r, gg, b, L, A, Bc);
+                if (i < nvalid) {
+                    atomicAdd(&sh->hist[0][L], 1u);
+                    if (reinhard) { atomicAdd(&sh->hist[1][A], 1u); atomicAdd(&sh->hist[2][Bc], 1u); }
+                }
+            });
+        }
+        __syncthreads();
+        if (reinhard) {
+            // mean and population std per channel exactly as cv.meanStdDev sees them (stain_utils.py:146-186):
+            // I1 = float32(L)/float32(2.55), I2 = a-128, I3 = b-128, double accumulators.
+            if (threadIdx.x < 3) {
+                const int c = threadIdx.x;
+                double s = 0.0, sq = 0.0;
+                for (int v = 0; v < 256; ++v) {
+                    const double q = c == 0 ? (double)((float)v / 2.55f) : (double)(v - 128);
+                    const double h = (double)sh->hist[c][v];
+                    s += h * q; sq += h * q * q;
+                }
+                const double mean = s / (double)npx;
+                double var = sq / (double)npx - mean * mean;
+                if (var < 0.0) var = 0.0;
+                sh->stat[c] = mean; sh->stat[3 + c] = sqrt(var);
+            }
+            __syncthreads();
+            if (a.mode == REINHARD_STATS) {
+                if (threadIdx.x < 3) {
+                    a.means_out[(size_t)tile * 3 + threadIdx.x] = sh->stat[threadIdx.x];
+                    a.stds_out[(size_t)tile * 3 + threadIdx.x] = sh->stat[3 + threadIdx.x];
+                }
+                __syncthreads();
+                continue;
+            }
+            // per-channel affine maps (normalizer.py:81-83) followed by merge_back's scale/offset, clip and truncation
+            for (int i = threadIdx.x; i < 768; i += NT) {
+                const int c = i >> 8, v = i & 255;
+                const double q = c == 0 ? (double)((float)v / 2.55f) : (double)(v - 128);
+                const double n = (q - sh->stat[c]) * (a.tstds[c] / sh->stat[3 + c]) + a.tmeans[c];
+                sh->cmap[c][v] = trunc_clip_u8(c == 0 ? n * 2.55 : n + 128.0);
+            }
+        } else {
+            if (threadIdx.x == 0) sh->p = hist_percentile(sh->hist[0], (unsigned long long)npx, a.percentile);
+            __syncthreads();
+            if (threadIdx.x < 256) sh->cmap[0][threadIdx.x] = trunc_clip_u8(255.0 * (double)threadIdx.x / sh->p);
+        }
+        __syncthreads();
+        // ---- pass 3: map and convert back
+        uint8_t* __restrict__ tout = a.out + (size_t)tile * npx * 3;
+        const bool use_mask = reinhard && a.mask_background;
+        const int lmax = a.lmax;
+        int seen = 0;
+        for (int g = threadIdx.x; g < G; g += NT) {
+            uint32_t w[12], o[12]; int nvalid;
+            load_group<false>(tin, npx, g, aligned, w, nvalid);
+            uint32_t ob[48];
+            for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
+                if (reinhard) { r = sh->smap[r]; gg = sh->smap[gg]; b = sh->smap[b]; }
+                int L, A, Bc;
+                lab_forward(sh, r, gg, b, L, A, Bc);
+                int L2, A2, B2;
+                if (reinhard) {
+                    const bool tissue = !use_mask || L <= lmax;
+                    seen |= (tissue && i < nvalid) ? 1 : 0;
+                    // background: L = clip((254 + 0) * 2.55) = 255, a = b = 0 + 128 (normalizer.py:85-90)
+                    L2 = tissue ? sh->cmap[0][L] : 255; A2 = tissue ? sh->cmap[1][A] : 128; B2 = tissue ? sh->cmap[2][Bc] : 128;
+                } else {
+                    L2 = sh->cmap[0][L]; A2 = A; B2 = Bc;
+                }
+                int ro, go, bo;
+                lab_inverse(sh, L2, A2, B2, ro, go, bo);
+                ob[3 * i] = ro; ob[3 * i + 1] = go; ob[3 * i + 2] = bo;
+            });
+#pragma unroll
+            for (int k = 0; k < 12; ++k) o[k] = ob[4 * k] | (ob[4 * k + 1] << 8) | (ob[4 * k + 2] << 16) | (ob[4 * k + 3] << 24);
+            store_group(tout, npx, g, aligned, o);
+        }
+        if (use_mask) {
+            if (seen) sh->any_tissue = 1;
+            __syncthreads();
+            if (threadIdx.x == 0 && a.status) a.status[tile] = sh->any_tissue ? 0 : SB_STATUS_EMPTY_MASK;
+        } else if (threadIdx.x == 0 && a.status) {
+            a.status[tile] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------ HED
+struct HedArgs {
+    const uint8_t* in;
+    uint8_t* out;
+    int B, npx, aligned;
+    const double* sigma;   // [B,3]
+    const double* bias;    // [B,3]
+    double cutoff_lo, cutoff_hi, log_base;
+    int32_t* status;       // 1 = tile outside the cutoff (copied through)
+    unsigned long long* sums;   // [B] workspace: sum of all channel bytes
+};
+
+__global__ void __launch_bounds__(256) byte_sum_kernel(const uint8_t* in, int npx, int aligned, unsigned long long* sums) {
+    const int tile = blockIdx.x;
+    const uint8_t* tin = in + (size_t)tile * npx * 3;
+    const int G = (npx + GROUP_PX - 1) / GROUP_PX;
+    unsigned s = 0;
+    unsigned long long acc = 0;
+    for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < G; g += gridDim.y * blockDim.x) {
+        uint32_t w[12]; int nvalid;
+        load_group<true>(in + (size_t)tile * npx * 3, npx, g, aligned != 0, w, nvalid);
+        (void)tin;
+        if (nvalid == GROUP_PX) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) s += __vsadu4(w[k], 0u);      // sum of the four bytes
+        } else {
+            for (int k = 0; k < nvalid * 3; ++k) s += (w[k >> 2] >> (8 * (k & 3))) & 255u;
+        }
+        acc += s; s = 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&sums[tile], acc);
+}
+
+__global__ void __launch_bounds__(256, 4) hed_kernel(HedArgs a) {
+    __shared__ float l2[256];        // log2(v/255 + 2)
+    __shared__ float A[9], c[3];
+    __shared__ int skip;
+    const int tile = blockIdx.x;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) l2[i] = (float)log2((double)i / 255.0 + 2.0);
+    if (threadIdx.x == 0) {
+        // patch mean in [0,1] (augmenter.py:288-293); exact integer sum instead of numpy's float32 pairwise mean
+        const double mean = (double)a.sums[tile] / (3.0 * (double)a.npx) / 255.0;
+        skip = !(a.cutoff_lo <= mean && mean <= a.cutoff_hi);
+        if (a.status) a.status[tile] = skip;
+        // A = inv(M) diag(1+sigma) M, c = bias M  (M = rgb_from_hed), exponent scaled to base 2
+        const double M[9] = {0.65, 0.70, 0.29, 0.07, 0.99, 0.11, 0.27, 0.57, 0.78};
+        const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+        double Mi[9];
+        Mi[0] = (M[4] * M[8] - M[5] * M[7]) / det; Mi[1] = (M[2] * M[7] - M[1] * M[8]) / det; Mi[2] = (M[1] * M[5] - M[2] * M[4]) / det;
+        Mi[3] = (M[5] * M[6] - M[3] * M[8]) / det; Mi[4] = (M[0] * M[8] - M[2] * M[6]) / det; Mi[5] = (M[2] * M[3] - M[0] * M[5]) / det;
+        Mi[6] = (M[3] * M[7] - M[4] * M[6]) / det; Mi[7] = (M[1] * M[6] - M[0] * M[7]) / det; Mi[8] = (M[0] * M[4] - M[1] * M[3]) / det;
+        const double l2b = log2(a.log_base);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < 3; ++k) s += Mi[3 * i + k] * (1.0 + a.sigma[(size_t)tile * 3 + k]) * M[3 * k + j];
+                A[3 * i + j] = (float)s;
+            }
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s += a.bias[(size_t)tile * 3 + k] * M[3 * k + j];
+            c[j] = (float)(s * l2b);
+        }
+    }
+    __syncthreads();
+    const uint8_t* tin = a.in + (size_t)tile * a.npx * 3;
+    uint8_t* tout = a.out + (size_t)tile * a.npx * 3;
+    const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
+    const float a00 = A[0], a01 = A[1], a02 = A[2], a10 = A[3], a11 = A[4], a12 = A[5], a20 = A[6], a21 = A[7], a22 = A[8];
+    const float c0 = -c[0], c1 = -c[1], c2 = -c[2];
+    const bool copy = skip != 0;
+    for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < G; g += gridDim.y * blockDim.x) {
+        uint32_t w[12], o[12]; int nvalid;
+        load_group<false>(tin, a.npx, g, a.aligned != 0, w, nvalid);
+        if (!copy) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
+                const uint32_t rr[4] = {byte_of(wa, 0), byte_of(wa, 3), byte_of(wb, 2), byte_of(wc, 1)};
+                const uint32_t gg[4] = {byte_of(wa, 1), byte_of(wb, 0), byte_of(wb, 3), byte_of(wc, 2)};
+                const uint32_t bb[4] = {byte_of(wa, 2), byte_of(wb, 1), byte_of(wc, 0), byte_of(wc, 3)};
+                uint32_t bits[12];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float lr = l2[rr[p]], lg = l2[gg[p]], lb = l2[bb[p]];
+                    const float e0 = fmaf(lb, a20, fmaf(lg, a10, fmaf(lr, a00, c0)));
+                    const float e1 = fmaf(lb, a21, fmaf(lg, a11, fmaf(lr, a01, c1)));
+                    const float e2 = fmaf(lb, a22, fmaf(lg, a12, fmaf(lr, a02, c2)));
+                    // clip(b^e - 2, [0,1]) * 255, truncated (hed2rgb clip to [-1,1], then augmenter.py:320-325)
+                    bits[3 * p] = clip_u8_bits(fmaxf(fmaf(ex2_approx(e0), 255.f, -510.f), 0.f));
+                    bits[3 * p + 1] = clip_u8_bits(fmaxf(fmaf(ex2_approx(e1), 255.f, -510.f), 0.f));
+                    bits[3 * p + 2] = clip_u8_bits(fmaxf(fmaf(ex2_approx(e2), 255.f, -510.f), 0.f));
+                }
+                o[3 * q] = pack4(bits[0], bits[1], bits[2], bits[3]);
+                o[3 * q + 1] = pack4(bits[4], bits[5], bits[6], bits[7]);
+                o[3 * q + 2] = pack4(bits[8], bits[9], bits[10], bits[11]);
+            }
+            store_group(tout, a.npx, g, a.aligned != 0, o);
+        } else {
+            store_group(tout, a.npx, g, a.aligned != 0, w);
+        }
+    }
+}
+
+struct GrayArgs {
+    const uint8_t* in;
+    uint8_t* out;
+    int B, npx, aligned;
+    const double* alpha;   // [B]
+    const double* beta;    // [B]
+};
+
+__global__ void __launch_bounds__(256, 4) gray_kernel(GrayArgs a) {
+    const int tile = blockIdx.x;
+    const float al = (float)a.alpha[tile], be = (float)a.beta[tile];
+    const uint8_t* tin = a.in + (size_t)tile * a.npx * 3;
+    uint8_t* tout = a.out + (size_t)tile * a.npx * 3;
+    const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
+    const float kr = (float)(0.2125 / 255.0), kg = (float)(0.7154 / 255.0), kb = (float)(0.0721 / 255.0);
+    for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < G; g += gridDim.y * blockDim.x) {
+        uint32_t w[12], o[12]; int nvalid;
+        load_group<false>(tin, a.npx, g, a.aligned != 0, w, nvalid);
+        uint32_t v[16];
+        for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
+            const float gray = fmaf((float)b, kb, fmaf((float)gg, kg, (float)r * kr));
+            const float x = fminf(fmaxf(fmaf(gray, al, be), 0.f), 1.f) * 255.f;
+            v[i] = clip_u8_bits(x) & 255u;
+        });
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t p0 = v[4 * q], p1 = v[4 * q + 1], p2 = v[4 * q + 2], p3 = v[4 * q + 3];
+            o[3 * q] = p0 | (p0 << 8) | (p0 << 16) | (p1 << 24);
+            o[3 * q + 1] = p1 | (p1 << 8) | (p2 << 16) | (p2 << 24);
+            o[3 * q + 2] = p2 | (p3 << 8) | (p3 << 16) | (p3 << 24);
+        }
+        store_group(tout, a.npx, g, a.aligned != 0, o);
+    }
+}
+
+}  // namespace sb
+
+// ------------------------------------------------------------------------------------------------------ C ABI glue
+
+namespace {
+int lab_lmax(double thr) {
+    int best = -1;
+    for (int L = 0; L < 256; ++L)
+        if ((double)L / 255.0 < thr) best = L;
+    return best;
+}
+int launch_lab(sb_handle* hh, sb::LabArgs& a, cudaStream_t st) {
+    sb_handle* h = hh;
+    a.tab = h->tab;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(sb::lab_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sb::LabShared)) != cudaSuccess) return SB_ERR_CUDA;
+        attr = true;
+    }
+    int grid = h->num_sms * 2;
+    if (grid > a.B) grid = a.B;
+    sb::lab_tile_kernel<<<grid, sb::NT, sizeof(sb::LabShared), st>>>(a);
+    if (cudaGetLastError() != cudaSuccess) return SB_ERR_CUDA;
+    h->launches += 1;
+    return SB_OK;
+}
+bool bad_img(const void* h, const void* p, int B, int H, int W) {
+    return !h || !p || B <= 0 || H <= 0 || W <= 0 || (long long)H * W > (1LL << 24);
+}
+int aligned16(const void* a, const void* b, int npx) {
+    return (((uintptr_t)a | (uintptr_t)b) % 16 == 0) && (((size_t)npx * 3) % 16 == 0);
+}
+dim3 tile_grid(int B, int npx, int num_sms) {
+    const int G = (npx + sb::GROUP_PX - 1) / sb::GROUP_PX;
+    int spans = (G + 255) / 256;
+    int want = (num_sms * 16 + B - 1) / B;
+    if (want < 1) want = 1;
+    if (spans > want) spans = want;
+    return dim3(B, spans);
+}
+}  // namespace
+
+extern "C" {
+
+int sb_reinhard_stats(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double* means, double* stds, void* stream) {
+    if (bad_img(h, rgb, B, H, W) || !means || !stds) return SB_ERR_ARG;
+    sb::LabArgs a{};
+    a.in = rgb; a.B = B; a.npx = H * W; a.aligned = aligned16(rgb, rgb, a.npx); a.mode = sb::REINHARD_STATS;
+    a.means_out = means; a.stds_out = stds;
+    return launch_lab(h, a, (cudaStream_t)stream);
+}
+
+int sb_reinhard_transform(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const double* target_means,
+                          const double* target_stds, int mask_background, double luminosity_threshold, int32_t* status, void* stream) {
+    if (bad_img(h, rgb_in, B, H, W) || !rgb_out || !target_means || !target_stds) return SB_ERR_ARG;
+    sb::LabArgs a{};
+    a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = aligned16(rgb_in, rgb_out, a.npx); a.mode = sb::REINHARD_TRANSFORM;
+    a.tmeans = target_means; a.tstds = target_stds; a.mask_background = mask_background; a.lmax = lab_lmax(luminosity_threshold);
+    a.status = status;
+    return launch_lab(h, a, (cudaStream_t)stream);
+}
+
+int sb_luminosity_standardize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, double percentile, void* stream) {
+    if (bad_img(h, rgb_in, B, H, W) || !rgb_out) return SB_ERR_ARG;
+    sb::LabArgs a{};
+    a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = aligned16(rgb_in, rgb_out, a.npx); a.mode = sb::LUM_STANDARDIZE;
+    a.percentile = percentile;
+    return launch_lab(h, a, (cudaStream_t)stream);
+}
+
+int sb_hed_augment(sb_handle* hh, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const double* sigma, const double* bias,
+                   double cutoff_lo, double cutoff_hi, double log_base, int32_t* status, void* stream) {
+    if (bad_img(hh, rgb_in, B, H, W) || !rgb_out || !sigma || !bias) return SB_ERR_ARG;
+    sb_handle* h = hh;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* sums = nullptr;
+    if (cudaMallocAsync(&sums, (size_t)B * 8, st) != cudaSuccess) return SB_ERR_CUDA;
+    if (cudaMemsetAsync(sums, 0, (size_t)B * 8, st) != cudaSuccess) return SB_ERR_CUDA;
+    const int npx = H * W, al = aligned16(rgb_in, rgb_out, npx);
+    const dim3 grid = tile_grid(B, npx, h->num_sms);
+    sb::byte_sum_kernel<<<grid, 256, 0, st>>>(rgb_in, npx, al, sums);
+    sb::HedArgs a{};
+    a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = npx; a.aligned = al; a.sigma = sigma; a.bias = bias;
+    a.cutoff_lo = cutoff_lo; a.cutoff_hi = cutoff_hi; a.log_base = log_base; a.status = status; a.sums = sums;
+    sb::hed_kernel<<<grid, 256, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(sums, st);
+    if (e != cudaSuccess) return SB_ERR_CUDA;
+    h->launches += 2;
+    return SB_OK;
+}
+
+int sb_grayscale_augment(sb_handle* hh, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const double* alpha,
+                         const double* beta, void* stream) {
+    if (bad_img(hh, rgb_in, B, H, W) || !rgb_out || !alpha || !beta) return SB_ERR_ARG;
+    sb_handle* h = hh;
+    sb::GrayArgs a{};
+    a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = aligned16(rgb_in, rgb_out, a.npx); a.alpha = alpha; a.beta = beta;
+    sb::gray_kernel<<<tile_grid(B, a.npx, h->num_sms), 256, 0, (cudaStream_t)stream>>>(a);
+    if (cudaGetLastError() != cudaSuccess) return SB_ERR_CUDA;
+    h->launches += 1;
+    return SB_OK;
+}
+
+}  // extern "C"
