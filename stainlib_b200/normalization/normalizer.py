@@ -21,17 +21,7 @@ from stainlib_b200.extraction.vahadane_stain_extractor import VahadaneStainExtra
 from stainlib_b200.utils.stain_utils import get_concentrations, is_uint8_image, raise_for_status
 
 
-def _share_fit_statistics(vec, src, group):
-    """One all-reduce(SUM) of the fitted target statistics: ``src`` contributes, every other rank adds zeros."""
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()):
-        return vec
-    if dist.get_rank(group) != src:
-        vec = torch.zeros_like(vec)
-    backend = dist.get_backend(group)
-    buf = vec.cuda() if backend == "nccl" else vec.cpu()
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    return buf.to(vec.device)
+from stainlib_b200.distributed import share_fit_statistics as _share_fit_statistics
 
 
 class ExtractiveStainNormalizer(object):
@@ -54,6 +44,23 @@ class ExtractiveStainNormalizer(object):
             kw["dl_iters"] = VahadaneStainExtractor.n_iter
         return nv.default_params(self._method, **kw)
 
+    def _fit_local(self, target):
+        """Stain matrix + maxC of one target tile on this rank's GPU -> float64 vector [M(6), maxC(2)]."""
+        assert is_uint8_image(target), "Image should be RGB uint8."
+        b = nv.Batch(target)
+        assert b.B == 1, "fit() takes one target tile"
+        M = b.dev_tensor((1, 2, 3), torch.float64)
+        maxC = b.dev_tensor((1, 2), torch.float64)
+        status = b.dev_tensor((1,), torch.int32)
+        p = self._params()
+        nv.check(nv.load_library().sb_fit(b.handle, nv.ptr(b.dev), 1, b.H, b.W, ctypes.byref(p), nv.ptr(M), nv.ptr(maxC),
+                                          nv.ptr(status), nv.stream_ptr(b.idx)))
+        st = status.cpu()
+        self.last_status = st
+        raise_for_status(st, True)
+        self._target = target
+        return torch.cat([M.reshape(6), maxC.reshape(2)]).cpu()
+
     def fit(self, target, src=0, group=None):
         """Fit to a target image (normalizer.py:27-36): stain matrix of the target and the 99th percentile of its
         concentrations, one fused kernel.  Under torch.distributed only rank ``src`` needs a real target."""
@@ -61,20 +68,7 @@ class ExtractiveStainNormalizer(object):
         distributed = dist.is_available() and dist.is_initialized()
         vec = torch.zeros(8, dtype=torch.float64)
         if not distributed or dist.get_rank(group) == src:
-            assert is_uint8_image(target), "Image should be RGB uint8."
-            b = nv.Batch(target)
-            assert b.B == 1, "fit() takes one target tile"
-            M = b.dev_tensor((1, 2, 3), torch.float64)
-            maxC = b.dev_tensor((1, 2), torch.float64)
-            status = b.dev_tensor((1,), torch.int32)
-            p = self._params()
-            nv.check(nv.load_library().sb_fit(b.handle, nv.ptr(b.dev), 1, b.H, b.W, ctypes.byref(p), nv.ptr(M), nv.ptr(maxC),
-                                              nv.ptr(status), nv.stream_ptr(b.idx)))
-            st = status.cpu()
-            self.last_status = st
-            raise_for_status(st, True)
-            vec = torch.cat([M.reshape(6), maxC.reshape(2)]).cpu()
-            self._target = target
+            vec = self._fit_local(target)
         vec = _share_fit_statistics(vec, src, group)
         self.stain_matrix_target = vec[:6].reshape(2, 3).numpy().copy()
         self.maxC_target = vec[6:].reshape(1, 2).numpy().copy()
