@@ -1,6 +1,7 @@
 // sb_api.cu -- the extern "C" boundary declared in include/stainb200.h.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -316,9 +317,13 @@ int sb_recombine(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, i
     sb::PointArgs a{};
     a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb_in, rgb_out, a.npx);
     a.tab = h->tab; a.M = M_src; a.scale = scale; a.Mt = M_target; a.lasso_lambda = lasso_lambda;
-    cudaError_t e = (cudaError_t)sb::launch_recombine(a, h->num_sms, (cudaStream_t)stream);
+    // TMA-staged ring when every tile is a whole number of 16-byte vectors; register-staged kernel otherwise
+    const bool tma = a.aligned && getenv("SB_K4_NO_TMA") == nullptr;
+    a.debug_copy = getenv("SB_K4_COPY") != nullptr;
+    cudaError_t e = (cudaError_t)(tma ? sb::launch_recombine_tma(a, h->num_sms, (cudaStream_t)stream)
+                                      : sb::launch_recombine_v2(a, h->num_sms, (cudaStream_t)stream));
     if (e != cudaSuccess) return cuda_fail(e, "recombine launch");
-    h->launches += 1;
+    h->launches += tma ? 2 : 1;
     return SB_OK;
 }
 

@@ -85,7 +85,9 @@ __device__ __forceinline__ void store_group(uint8_t* __restrict__ tile, int npx,
         stg_stream(v + 2, make_uint4(w[8], w[9], w[10], w[11]));
     } else {
         const int nbytes = nvalid * 3;
-        for (int k = 0; k < nbytes; ++k) dst[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+#pragma unroll
+        for (int k = 0; k < 48; ++k)
+            if (k < nbytes) dst[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
     }
 }
 

@@ -58,12 +58,15 @@ struct PointArgs {
     const double* Mt;      // [2,3]   (recombine)
     double lasso_lambda;
     int augment_background;
+    int debug_copy;        // development: K4 ring moves bytes without computing
     float* conc_out;       // [B,N,2] (concentrations)
     uint8_t* mask_out;     // [B,N]   (mask)
     int32_t* status;
 };
 int launch_mask(const PointArgs& a, int num_sms, cudaStream_t stream);
 int launch_recombine(const PointArgs& a, int num_sms, cudaStream_t stream);
+int launch_recombine_v2(const PointArgs& a, int num_sms, cudaStream_t stream);
+int launch_recombine_tma(const PointArgs& a, int num_sms, cudaStream_t stream);
 int launch_stain_augment(const PointArgs& a, int num_sms, cudaStream_t stream);
 int launch_concentrations(const PointArgs& a, int num_sms, cudaStream_t stream);
 
