@@ -68,17 +68,40 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
     if (p->method != SB_METHOD_MACENKO && p->method != SB_METHOD_VAHADANE) return SB_ERR_ARG;
     sb::PipeArgs a{};
     a.in = in; a.out = out; a.B = B; a.npx = H * W;
-    a.aligned = is_aligned(in, out, a.npx);
+    a.aligned = is_aligned(in, out ? out : in, a.npx);
     a.tab = h->tab;
-    a.mode = mode; a.method = p->method;
+    a.method = p->method;
     a.cluster_size = pick_cluster(h, B, a.npx, p->cluster_size);
     a.ybound = mask_ybound_f(p->luminosity_threshold);
     a.ang_pct = p->angular_percentile; a.lasso_lambda = p->lasso_lambda; a.conc_pct = p->conc_percentile;
     a.dl_lambda = p->dl_lambda; a.dl_iters = p->dl_iters;
-    a.Mt = Mt; a.maxCt = maxCt; a.M_out = M; a.maxC_out = maxC; a.status = status;
+    a.Mt = Mt; a.maxCt = maxCt;
+    if (mode != sb::PIPE_NORMALIZE) {
+        a.mode = mode; a.M_out = M; a.maxC_out = maxC; a.status = status;
+        cudaError_t e = (cudaError_t)sb::launch_tile_pipeline(a, h->num_sms, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "tile_pipeline launch");
+        h->launches += 1;
+        return SB_OK;
+    }
+    // transform = fused per-tile statistics kernel (stain matrix + maxC of every source tile) followed by the
+    // TMA-ring recombine kernel on the same stream; the statistics go through a stream-ordered workspace unless the
+    // caller asked for them.
+    double* ws = nullptr;
+    const size_t need = (size_t)B * 8 * sizeof(double) + (size_t)B * sizeof(int32_t);
+    if (!M || !maxC || !status) SB_CUDA(cudaMallocAsync(&ws, need, stream));
+    double* Mw = M ? M : ws;
+    double* Cw = maxC ? maxC : ws + (size_t)B * 6;
+    int32_t* Sw = status ? status : reinterpret_cast<int32_t*>(ws + (size_t)B * 8);
+    a.mode = sb::PIPE_FIT; a.M_out = Mw; a.maxC_out = Cw; a.status = Sw;
     cudaError_t e = (cudaError_t)sb::launch_tile_pipeline(a, h->num_sms, stream);
     if (e != cudaSuccess) return cuda_fail(e, "tile_pipeline launch");
-    h->launches += 1;
+    sb::PointArgs k{};
+    k.in = in; k.out = out; k.B = B; k.npx = a.npx; k.aligned = a.aligned; k.tab = h->tab; k.lasso_lambda = p->lasso_lambda;
+    const bool tma = a.aligned && getenv("SB_K4_NO_TMA") == nullptr;
+    e = (cudaError_t)sb::launch_recombine_normalize(k, h->num_sms, stream, tma, Mw, Cw, Mt, maxCt, Sw);
+    if (ws) cudaFreeAsync(ws, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "recombine launch");
+    h->launches += 3;
     return SB_OK;
 }
 
@@ -320,10 +343,9 @@ int sb_recombine(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, i
     // TMA-staged ring when every tile is a whole number of 16-byte vectors; register-staged kernel otherwise
     const bool tma = a.aligned && getenv("SB_K4_NO_TMA") == nullptr;
     a.debug_copy = getenv("SB_K4_COPY") != nullptr;
-    cudaError_t e = (cudaError_t)(tma ? sb::launch_recombine_tma(a, h->num_sms, (cudaStream_t)stream)
-                                      : sb::launch_recombine_v2(a, h->num_sms, (cudaStream_t)stream));
+    cudaError_t e = (cudaError_t)sb::launch_recombine(a, h->num_sms, (cudaStream_t)stream, tma);
     if (e != cudaSuccess) return cuda_fail(e, "recombine launch");
-    h->launches += tma ? 2 : 1;
+    h->launches += 2;
     return SB_OK;
 }
 

@@ -166,6 +166,119 @@ __device__ __forceinline__ uint32_t clip_u8_bits(float x) {
     return __float_as_uint(__fadd_rd(fminf(x, 255.f), 8388608.f));
 }
 
+// ------------------------------------------------------------------------------------------------ K4 arithmetic
+// Lane-replicated OD table (256-byte rows: words 0..31 = one copy per lane, words 32..63 free for the caller), the
+// PRMT-built lookup offset, and the packed two-pixel recombine step shared by sb_recombine.cu and sb_pipeline.cu.
+constexpr int OD_ROW_BYTES = 256;             // row stride of the lane-replicated OD table
+constexpr int OD_REP_BYTES = 256 * OD_ROW_BYTES;
+
+struct __align__(16) K4Consts {
+    float m[6];      // source stain matrix rows
+    float nlam;      // -lambda
+    float i00, i01, i11;
+    float rg00, rg11, g01;
+    float A[6];      // -scale_j * Mt_jk * log2(e)
+    int unit_diag, need_check;
+    int mode;        // 0 = recombine, 1 = write zeros (reference divides by a zero percentile), 2 = copy the input through
+};
+
+__device__ __forceinline__ float od_lookup(const unsigned char* tab, uint32_t w, uint32_t lane_off, int k) {
+    // offset = (byte k of w) << 8 | lane << 2 : one PRMT
+    const uint32_t off = __byte_perm(w, lane_off, 0x6504u | (k << 4));
+    return *reinterpret_cast<const float*>(tab + off);
+}
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
+
+template <bool CHECK, bool UNIT>
+__device__ __forceinline__ void recombine_pair(const K4Consts& k, const float2 o0, const float2 o1, const float2 o2, uint32_t (&bits)[6]) {
+    const float2 u0 = __ffma2_rn(dup(k.m[2]), o2, __ffma2_rn(dup(k.m[1]), o1, __ffma2_rn(dup(k.m[0]), o0, dup(k.nlam))));
+    const float2 u1 = __ffma2_rn(dup(k.m[5]), o2, __ffma2_rn(dup(k.m[4]), o1, __ffma2_rn(dup(k.m[3]), o0, dup(k.nlam))));
+    const float2 a0 = __ffma2_rn(dup(k.i01), u1, __fmul2_rn(dup(k.i00), u0));
+    const float2 a1 = __ffma2_rn(dup(k.i11), u1, __fmul2_rn(dup(k.i01), u0));
+    float2 c0, c1;
+    if (UNIT) {
+        const float x0a = fmaxf(u0.x, 0.f), x1a = fmaxf(u1.x, 0.f), x0b = fmaxf(u0.y, 0.f), x1b = fmaxf(u1.y, 0.f);
+        const bool ba = (a0.x > 0.f) & (a1.x > 0.f), bb = (a0.y > 0.f) & (a1.y > 0.f);
+        const bool pa = x0a >= x1a, pb = x0b >= x1b;
+        c0.x = ba ? a0.x : (pa ? x0a : 0.f); c1.x = ba ? a1.x : (pa ? 0.f : x1a);
+        c0.y = bb ? a0.y : (pb ? x0b : 0.f); c1.y = bb ? a1.y : (pb ? 0.f : x1b);
+    } else {
+        // general Gram diagonal: KKT form (same as lasso2 in sb_device.cuh)
+        const float p0a = fmaxf(u0.x, 0.f) * k.rg00, p1a = fmaxf(u1.x, 0.f) * k.rg11;
+        const float p0b = fmaxf(u0.y, 0.f) * k.rg00, p1b = fmaxf(u1.y, 0.f) * k.rg11;
+        const bool ba = (a0.x > 0.f) & (a1.x > 0.f), bb = (a0.y > 0.f) & (a1.y > 0.f);
+        const bool o0a = (p0a > 0.f) & (fmaf(-k.g01, p0a, u1.x) <= 0.f), o1a = (p1a > 0.f) & (fmaf(-k.g01, p1a, u0.x) <= 0.f);
+        const bool o0b = (p0b > 0.f) & (fmaf(-k.g01, p0b, u1.y) <= 0.f), o1b = (p1b > 0.f) & (fmaf(-k.g01, p1b, u0.y) <= 0.f);
+        c0.x = ba ? a0.x : (o0a ? p0a : 0.f); c1.x = ba ? a1.x : ((!o0a & o1a) ? p1a : 0.f);
+        c0.y = bb ? a0.y : (o0b ? p0b : 0.f); c1.y = bb ? a1.y : ((!o0b & o1b) ? p1b : 0.f);
+    }
+    const float2 L = dup(LOG2_255_UP);
+    const float2 e0 = __ffma2_rn(c1, dup(k.A[3]), __ffma2_rn(c0, dup(k.A[0]), L));
+    const float2 e1 = __ffma2_rn(c1, dup(k.A[4]), __ffma2_rn(c0, dup(k.A[1]), L));
+    const float2 e2 = __ffma2_rn(c1, dup(k.A[5]), __ffma2_rn(c0, dup(k.A[2]), L));
+    const float2 x0 = f2(ex2_approx(e0.x), ex2_approx(e0.y));
+    const float2 x1 = f2(ex2_approx(e1.x), ex2_approx(e1.y));
+    const float2 x2 = f2(ex2_approx(e2.x), ex2_approx(e2.y));
+    if (!CHECK) {
+        const float2 MAGIC = dup(8388608.f);
+        const float2 r0 = __fadd2_rd(x0, MAGIC), r1 = __fadd2_rd(x1, MAGIC), r2 = __fadd2_rd(x2, MAGIC);
+        bits[0] = __float_as_uint(r0.x); bits[1] = __float_as_uint(r1.x); bits[2] = __float_as_uint(r2.x);
+        bits[3] = __float_as_uint(r0.y); bits[4] = __float_as_uint(r1.y); bits[5] = __float_as_uint(r2.y);
+    } else {
+        bits[0] = wrap_u8_bits(x0.x); bits[1] = wrap_u8_bits(x1.x); bits[2] = wrap_u8_bits(x2.x);
+        bits[3] = wrap_u8_bits(x0.y); bits[4] = wrap_u8_bits(x1.y); bits[5] = wrap_u8_bits(x2.y);
+    }
+}
+
+
+__device__ __forceinline__ void fill_od_rep(unsigned char* od_rep, const float* od, int nthreads) {
+    for (int i = threadIdx.x; i < 256 * 32; i += nthreads)
+        *reinterpret_cast<float*>(od_rep + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = od[i >> 5];
+}
+
+// Fills the recombine constants from a source matrix, the per-stain scale and the target matrix (all fp64).
+__device__ inline void make_k4_consts(const double M[6], double lam, const double scale[2], const double Mt[6], K4Consts& k) {
+    LassoK lk;
+    make_lasso_consts(M, lam, lk);
+    k.m[0] = lk.m00; k.m[1] = lk.m01; k.m[2] = lk.m02; k.m[3] = lk.m10; k.m[4] = lk.m11; k.m[5] = lk.m12;
+    k.nlam = -lk.lam; k.i00 = lk.i00; k.i01 = lk.i01; k.i11 = lk.i11; k.rg00 = lk.rg00; k.rg11 = lk.rg11; k.g01 = lk.g01;
+    k.unit_diag = (lk.rg00 == 1.0f && lk.rg11 == 1.0f) ? 1 : 0;
+    const double LOG2E = 1.4426950408889634;
+    bool finite = true, need = false;
+    for (int j = 0; j < 2; ++j) {
+        finite = finite && isfinite(scale[j]);
+        for (int c = 0; c < 3; ++c) {
+            const double v = -scale[j] * Mt[3 * j + c] * LOG2E;
+            k.A[3 * j + c] = (float)v;
+            need = need || !(v <= 0.0);
+        }
+    }
+    k.need_check = need ? 1 : 0;
+    k.mode = finite ? 0 : 1;
+}
+
+// 16 pixels (12 packed words) -> 16 recombined pixels.
+template <bool CHECK, bool UNIT>
+__device__ __forceinline__ void recombine_words(const K4Consts& k, const unsigned char* tab, const uint32_t (&w)[12], uint32_t (&o)[12], uint32_t lane_off) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
+        // pixels: p0=(a0,a1,a2) p1=(a3,b0,b1) p2=(b2,b3,c0) p3=(c1,c2,c3)
+        uint32_t b01[6], b23[6];
+        recombine_pair<CHECK, UNIT>(k, f2(od_lookup(tab, wa, lane_off, 0), od_lookup(tab, wa, lane_off, 3)),
+                                    f2(od_lookup(tab, wa, lane_off, 1), od_lookup(tab, wb, lane_off, 0)),
+                                    f2(od_lookup(tab, wa, lane_off, 2), od_lookup(tab, wb, lane_off, 1)), b01);
+        recombine_pair<CHECK, UNIT>(k, f2(od_lookup(tab, wb, lane_off, 2), od_lookup(tab, wc, lane_off, 1)),
+                                    f2(od_lookup(tab, wb, lane_off, 3), od_lookup(tab, wc, lane_off, 2)),
+                                    f2(od_lookup(tab, wc, lane_off, 0), od_lookup(tab, wc, lane_off, 3)), b23);
+        o[3 * q] = pack4(b01[0], b01[1], b01[2], b01[3]);
+        o[3 * q + 1] = pack4(b01[4], b01[5], b23[0], b23[1]);
+        o[3 * q + 2] = pack4(b23[2], b23[3], b23[4], b23[5]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ selection keys
 // Monotone 23-bit key of the angle atan2(y, x): the "diamond angle" d in [-2,2] mapped to t = d/4 + 1.5 in [1,2];
 // key = mantissa bits of t.  Exact order statistics of the key give the order statistics of the angle.

@@ -64,9 +64,9 @@ struct PointArgs {
     int32_t* status;
 };
 int launch_mask(const PointArgs& a, int num_sms, cudaStream_t stream);
-int launch_recombine(const PointArgs& a, int num_sms, cudaStream_t stream);
-int launch_recombine_v2(const PointArgs& a, int num_sms, cudaStream_t stream);
-int launch_recombine_tma(const PointArgs& a, int num_sms, cudaStream_t stream);
+int launch_recombine(const PointArgs& a, int num_sms, cudaStream_t stream, bool use_tma);
+int launch_recombine_normalize(const PointArgs& a, int num_sms, cudaStream_t stream, bool use_tma, const double* M_src,
+                               const double* maxC_src, const double* Mt, const double* maxCt, int32_t* status);
 int launch_stain_augment(const PointArgs& a, int num_sms, cudaStream_t stream);
 int launch_concentrations(const PointArgs& a, int num_sms, cudaStream_t stream);
 

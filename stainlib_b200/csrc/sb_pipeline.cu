@@ -13,10 +13,14 @@
 //   common (stain_utils.py:69-78, normalizer.py:46-50)
 //     C1  closed-form non-negative LASSO concentrations of ALL pixels -> two 4096-bin histograms
 //     C2  11-bit refinement                                              -> exact 99th percentiles (maxC)
-//     D   recombine with the target matrix, 255*exp(.), unclipped uint8 wrap, 16-byte stores
+//     D   recombine with the target matrix: the TMA-ring K4 kernel of sb_recombine.cu, launched right behind this
+//         kernel on the same stream with the per-tile statistics computed here (sb_normalize = this kernel + K4)
 //
-// Every pass re-reads the tile with 16-byte vector loads; the working set of all in-flight tiles is sized to stay in
-// the 126 MB L2 (cluster size is chosen by the host), so HBM sees ~3 B/px in and 3 B/px out.  Cross-CTA reductions
+// Every pass re-reads the tile with 16-byte vector loads.  Instruction issue, not HBM, bounds this kernel, so the
+// passes are built to minimise instructions: the OD table is replicated per lane with 256-byte rows (one PRMT makes
+// the lookup offset, no bank conflicts), the tissue mask is computed once (pass A) and kept as one bit per pixel in
+// the unused half of those rows, the ragged last group is peeled off so the main loops carry no validity checks, and
+// the final pass is the packed f32x2 recombine of sb_recombine.cu.  Cross-CTA reductions
 // (moments, histograms) go through distributed shared memory; every CTA of a cluster redundantly evaluates the small
 // serial steps (eigenvectors, selections) so no broadcast is needed and results are bit-identical.
 #include "sb_kernels.h"
@@ -25,7 +29,6 @@ namespace sb {
 
 struct __align__(16) PipeShared {
     unsigned hist[2 * L1_BINS];      // 32 KB: 2 x 4096 (level 1) or 4 x 2048 (level 2)
-    float od[256];
     float gy[3 * 256];
     double red[NWARP][10];
     double part[2][12];              // this CTA's partial sums (double-buffered; read by cluster peers)
@@ -36,8 +39,6 @@ struct __align__(16) PipeShared {
     int n_distinct;
     float V[6];
     LassoK lk;
-    float A[6];
-    float need_check;
     int flags;
     double D[6];                     // Vahadane dictionary, rows = atoms
     double Msrc[6];
@@ -144,20 +145,65 @@ __device__ inline void plan_level2(PipeShared* sh, const unsigned src[4]) {
     sh->n_distinct = nd;
 }
 
-// Runs f over this CTA's share of the tile.  f(w, nvalid, g) sees the raw 12 words of one 16-pixel group.
-template <class F>
+// Runs f over this CTA's share [gb, ge) of the tile's 16-pixel groups.  Complete groups go through the main loop with
+// TAIL = false_type (no validity checks); the single ragged group of a tile whose pixel count is not a multiple of 16
+// is handled by one thread with TAIL = true_type.  f(tail, w, nvalid, g) sees the raw 12 words of the group.
+struct NoTail { static constexpr bool value = false; };
+struct IsTail { static constexpr bool value = true; };
+
+template <bool KEEP, class F>
 __device__ __forceinline__ void for_each_group(const uint8_t* __restrict__ tile, int npx, int gb, int ge, bool aligned, F&& f) {
-    for (int g = gb + threadIdx.x; g < ge; g += NT) {
+    const int nfull = npx / GROUP_PX;
+    const int fe = ge < nfull ? ge : nfull;
+    for (int g = gb + threadIdx.x; g < fe; g += NT) {
         uint32_t w[12];
         int nvalid;
-        load_group<true>(tile, npx, g, aligned, w, nvalid);
-        f(w, nvalid, g);
+        load_group<KEEP>(tile, npx, g, aligned, w, nvalid);
+        f(NoTail{}, w, GROUP_PX, g);
+    }
+    if (ge > nfull && threadIdx.x == 0) {
+        uint32_t w[12];
+        int nvalid;
+        load_group<KEEP>(tile, npx, nfull, false, w, nvalid);
+        f(IsTail{}, w, nvalid, nfull);
+    }
+}
+
+// One bit per pixel of the tissue mask, 16 bits per group, stored in bytes 128..255 of the OD-table rows.
+__device__ __forceinline__ unsigned short* mask_slot(unsigned char* od_rep, int gl) {
+    return reinterpret_cast<unsigned short*>(od_rep + ((gl >> 6) << 8) + 128 + ((gl & 63) << 1));
+}
+
+// 16-bit tissue mask of a group from the pre-weighted luminance tables (integer-exact collapse of cv2's L channel).
+template <bool TAIL>
+__device__ __forceinline__ uint32_t mask16(const uint32_t (&w)[12], const float* gyR, const float* gyG, const float* gyB, float ybound, int nvalid) {
+    uint32_t mbits = 0;
+    for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
+        const float y = gyR[r] + gyG[g] + gyB[b];
+        const bool m = TAIL ? ((y < ybound) & (i < nvalid)) : (y < ybound);
+        mbits |= m ? (1u << i) : 0u;
+    });
+    return mbits;
+}
+constexpr int MASK_CAP_GROUPS = 256 * 64;   // 16-bit slots available in the table rows = 262,144 pixels per CTA
+
+// OD of the three channels of the 16 pixels of a group through the replicated table: calls f(i, od_r, od_g, od_b).
+template <class F>
+__device__ __forceinline__ void for_each_px_od(const unsigned char* tab, uint32_t lane_off, const uint32_t (&w)[12], F&& f) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        f(4 * q + 0, od_lookup(tab, a, lane_off, 0), od_lookup(tab, a, lane_off, 1), od_lookup(tab, a, lane_off, 2));
+        f(4 * q + 1, od_lookup(tab, a, lane_off, 3), od_lookup(tab, b, lane_off, 0), od_lookup(tab, b, lane_off, 1));
+        f(4 * q + 2, od_lookup(tab, b, lane_off, 2), od_lookup(tab, b, lane_off, 3), od_lookup(tab, c, lane_off, 0));
+        f(4 * q + 3, od_lookup(tab, c, lane_off, 1), od_lookup(tab, c, lane_off, 2), od_lookup(tab, c, lane_off, 3));
     }
 }
 
 __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PipeShared* sh = reinterpret_cast<PipeShared*>(smem_raw);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* od_rep = smem_raw;                                        // 64 KB: OD table + mask bits
+    PipeShared* sh = reinterpret_cast<PipeShared*>(smem_raw + OD_REP_BYTES);
     const int S = a.cluster_size;
     const int crank = S > 1 ? (int)cg::this_cluster().block_rank() : 0;
     const int cluster_id = blockIdx.x / S, n_clusters = gridDim.x / S;
@@ -167,11 +213,12 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
     const size_t tile_bytes = (size_t)npx * 3;
     const bool aligned = a.aligned != 0;
     const float ybound = a.ybound;
+    const uint32_t lane_off = (threadIdx.x & 31) << 2;
+    const bool cache_mask = (ge - gb) <= MASK_CAP_GROUPS;   // else the mask is recomputed in every pass that needs it
 
-    for (int i = threadIdx.x; i < 256; i += NT) sh->od[i] = a.tab.od[i];
+    fill_od_rep(od_rep, a.tab.od, NT);
     for (int i = threadIdx.x; i < 768; i += NT) sh->gy[i] = a.tab.gy[i];
     __syncthreads();
-    const float* od = sh->od;
     const float* gyR = sh->gy, *gyG = sh->gy + 256, *gyB = sh->gy + 512;
     int pbuf = 0;   // parity of sh->part
 
@@ -186,19 +233,24 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) acc[i] = 0.0;
             unsigned cnt = 0;
-            for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
+            for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                constexpr bool TAIL = decltype(tail)::value;
                 float f[9];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) f[i] = 0.f;
-                for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
-                    const float y = gyR[r] + gyG[g] + gyB[b];
-                    const bool m = (y < ybound) & (i < nvalid);
-                    const float o0 = m ? od[r] : 0.f, o1 = m ? od[g] : 0.f, o2 = m ? od[b] : 0.f;
-                    cnt += m ? 1u : 0u;
+                uint32_t mbits = 0;
+                for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
+                    const float y = gyR[r] + gyG[gg] + gyB[b];
+                    const bool m = TAIL ? ((y < ybound) & (i < nvalid)) : (y < ybound);
+                    const float* row = reinterpret_cast<const float*>(od_rep + lane_off);
+                    const float o0 = m ? row[r * 64] : 0.f, o1 = m ? row[gg * 64] : 0.f, o2 = m ? row[b * 64] : 0.f;
+                    mbits |= m ? (1u << i) : 0u;
                     f[0] += o0; f[1] += o1; f[2] += o2;
                     f[3] = fmaf(o0, o0, f[3]); f[4] = fmaf(o0, o1, f[4]); f[5] = fmaf(o0, o2, f[5]);
                     f[6] = fmaf(o1, o1, f[6]); f[7] = fmaf(o1, o2, f[7]); f[8] = fmaf(o2, o2, f[8]);
                 });
+                cnt += __popc(mbits);
+                if (cache_mask) *mask_slot(od_rep, g - gb) = (unsigned short)mbits;
 #pragma unroll
                 for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
             });
@@ -242,15 +294,13 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                 // -------------------------------------------------------------- B1: angle histogram (tissue pixels)
                 zero_hist(sh);
                 const float v00 = sh->V[0], v01 = sh->V[1], v02 = sh->V[2], v10 = sh->V[3], v11 = sh->V[4], v12 = sh->V[5];
-                for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
-                    for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
-                        const float y = gyR[r] + gyG[g] + gyB[b];
-                        const bool m = (y < ybound) & (i < nvalid);
-                        const float o0 = od[r], o1 = od[g], o2 = od[b];
+                for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                    const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                    for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                         const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
                         const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
                         const uint32_t key = angle_key(px, py);
-                        if (m) atomicAdd(&sh->hist[key >> L2_BITS], 1u);
+                        if (mbits & (1u << i)) atomicAdd(&sh->hist[key >> L2_BITS], 1u);
                     });
                 });
                 if (threadIdx.x == 0) {
@@ -271,16 +321,14 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                 {
                     const int nd = sh->n_distinct;
                     const unsigned b0 = sh->d_bin[0], b1 = sh->d_bin[1], b2 = sh->d_bin[2], b3 = sh->d_bin[3];
-                    for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
-                        for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
-                            const float y = gyR[r] + gyG[g] + gyB[b];
-                            const bool m = (y < ybound) & (i < nvalid);
-                            const float o0 = od[r], o1 = od[g], o2 = od[b];
+                    for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                        const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                        for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                             const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
                             const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
                             const uint32_t key = angle_key(px, py);
                             const uint32_t bin = key >> L2_BITS, low = key & (L2_BINS - 1);
-                            if (m) {
+                            if (mbits & (1u << i)) {
                                 if (bin == b0) atomicAdd(&sh->hist[low], 1u);
                                 if (nd > 1 && bin == b1) atomicAdd(&sh->hist[L2_BINS + low], 1u);
                                 if (nd > 2 && bin == b2) atomicAdd(&sh->hist[2 * L2_BINS + low], 1u);
@@ -328,24 +376,29 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                 make_lasso_consts(sh->D, a.dl_lambda, sh->lk);
             }
             __syncthreads();
+            // V0: tissue mask -> one bit per pixel (reused by every iteration)
+            unsigned cnt_tissue = 0;
+            for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                const uint32_t mbits = mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                cnt_tissue += __popc(mbits);
+                if (cache_mask) *mask_slot(od_rep, g - gb) = (unsigned short)mbits;
+            });
             for (int it = 0; it < a.dl_iters; ++it) {
                 const LassoK lk = sh->lk;
                 double acc[9];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) acc[i] = 0.0;
-                unsigned cnt = 0;
-                for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
+                const unsigned cnt = cnt_tissue;
+                for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                    const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
                     float f[9];
 #pragma unroll
                     for (int i = 0; i < 9; ++i) f[i] = 0.f;
-                    for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
-                        const float y = gyR[r] + gyG[g] + gyB[b];
-                        const bool m = (y < ybound) & (i < nvalid);
-                        const float o0 = od[r], o1 = od[g], o2 = od[b];
+                    for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                         float c0, c1;
                         lasso2(lk, o0, o1, o2, c0, c1);
+                        const bool m = (mbits & (1u << i)) != 0;
                         c0 = m ? c0 : 0.f; c1 = m ? c1 : 0.f;
-                        cnt += m ? 1u : 0u;
                         f[0] = fmaf(c0, c0, f[0]); f[1] = fmaf(c0, c1, f[1]); f[2] = fmaf(c1, c1, f[2]);
                         f[3] = fmaf(o0, c0, f[3]); f[4] = fmaf(o1, c0, f[4]); f[5] = fmaf(o2, c0, f[5]);
                         f[6] = fmaf(o0, c1, f[6]); f[7] = fmaf(o1, c1, f[7]); f[8] = fmaf(o2, c1, f[8]);
@@ -407,11 +460,12 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
             if (threadIdx.x == 0) make_lasso_consts(sh->Msrc, a.lasso_lambda, sh->lk);
             zero_hist(sh);
             const LassoK lk = sh->lk;
-            for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
-                for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
+            for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int) {
+                constexpr bool TAIL = decltype(tail)::value;
+                for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                     float c0, c1;
-                    lasso2(lk, od[r], od[g], od[b], c0, c1);
-                    if (i < nvalid) {
+                    lasso2(lk, o0, o1, o2, c0, c1);
+                    if (!TAIL || i < nvalid) {
                         atomicAdd(&sh->hist[conc_key(c0) >> L2_BITS], 1u);
                         atomicAdd(&sh->hist[L1_BINS + (conc_key(c1) >> L2_BITS)], 1u);
                     }
@@ -435,12 +489,13 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                 const int nd = sh->n_distinct;
                 const unsigned b0 = sh->d_bin[0], b1 = sh->d_bin[1], b2 = sh->d_bin[2], b3 = sh->d_bin[3];
                 const unsigned s0 = sh->d_src[0], s1 = sh->d_src[1], s2 = sh->d_src[2], s3 = sh->d_src[3];
-                for_each_group(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], int nvalid, int) {
-                    for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
+                for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int) {
+                    constexpr bool TAIL = decltype(tail)::value;
+                    for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                         float c0, c1;
-                        lasso2(lk, od[r], od[g], od[b], c0, c1);
+                        lasso2(lk, o0, o1, o2, c0, c1);
                         const uint32_t k0 = conc_key(c0), k1 = conc_key(c1);
-                        if (i < nvalid) {
+                        if (!TAIL || i < nvalid) {
                             { const uint32_t k = s0 ? k1 : k0; if ((k >> L2_BITS) == b0) atomicAdd(&sh->hist[k & (L2_BINS - 1)], 1u); }
                             if (nd > 1) { const uint32_t k = s1 ? k1 : k0; if ((k >> L2_BITS) == b1) atomicAdd(&sh->hist[L2_BINS + (k & (L2_BINS - 1))], 1u); }
                             if (nd > 2) { const uint32_t k = s2 ? k1 : k0; if ((k >> L2_BITS) == b2) atomicAdd(&sh->hist[2 * L2_BINS + (k & (L2_BINS - 1))], 1u); }
@@ -467,74 +522,6 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
             a.maxC_out[(size_t)tile * 2] = a.maxC_out[(size_t)tile * 2 + 1] = __longlong_as_double(0x7ff8000000000000LL);
         }
 
-        if (a.mode == PIPE_NORMALIZE) {
-            // ------------------------------------------------------------------ D: recombine + store
-            uint8_t* __restrict__ tout = a.out + (size_t)tile * tile_bytes;
-            if (threadIdx.x == 0 && sh->flags == 0) {
-                const double LOG2E = 1.4426950408889634;
-                float need = 0.f;
-                bool finite = true;
-                for (int j = 0; j < 2; ++j) {
-                    const double s = a.maxCt[j] / sh->maxC[j];
-                    finite = finite && isfinite(s);
-                    for (int k = 0; k < 3; ++k) {
-                        const double v = -s * a.Mt[3 * j + k] * LOG2E;
-                        sh->A[3 * j + k] = (float)v;
-                        if (v > 0.0) need = 1.f;
-                    }
-                }
-                sh->need_check = need;
-                if (!finite) sh->flags |= SB_STATUS_ZERO_MAXC;
-            }
-            __syncthreads();
-            const int flags = sh->flags;
-            if (flags == 0) {
-                const LassoK lk = sh->lk;
-                const float a00 = sh->A[0], a01 = sh->A[1], a02 = sh->A[2], a10 = sh->A[3], a11 = sh->A[4], a12 = sh->A[5];
-                const float L255 = LOG2_255_UP;
-                for (int g = gb + threadIdx.x; g < ge; g += NT) {
-                    uint32_t w[12], o[12];
-                    int nvalid;
-                    load_group<false>(tin, npx, g, aligned, w, nvalid);
-                    uint32_t bits[12];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
-                        const uint32_t rr[4] = {byte_of(wa, 0), byte_of(wa, 3), byte_of(wb, 2), byte_of(wc, 1)};
-                        const uint32_t gg[4] = {byte_of(wa, 1), byte_of(wb, 0), byte_of(wb, 3), byte_of(wc, 2)};
-                        const uint32_t bb[4] = {byte_of(wa, 2), byte_of(wb, 1), byte_of(wc, 0), byte_of(wc, 3)};
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            float c0, c1;
-                            lasso2(lk, od[rr[p]], od[gg[p]], od[bb[p]], c0, c1);
-                            const float e0 = fmaf(c1, a10, fmaf(c0, a00, L255));
-                            const float e1 = fmaf(c1, a11, fmaf(c0, a01, L255));
-                            const float e2 = fmaf(c1, a12, fmaf(c0, a02, L255));
-                            bits[3 * p] = wrap_u8_bits(ex2_approx(e0));
-                            bits[3 * p + 1] = wrap_u8_bits(ex2_approx(e1));
-                            bits[3 * p + 2] = wrap_u8_bits(ex2_approx(e2));
-                        }
-                        o[3 * q] = pack4(bits[0], bits[1], bits[2], bits[3]);
-                        o[3 * q + 1] = pack4(bits[4], bits[5], bits[6], bits[7]);
-                        o[3 * q + 2] = pack4(bits[8], bits[9], bits[10], bits[11]);
-                    }
-                    store_group(tout, npx, g, aligned, o);
-                }
-            } else {
-                // flagged tile: zeros where the reference divides by zero, otherwise the input is passed through
-                const bool zeros = (flags & SB_STATUS_ZERO_MAXC) != 0 && (flags & ~SB_STATUS_ZERO_MAXC) == 0;
-                for (int g = gb + threadIdx.x; g < ge; g += NT) {
-                    uint32_t w[12];
-                    int nvalid;
-                    load_group<false>(tin, npx, g, aligned, w, nvalid);
-                    if (zeros) {
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) w[i] = 0;
-                    }
-                    store_group(tout, npx, g, aligned, w);
-                }
-            }
-        }
         if (threadIdx.x == 0 && crank == 0 && a.status) a.status[tile] = sh->flags;
         tile_sync(S);   // protects sh->flags / histograms of the next tile from slow peers
     }
@@ -542,7 +529,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
 
 int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
-    const size_t smem = sizeof(PipeShared);
+    const size_t smem = OD_REP_BYTES + sizeof(PipeShared);
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tile_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;

@@ -1,7 +1,7 @@
 // sb_pointwise.cu -- per-pixel kernels that need no per-tile reduction (sm_100a).
 //
 //   mask_kernel            LuminosityThresholdTissueLocator.get_tissue_mask   stain_utils.py:32-48
-//   recombine_kernel (K4)  normalizer.py:46,48-50: OD LUT -> closed-form LASSO -> scale -> 2x3 mat-vec -> 255*exp -> u8
+//   (K4, the fused OD+recombine kernel, lives in sb_recombine.cu)
 //   stain_augment_kernel   StainAugmentor.pop                                  augmenter.py:428-449
 //   concentrations_kernel  get_concentrations                                  stain_utils.py:69-78
 //
@@ -65,59 +65,6 @@ __global__ void __launch_bounds__(PT) mask_kernel(PointArgs a) {
     __syncthreads();
     // status was preset to EMPTY_MASK by the host; any CTA that saw tissue clears it
     if (threadIdx.x == 0 && any && a.status) atomicAnd(&a.status[tile], ~SB_STATUS_EMPTY_MASK);
-}
-
-__global__ void __launch_bounds__(PT, 4) recombine_kernel(PointArgs a) {
-    __shared__ PointShared sh;
-    load_tables(&sh, a.tab, false);
-    const int tile = blockIdx.x;
-    if (threadIdx.x == 0) {
-        double M[6];
-        for (int k = 0; k < 6; ++k) M[k] = a.M[(size_t)tile * 6 + k];
-        make_lasso_consts(M, a.lasso_lambda, sh.lk);
-        const double LOG2E = 1.4426950408889634;
-        bool finite = true;
-        for (int j = 0; j < 2; ++j) {
-            const double s = a.scale[(size_t)tile * 2 + j];
-            finite = finite && isfinite(s);
-            for (int k = 0; k < 3; ++k) sh.A[3 * j + k] = (float)(-s * a.Mt[3 * j + k] * LOG2E);
-        }
-        sh.zero_out = finite ? 0 : 1;
-    }
-    __syncthreads();
-    const uint8_t* tin = a.in + (size_t)tile * a.npx * 3;
-    uint8_t* tout = a.out + (size_t)tile * a.npx * 3;
-    const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
-    const LassoK lk = sh.lk;
-    const float a00 = sh.A[0], a01 = sh.A[1], a02 = sh.A[2], a10 = sh.A[3], a11 = sh.A[4], a12 = sh.A[5];
-    const float L255 = LOG2_255_UP;
-    const bool zero_out = sh.zero_out != 0;
-    const float* od = sh.od;
-    for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < G; g += gridDim.y * blockDim.x) {
-        uint32_t w[12], o[12];
-        int nvalid;
-        load_group<false>(tin, a.npx, g, a.aligned != 0, w, nvalid);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
-            const uint32_t rr[4] = {byte_of(wa, 0), byte_of(wa, 3), byte_of(wb, 2), byte_of(wc, 1)};
-            const uint32_t gg[4] = {byte_of(wa, 1), byte_of(wb, 0), byte_of(wb, 3), byte_of(wc, 2)};
-            const uint32_t bb[4] = {byte_of(wa, 2), byte_of(wb, 1), byte_of(wc, 0), byte_of(wc, 3)};
-            uint32_t bits[12];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                float c0, c1;
-                lasso2(lk, od[rr[p]], od[gg[p]], od[bb[p]], c0, c1);
-                bits[3 * p] = wrap_u8_bits(ex2_approx(fmaf(c1, a10, fmaf(c0, a00, L255))));
-                bits[3 * p + 1] = wrap_u8_bits(ex2_approx(fmaf(c1, a11, fmaf(c0, a01, L255))));
-                bits[3 * p + 2] = wrap_u8_bits(ex2_approx(fmaf(c1, a12, fmaf(c0, a02, L255))));
-            }
-            o[3 * q] = zero_out ? 0u : pack4(bits[0], bits[1], bits[2], bits[3]);
-            o[3 * q + 1] = zero_out ? 0u : pack4(bits[4], bits[5], bits[6], bits[7]);
-            o[3 * q + 2] = zero_out ? 0u : pack4(bits[8], bits[9], bits[10], bits[11]);
-        }
-        store_group(tout, a.npx, g, a.aligned != 0, o);
-    }
 }
 
 __global__ void __launch_bounds__(PT, 4) stain_augment_kernel(PointArgs a) {
@@ -213,10 +160,6 @@ static dim3 point_grid(const PointArgs& a, int num_sms, int ctas_per_sm) {
 
 int launch_mask(const PointArgs& a, int num_sms, cudaStream_t stream) {
     mask_kernel<<<point_grid(a, num_sms, 8), PT, 0, stream>>>(a);
-    return (int)cudaGetLastError();
-}
-int launch_recombine(const PointArgs& a, int num_sms, cudaStream_t stream) {
-    recombine_kernel<<<point_grid(a, num_sms, 4), PT, 0, stream>>>(a);
     return (int)cudaGetLastError();
 }
 int launch_stain_augment(const PointArgs& a, int num_sms, cudaStream_t stream) {

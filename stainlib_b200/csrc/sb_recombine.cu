@@ -15,68 +15,6 @@
 namespace sb {
 
 constexpr int RT = 256;                       // threads per CTA
-constexpr int OD_ROW_BYTES = 256;             // row stride of the lane-replicated OD table
-constexpr int OD_REP_BYTES = 256 * OD_ROW_BYTES;
-
-struct __align__(16) K4Consts {
-    float m[6];      // source stain matrix rows
-    float nlam;      // -lambda
-    float i00, i01, i11;
-    float rg00, rg11, g01;
-    float A[6];      // -scale_j * Mt_jk * log2(e)
-    int unit_diag, need_check, zero_out;
-};
-
-__device__ __forceinline__ float od_lookup(const unsigned char* tab, uint32_t w, uint32_t lane_off, int k) {
-    // offset = (byte k of w) << 8 | lane << 2 : one PRMT
-    const uint32_t off = __byte_perm(w, lane_off, 0x6504u | (k << 4));
-    return *reinterpret_cast<const float*>(tab + off);
-}
-
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
-
-template <bool CHECK, bool UNIT>
-__device__ __forceinline__ void recombine_pair(const K4Consts& k, const float2 o0, const float2 o1, const float2 o2, uint32_t (&bits)[6]) {
-    const float2 u0 = __ffma2_rn(dup(k.m[2]), o2, __ffma2_rn(dup(k.m[1]), o1, __ffma2_rn(dup(k.m[0]), o0, dup(k.nlam))));
-    const float2 u1 = __ffma2_rn(dup(k.m[5]), o2, __ffma2_rn(dup(k.m[4]), o1, __ffma2_rn(dup(k.m[3]), o0, dup(k.nlam))));
-    const float2 a0 = __ffma2_rn(dup(k.i01), u1, __fmul2_rn(dup(k.i00), u0));
-    const float2 a1 = __ffma2_rn(dup(k.i11), u1, __fmul2_rn(dup(k.i01), u0));
-    float2 c0, c1;
-    if (UNIT) {
-        const float x0a = fmaxf(u0.x, 0.f), x1a = fmaxf(u1.x, 0.f), x0b = fmaxf(u0.y, 0.f), x1b = fmaxf(u1.y, 0.f);
-        const bool ba = (a0.x > 0.f) & (a1.x > 0.f), bb = (a0.y > 0.f) & (a1.y > 0.f);
-        const bool pa = x0a >= x1a, pb = x0b >= x1b;
-        c0.x = ba ? a0.x : (pa ? x0a : 0.f); c1.x = ba ? a1.x : (pa ? 0.f : x1a);
-        c0.y = bb ? a0.y : (pb ? x0b : 0.f); c1.y = bb ? a1.y : (pb ? 0.f : x1b);
-    } else {
-        // general Gram diagonal: KKT form (same as lasso2 in sb_device.cuh)
-        const float p0a = fmaxf(u0.x, 0.f) * k.rg00, p1a = fmaxf(u1.x, 0.f) * k.rg11;
-        const float p0b = fmaxf(u0.y, 0.f) * k.rg00, p1b = fmaxf(u1.y, 0.f) * k.rg11;
-        const bool ba = (a0.x > 0.f) & (a1.x > 0.f), bb = (a0.y > 0.f) & (a1.y > 0.f);
-        const bool o0a = (p0a > 0.f) & (fmaf(-k.g01, p0a, u1.x) <= 0.f), o1a = (p1a > 0.f) & (fmaf(-k.g01, p1a, u0.x) <= 0.f);
-        const bool o0b = (p0b > 0.f) & (fmaf(-k.g01, p0b, u1.y) <= 0.f), o1b = (p1b > 0.f) & (fmaf(-k.g01, p1b, u0.y) <= 0.f);
-        c0.x = ba ? a0.x : (o0a ? p0a : 0.f); c1.x = ba ? a1.x : ((!o0a & o1a) ? p1a : 0.f);
-        c0.y = bb ? a0.y : (o0b ? p0b : 0.f); c1.y = bb ? a1.y : ((!o0b & o1b) ? p1b : 0.f);
-    }
-    const float2 L = dup(LOG2_255_UP);
-    const float2 e0 = __ffma2_rn(c1, dup(k.A[3]), __ffma2_rn(c0, dup(k.A[0]), L));
-    const float2 e1 = __ffma2_rn(c1, dup(k.A[4]), __ffma2_rn(c0, dup(k.A[1]), L));
-    const float2 e2 = __ffma2_rn(c1, dup(k.A[5]), __ffma2_rn(c0, dup(k.A[2]), L));
-    const float2 x0 = f2(ex2_approx(e0.x), ex2_approx(e0.y));
-    const float2 x1 = f2(ex2_approx(e1.x), ex2_approx(e1.y));
-    const float2 x2 = f2(ex2_approx(e2.x), ex2_approx(e2.y));
-    if (!CHECK) {
-        const float2 MAGIC = dup(8388608.f);
-        const float2 r0 = __fadd2_rd(x0, MAGIC), r1 = __fadd2_rd(x1, MAGIC), r2 = __fadd2_rd(x2, MAGIC);
-        bits[0] = __float_as_uint(r0.x); bits[1] = __float_as_uint(r1.x); bits[2] = __float_as_uint(r2.x);
-        bits[3] = __float_as_uint(r0.y); bits[4] = __float_as_uint(r1.y); bits[5] = __float_as_uint(r2.y);
-    } else {
-        bits[0] = wrap_u8_bits(x0.x); bits[1] = wrap_u8_bits(x1.x); bits[2] = wrap_u8_bits(x2.x);
-        bits[3] = wrap_u8_bits(x0.y); bits[4] = wrap_u8_bits(x1.y); bits[5] = wrap_u8_bits(x2.y);
-    }
-}
-
 template <bool CHECK, bool UNIT>
 __device__ __forceinline__ void recombine_loop(const PointArgs& a, const K4Consts& k, const unsigned char* tab, int tile) {
     const uint8_t* __restrict__ tin = a.in + (size_t)tile * a.npx * 3;
@@ -88,63 +26,31 @@ __device__ __forceinline__ void recombine_loop(const PointArgs& a, const K4Const
         uint32_t w[12], o[12];
         int nvalid;
         load_group<false>(tin, a.npx, g, aligned, w, nvalid);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
-            // pixels: p0=(a0,a1,a2) p1=(a3,b0,b1) p2=(b2,b3,c0) p3=(c1,c2,c3)
-            uint32_t b01[6], b23[6];
-            recombine_pair<CHECK, UNIT>(k, f2(od_lookup(tab, wa, lane_off, 0), od_lookup(tab, wa, lane_off, 3)),
-                                        f2(od_lookup(tab, wa, lane_off, 1), od_lookup(tab, wb, lane_off, 0)),
-                                        f2(od_lookup(tab, wa, lane_off, 2), od_lookup(tab, wb, lane_off, 1)), b01);
-            recombine_pair<CHECK, UNIT>(k, f2(od_lookup(tab, wb, lane_off, 2), od_lookup(tab, wc, lane_off, 1)),
-                                        f2(od_lookup(tab, wb, lane_off, 3), od_lookup(tab, wc, lane_off, 2)),
-                                        f2(od_lookup(tab, wc, lane_off, 0), od_lookup(tab, wc, lane_off, 3)), b23);
-            o[3 * q] = pack4(b01[0], b01[1], b01[2], b01[3]);
-            o[3 * q + 1] = pack4(b01[4], b01[5], b23[0], b23[1]);
-            o[3 * q + 2] = pack4(b23[2], b23[3], b23[4], b23[5]);
-        }
+        recombine_words<CHECK, UNIT>(k, tab, w, o, lane_off);
         store_group(tout, a.npx, g, aligned, o);
     }
 }
 
-__global__ void __launch_bounds__(RT, 3) recombine_v2_kernel(PointArgs a) {
+__global__ void __launch_bounds__(RT, 3) recombine_v2_kernel(PointArgs a, const K4Consts* __restrict__ consts) {
     extern __shared__ __align__(256) unsigned char od_rep[];   // [256 values][64 words]; words 0..31 = lane copies
-    __shared__ K4Consts ks;
     const int tile = blockIdx.x;
-    for (int i = threadIdx.x; i < 256 * 32; i += RT)
-        *reinterpret_cast<float*>(od_rep + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = a.tab.od[i >> 5];
-    if (threadIdx.x == 0) {
-        double M[6];
-        for (int j = 0; j < 6; ++j) M[j] = a.M[(size_t)tile * 6 + j];
-        LassoK lk;
-        make_lasso_consts(M, a.lasso_lambda, lk);
-        ks.m[0] = lk.m00; ks.m[1] = lk.m01; ks.m[2] = lk.m02; ks.m[3] = lk.m10; ks.m[4] = lk.m11; ks.m[5] = lk.m12;
-        ks.nlam = -lk.lam; ks.i00 = lk.i00; ks.i01 = lk.i01; ks.i11 = lk.i11; ks.rg00 = lk.rg00; ks.rg11 = lk.rg11; ks.g01 = lk.g01;
-        ks.unit_diag = (lk.rg00 == 1.0f && lk.rg11 == 1.0f) ? 1 : 0;
-        const double LOG2E = 1.4426950408889634;
-        bool finite = true, need = false;
-        for (int j = 0; j < 2; ++j) {
-            const double s = a.scale[(size_t)tile * 2 + j];
-            finite = finite && isfinite(s);
-            for (int c = 0; c < 3; ++c) {
-                const double v = -s * a.Mt[3 * j + c] * LOG2E;
-                ks.A[3 * j + c] = (float)v;
-                need = need || !(v <= 0.0);
-            }
-        }
-        ks.need_check = need ? 1 : 0;
-        ks.zero_out = finite ? 0 : 1;
-    }
+    fill_od_rep(od_rep, a.tab.od, RT);
     __syncthreads();
-    const K4Consts k = ks;
-    if (k.zero_out) {
-        // reference: division by a zero 99th percentile -> inf/NaN -> uint8 0 everywhere (normalizer.py:48-50)
+    const K4Consts k = consts[tile];
+    if (k.mode != 0) {
+        const uint8_t* tin = a.in + (size_t)tile * a.npx * 3;
         uint8_t* tout = a.out + (size_t)tile * a.npx * 3;
         const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
-        uint32_t z[12];
+        for (int g = blockIdx.y * RT + threadIdx.x; g < G; g += gridDim.y * RT) {
+            uint32_t w[12];
+            int nvalid;
+            load_group<false>(tin, a.npx, g, a.aligned != 0, w, nvalid);
+            if (k.mode == 1) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) z[i] = 0;
-        for (int g = blockIdx.y * RT + threadIdx.x; g < G; g += gridDim.y * RT) store_group(tout, a.npx, g, a.aligned != 0, z);
+                for (int i = 0; i < 12; ++i) w[i] = 0;
+            }
+            store_group(tout, a.npx, g, a.aligned != 0, w);
+        }
         return;
     }
     if (k.need_check) {
@@ -189,30 +95,40 @@ __device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src,
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+// Per-tile constants for sb_recombine: source matrices + scales given by the caller.
 __global__ void k4_prepare_kernel(PointArgs a, K4Consts* out) {
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= a.B) return;
-    double M[6];
-    for (int j = 0; j < 6; ++j) M[j] = a.M[(size_t)tile * 6 + j];
-    LassoK lk;
-    make_lasso_consts(M, a.lasso_lambda, lk);
+    double M[6], Mt[6], sc[2];
+    for (int j = 0; j < 6; ++j) { M[j] = a.M[(size_t)tile * 6 + j]; Mt[j] = a.Mt[j]; }
+    sc[0] = a.scale[(size_t)tile * 2]; sc[1] = a.scale[(size_t)tile * 2 + 1];
     K4Consts k;
-    k.m[0] = lk.m00; k.m[1] = lk.m01; k.m[2] = lk.m02; k.m[3] = lk.m10; k.m[4] = lk.m11; k.m[5] = lk.m12;
-    k.nlam = -lk.lam; k.i00 = lk.i00; k.i01 = lk.i01; k.i11 = lk.i11; k.rg00 = lk.rg00; k.rg11 = lk.rg11; k.g01 = lk.g01;
-    k.unit_diag = (lk.rg00 == 1.0f && lk.rg11 == 1.0f) ? 1 : 0;
-    const double LOG2E = 1.4426950408889634;
-    bool finite = true, need = false;
-    for (int j = 0; j < 2; ++j) {
-        const double s = a.scale[(size_t)tile * 2 + j];
-        finite = finite && isfinite(s);
-        for (int c = 0; c < 3; ++c) {
-            const double v = -s * a.Mt[3 * j + c] * LOG2E;
-            k.A[3 * j + c] = (float)v;
-            need = need || !(v <= 0.0);
-        }
+    make_k4_consts(M, a.lasso_lambda, sc, Mt, k);
+    out[tile] = k;
+}
+
+// Per-tile constants for sb_normalize: source statistics from the fused pipeline kernel, target statistics from fit().
+// Flagged tiles: a zero / non-finite source percentile writes zeros like the reference's division by zero
+// (normalizer.py:48-50); tiles without a stain matrix (empty mask, < 2 tissue pixels, degenerate) are copied through.
+__global__ void k4_prepare_normalize_kernel(int B, const double* __restrict__ M_src, const double* __restrict__ maxC_src,
+                                            const double* __restrict__ Mt_dev, const double* __restrict__ maxCt, double lam,
+                                            int32_t* __restrict__ status, K4Consts* out) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= B) return;
+    K4Consts k;
+    const int st = status[tile];
+    if (st != 0) {
+        for (int j = 0; j < 6; ++j) { k.m[j] = 0.f; k.A[j] = 0.f; }
+        k.nlam = k.i00 = k.i01 = k.i11 = k.rg00 = k.rg11 = k.g01 = 0.f;
+        k.unit_diag = k.need_check = 0;
+        k.mode = 2;
+    } else {
+        double M[6], Mt[6], sc[2];
+        for (int j = 0; j < 6; ++j) { M[j] = M_src[(size_t)tile * 6 + j]; Mt[j] = Mt_dev[j]; }
+        sc[0] = maxCt[0] / maxC_src[(size_t)tile * 2]; sc[1] = maxCt[1] / maxC_src[(size_t)tile * 2 + 1];
+        make_k4_consts(M, lam, sc, Mt, k);
+        if (k.mode == 1) status[tile] = st | SB_STATUS_ZERO_MAXC;
     }
-    k.need_check = need ? 1 : 0;
-    k.zero_out = finite ? 0 : 1;
     out[tile] = k;
 }
 
@@ -221,20 +137,7 @@ __device__ __forceinline__ void recombine_group_smem(const K4Consts& k, const un
     const uint4 va = grp[0], vb = grp[1], vc = grp[2];
     const uint32_t w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
     uint32_t o[12];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
-        uint32_t b01[6], b23[6];
-        recombine_pair<CHECK, UNIT>(k, f2(od_lookup(tab, wa, lane_off, 0), od_lookup(tab, wa, lane_off, 3)),
-                                    f2(od_lookup(tab, wa, lane_off, 1), od_lookup(tab, wb, lane_off, 0)),
-                                    f2(od_lookup(tab, wa, lane_off, 2), od_lookup(tab, wb, lane_off, 1)), b01);
-        recombine_pair<CHECK, UNIT>(k, f2(od_lookup(tab, wb, lane_off, 2), od_lookup(tab, wc, lane_off, 1)),
-                                    f2(od_lookup(tab, wb, lane_off, 3), od_lookup(tab, wc, lane_off, 2)),
-                                    f2(od_lookup(tab, wc, lane_off, 0), od_lookup(tab, wc, lane_off, 3)), b23);
-        o[3 * q] = pack4(b01[0], b01[1], b01[2], b01[3]);
-        o[3 * q + 1] = pack4(b01[4], b01[5], b23[0], b23[1]);
-        o[3 * q + 2] = pack4(b23[2], b23[3], b23[4], b23[5]);
-    }
+    recombine_words<CHECK, UNIT>(k, tab, w, o, lane_off);
     grp[0] = make_uint4(o[0], o[1], o[2], o[3]);
     grp[1] = make_uint4(o[4], o[5], o[6], o[7]);
     grp[2] = make_uint4(o[8], o[9], o[10], o[11]);
@@ -309,7 +212,7 @@ __global__ void __launch_bounds__(TT + 32, 1) recombine_tma_kernel(PointArgs a, 
         int run = chunks_per_tile - first_in_tile;
         if (run > n_local - i) run = n_local - i;
         const K4Consts k = consts[tile];
-        const int variant = copy_only ? 5 : (k.zero_out ? 4 : (k.need_check ? 2 : 0) + (k.unit_diag ? 1 : 0));
+        const int variant = (copy_only || k.mode == 2) ? 5 : (k.mode == 1 ? 4 : (k.need_check ? 2 : 0) + (k.unit_diag ? 1 : 0));
         for (int j = 0; j < run; ++j, ++i) {
             const int s = i % NSTAGE;
             const uint32_t parity = (uint32_t)((i / NSTAGE) & 1);
@@ -355,24 +258,18 @@ static int launch_tma_variant(const PointArgs& a, int num_sms, cudaStream_t stre
     return (int)cudaGetLastError();
 }
 
-int launch_recombine_tma(const PointArgs& a, int num_sms, cudaStream_t stream) {
-    K4Consts* consts = nullptr;
-    cudaError_t e = cudaMallocAsync(&consts, (size_t)a.B * sizeof(K4Consts), stream);
-    if (e != cudaSuccess) return (int)e;
-    k4_prepare_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a, consts);
-    // ring geometry: 512 compute threads x 6 slots of 24 KB (chunks divide 256^2 and 512^2 tiles evenly); the sweep in
-    // profiles/r01_k4_ring_sweep.txt shows 512x6, 640x5 and 768x4 within 2 % of each other
-    static int variant = -1;
-    if (variant < 0) { const char* v = getenv("SB_K4_TT"); variant = v ? atoi(v) : 512; }
-    int rc;
-    if (variant == 640) rc = launch_tma_variant<640, 5>(a, num_sms, stream, consts);
-    else if (variant == 768) rc = launch_tma_variant<768, 4>(a, num_sms, stream, consts);
-    else rc = launch_tma_variant<512, 6>(a, num_sms, stream, consts);
-    cudaFreeAsync(consts, stream);
-    return rc;
-}
-
-int launch_recombine_v2(const PointArgs& a, int num_sms, cudaStream_t stream) {
+// Runs K4 over the batch with the given per-tile constants: TMA ring when every tile is a whole number of 16-byte
+// vectors at a 16-byte aligned address, register-staged kernel otherwise.
+static int launch_k4(const PointArgs& a, int num_sms, cudaStream_t stream, const K4Consts* consts, bool use_tma) {
+    if (use_tma) {
+        // ring geometry: 512 compute threads x 6 slots of 24 KB (chunks divide 256^2 and 512^2 tiles evenly); the sweep in
+        // profiles/r01_k4_ring_sweep.txt shows 512x6, 640x5 and 768x4 within 2 % of each other
+        static int variant = -1;
+        if (variant < 0) { const char* v = getenv("SB_K4_TT"); variant = v ? atoi(v) : 512; }
+        if (variant == 640) return launch_tma_variant<640, 5>(a, num_sms, stream, consts);
+        if (variant == 768) return launch_tma_variant<768, 4>(a, num_sms, stream, consts);
+        return launch_tma_variant<512, 6>(a, num_sms, stream, consts);
+    }
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(recombine_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OD_REP_BYTES);
@@ -386,8 +283,29 @@ int launch_recombine_v2(const PointArgs& a, int num_sms, cudaStream_t stream) {
     if (want < 1) want = 1;
     if (spans > want) spans = want;
     if (spans < 1) spans = 1;
-    recombine_v2_kernel<<<dim3(a.B, spans), RT, OD_REP_BYTES, stream>>>(a);
+    recombine_v2_kernel<<<dim3(a.B, spans), RT, OD_REP_BYTES, stream>>>(a, consts);
     return (int)cudaGetLastError();
+}
+
+int launch_recombine(const PointArgs& a, int num_sms, cudaStream_t stream, bool use_tma) {
+    K4Consts* consts = nullptr;
+    cudaError_t e = cudaMallocAsync(&consts, (size_t)a.B * sizeof(K4Consts), stream);
+    if (e != cudaSuccess) return (int)e;
+    k4_prepare_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a, consts);
+    const int rc = launch_k4(a, num_sms, stream, consts, use_tma);
+    cudaFreeAsync(consts, stream);
+    return rc;
+}
+
+int launch_recombine_normalize(const PointArgs& a, int num_sms, cudaStream_t stream, bool use_tma, const double* M_src,
+                               const double* maxC_src, const double* Mt, const double* maxCt, int32_t* status) {
+    K4Consts* consts = nullptr;
+    cudaError_t e = cudaMallocAsync(&consts, (size_t)a.B * sizeof(K4Consts), stream);
+    if (e != cudaSuccess) return (int)e;
+    k4_prepare_normalize_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a.B, M_src, maxC_src, Mt, maxCt, a.lasso_lambda, status, consts);
+    const int rc = launch_k4(a, num_sms, stream, consts, use_tma);
+    cudaFreeAsync(consts, stream);
+    return rc;
 }
 
 }  // namespace sb

@@ -190,3 +190,17 @@ def test_full_size_properties(sb):
     ref = so.recombine(tile, so.macenko_stain_matrix(tile), [1.0, 1.0], so.macenko_stain_matrix(tile))
     mx, frac = lsb_stats(out[0].cpu().numpy(), ref)
     assert mx <= 1 and frac >= 0.999
+
+
+def test_large_tile_mask_recompute_path(sb):
+    """A slice of more than 262,144 pixels per CTA cannot cache its mask bits in shared memory and recomputes them
+    per pass; same results required (1600x1400 px, cluster of 8 -> 280,000 px per CTA)."""
+    src = synth_tile(91, 1600, 1400)
+    tgt = synth_tile(92, 512, kind="target")
+    o = so.ExtractiveStainNormalizer("macenko")
+    o.fit(tgt)
+    n = sb.ExtractiveStainNormalizer("macenko")
+    n.fit(tgt)
+    np.testing.assert_allclose(sb.MacenkoStainExtractor.get_stain_matrix(src), so.macenko_stain_matrix(src), rtol=0, atol=M_ATOL)
+    mx, frac = lsb_stats(n.transform(src), o.transform(src))
+    assert mx <= 1 and frac >= 0.999, (mx, frac)
