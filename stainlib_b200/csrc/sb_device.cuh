@@ -17,7 +17,6 @@ constexpr int GROUP_PX = 16;        // pixels per thread-iteration: 48 B = 3 x 1
 constexpr int KEY_BITS = 23;
 constexpr int L1_BITS = 12, L1_BINS = 1 << L1_BITS;   // level-1 histogram: top 12 bits of the key
 constexpr int L2_BITS = 11, L2_BINS = 1 << L2_BITS;   // level-2 histogram: low 11 bits
-constexpr float CONC_KEY_K = 2.0f;  // concentration key: t = 2 - K/(C+K) in [1,2)
 // log2(255) rounded UP by one float step (2^x = 255 * (1 + 5.6e-7)): a pixel with zero concentrations must come out
 // as exactly 255 like the reference's 255*exp(0), even when ex2.approx errs low by its 2^-22 bound.
 constexpr float LOG2_255_UP = 7.994354248046875f;
@@ -298,7 +297,9 @@ __device__ inline double angle_from_key(uint32_t key) {
     if (d < -1.0) return atan2(-2.0 - d, -(-1.0 - d));
     return atan2(d, 1.0 - fabs(d));
 }
-// Monotone 23-bit key of a concentration C >= 0: t = 2 - K/(C+K).
+// Monotone 23-bit key of a concentration C >= 0 with unbounded range: t = 2 - K/(C+K) in [1,2), key = mantissa of t.
+// Resolution dC = 2^-23 (C+K)^2 / K: 7e-7 at C = 1.5, 6e-6 at C = 8 (K = 2).
+constexpr float CONC_KEY_K = 2.0f;
 __device__ __forceinline__ uint32_t conc_key(float c) {
     const float t = fmaf(-CONC_KEY_K, rcp_approx(c + CONC_KEY_K), 2.f);
     const uint32_t k = __float_as_uint(t) - 0x3F800000u;

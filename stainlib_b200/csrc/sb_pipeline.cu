@@ -37,6 +37,12 @@ struct __align__(16) PipeShared {
     unsigned q_rank[4], q_bin[4], q_rem[4], q_key[4], q_hist[4], q_tmp[4];
     unsigned d_bin[4], d_src[4];     // distinct level-2 histograms: level-1 bin and key source (0/1)
     int n_distinct;
+    unsigned okey[4];                // the four selected 23-bit keys (either selection path writes them)
+    // sampled-bracket selection
+    unsigned lhist[256];
+    unsigned l_len[2], l_below[2], l_bin, l_rem, s_cnt;
+    unsigned brk_a[2], brk_b[2];
+    int s_ok;
     float V[6];
     LassoK lk;
     int flags;
@@ -200,6 +206,79 @@ __device__ __forceinline__ void for_each_px_od(const unsigned char* tab, uint32_
     }
 }
 
+// ------------------------------------------------------------------------------------------ sampled-bracket selection
+// Exact order statistics in ONE full pass: a 1-in-16 sample of the groups gives a 4096-bin histogram from which a key
+// bracket [ka, kb) around each target rank is chosen (4 sigma of the binomial sampling error plus slack); the full pass
+// counts the keys below the bracket and appends the keys inside it to a shared-memory list; the target rank is then
+// selected inside the list.  The exact counts prove (or refute) that the rank fell inside the bracket -- on a miss or
+// a list overflow the caller falls back to the two-level histogram selection, so the result is always exact.
+constexpr unsigned LIST_CAP = L1_BINS;      // two lists alias the 32 KB histogram buffer
+constexpr int SAMPLE_STRIDE = 16;
+
+__device__ __forceinline__ unsigned warp_sum_u(unsigned x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    return x;
+}
+
+__device__ inline void plan_bracket(unsigned n, unsigned n_s, unsigned lo, unsigned& ra, unsigned& rb) {
+    const double q = (double)lo / (double)n;
+    const double pos = q * (double)n_s;
+    const double m = 4.0 * sqrt((double)n_s * q * (1.0 - q)) + 16.0;
+    const double a = floor(pos - m), b = ceil(pos + m) + 1.0;
+    ra = a < 0.0 ? 0u : (unsigned)a;
+    rb = b > (double)(n_s - 1) ? n_s - 1 : (unsigned)b;
+}
+
+// rank-th smallest (0-based) of list[0..len): three 8-bit radix levels with a 256-bin histogram; whole block calls.
+__device__ __forceinline__ unsigned list_select(PipeShared* sh, const unsigned* list, unsigned len, unsigned rank) {
+    unsigned prefix = 0, mask = 0;
+    for (int shift = 16; shift >= 0; shift -= 8) {
+        if (threadIdx.x < 256) sh->lhist[threadIdx.x] = 0;
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < len; i += NT) {
+            const unsigned k = list[i];
+            if ((k & mask) == prefix) atomicAdd(&sh->lhist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned v[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i] = sh->lhist[threadIdx.x * 8 + i]; sum += v[i]; }
+            const unsigned incl = warp_incl_scan(sum);
+            unsigned c = incl - sum;
+            if (rank >= c && rank < incl) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (rank >= c && rank < c + v[i]) { sh->l_bin = threadIdx.x * 8 + i; sh->l_rem = rank - c; }
+                    c += v[i];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= sh->l_bin << shift;
+        mask |= 255u << shift;
+        rank = sh->l_rem;
+    }
+    return prefix;
+}
+
+// Like for_each_group but visits ONE complete group out of every SAMPLE_STRIDE consecutive groups, at a hashed offset
+// inside the block (a fixed offset would alias with the row length and sample vertical stripes of the image).
+template <class F>
+__device__ __forceinline__ void for_each_sample_group(const uint8_t* __restrict__ tile, int npx, int gb, int ge, bool aligned, F&& f) {
+    const int nfull = npx / GROUP_PX;
+    const int fe = ge < nfull ? ge : nfull;
+    const int nblk = (fe - gb) / SAMPLE_STRIDE;
+    for (int j = threadIdx.x; j < nblk; j += NT) {
+        const int g = gb + j * SAMPLE_STRIDE + (int)(((uint32_t)j * 2654435761u) >> 28);
+        uint32_t w[12];
+        int nvalid;
+        load_group<true>(tile, npx, g, aligned, w, nvalid);
+        f(NoTail{}, w, GROUP_PX, g);
+    }
+}
+
 __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* od_rep = smem_raw;                                        // 64 KB: OD table + mask bits
@@ -291,59 +370,142 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
             }
             __syncthreads();
             if (sh->flags == 0) {
-                // -------------------------------------------------------------- B1: angle histogram (tissue pixels)
-                zero_hist(sh);
                 const float v00 = sh->V[0], v01 = sh->V[1], v02 = sh->V[2], v10 = sh->V[3], v11 = sh->V[4], v12 = sh->V[5];
-                for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                    const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
-                    for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
-                        const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
-                        const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
-                        const uint32_t key = angle_key(px, py);
-                        if (mbits & (1u << i)) atomicAdd(&sh->hist[key >> L2_BITS], 1u);
+                unsigned p_lo[2], p_hi[2];
+                { double fr; percentile_index(n_tissue, 100.0 - a.ang_pct, p_lo[0], p_hi[0], fr); percentile_index(n_tissue, a.ang_pct, p_lo[1], p_hi[1], fr); }
+                bool sampled = false;
+                if (S == 1 && n_tissue >= 16384u) {
+                    // ---------------------------------------------------------- B0: angle keys of a 1-in-16 sample
+                    if (threadIdx.x == 0) { sh->s_cnt = 0; sh->l_len[0] = sh->l_len[1] = 0; sh->l_below[0] = sh->l_below[1] = 0; sh->s_ok = 0; }
+                    zero_hist(sh);
+                    unsigned scnt = 0;
+                    for_each_sample_group(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                        const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                        scnt += __popc(mbits);
+                        for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
+                            const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
+                            const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
+                            if (mbits & (1u << i)) atomicAdd(&sh->hist[angle_key(px, py) >> L2_BITS], 1u);
+                        });
                     });
-                });
-                if (threadIdx.x == 0) {
-                    unsigned lo, hi; double fr;
-                    percentile_index(n_tissue, 100.0 - a.ang_pct, lo, hi, fr);
-                    sh->q_rank[0] = lo; sh->q_rank[1] = hi;
-                    percentile_index(n_tissue, a.ang_pct, lo, hi, fr);
-                    sh->q_rank[2] = lo; sh->q_rank[3] = hi;
-                    for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
+                    scnt = warp_sum_u(scnt);
+                    if ((threadIdx.x & 31) == 0 && scnt) atomicAdd(&sh->s_cnt, scnt);
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        const unsigned n_s = sh->s_cnt;
+                        if (n_s >= 1024u) {
+                            plan_bracket(n_tissue, n_s, p_lo[0], sh->q_rank[0], sh->q_rank[1]);
+                            plan_bracket(n_tissue, n_s, p_lo[1], sh->q_rank[2], sh->q_rank[3]);
+                            for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
+                            sh->s_ok = 1;
+                        }
+                    }
+                    __syncthreads();
+                    if (sh->s_ok) {
+                        select_ranks<L1_BINS>(sh, sh->hist, 1, sh->q_rank, 4, sh->q_bin, sh->q_rem);
+                        if (threadIdx.x < 2) {
+                            const unsigned n_s = sh->s_cnt, j = threadIdx.x;
+                            sh->brk_a[j] = sh->q_rank[2 * j] == 0 ? 0u : (sh->q_bin[2 * j] << L2_BITS);
+                            sh->brk_b[j] = sh->q_rank[2 * j + 1] >= n_s - 1 ? (1u << KEY_BITS) : ((sh->q_bin[2 * j + 1] + 1u) << L2_BITS);
+                        }
+                        __syncthreads();
+                        // ------------------------------------------------------ B1': count below / collect inside the brackets
+                        const unsigned ka0 = sh->brk_a[0], kb0 = sh->brk_b[0], ka1 = sh->brk_a[1], kb1 = sh->brk_b[1];
+                        unsigned* list0 = sh->hist;
+                        unsigned* list1 = sh->hist + LIST_CAP;
+                        unsigned below0 = 0, below1 = 0;
+                        for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                            const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                            for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
+                                const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
+                                const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
+                                const uint32_t key = angle_key(px, py);
+                                if (mbits & (1u << i)) {
+                                    if (key < ka0) ++below0;
+                                    else if (key < kb0) { const unsigned idx = atomicAdd(&sh->l_len[0], 1u); if (idx < LIST_CAP) list0[idx] = key; }
+                                    if (key < ka1) ++below1;
+                                    else if (key < kb1) { const unsigned idx = atomicAdd(&sh->l_len[1], 1u); if (idx < LIST_CAP) list1[idx] = key; }
+                                }
+                            });
+                        });
+                        below0 = warp_sum_u(below0); below1 = warp_sum_u(below1);
+                        if ((threadIdx.x & 31) == 0) { if (below0) atomicAdd(&sh->l_below[0], below0); if (below1) atomicAdd(&sh->l_below[1], below1); }
+                        __syncthreads();
+                        if (threadIdx.x == 0) {
+                            bool ok = true;
+                            for (int j = 0; j < 2; ++j)
+                                ok = ok && sh->l_len[j] <= LIST_CAP && sh->l_below[j] <= p_lo[j] && p_hi[j] < sh->l_below[j] + sh->l_len[j];
+                            sh->s_ok = ok ? 1 : 0;
+                        }
+                        __syncthreads();
+                        if (sh->s_ok) {
+                            for (int q = 0; q < 4; ++q) {
+                                const int j = q >> 1;
+                                const unsigned r = ((q & 1) ? p_hi[j] : p_lo[j]) - sh->l_below[j];
+                                const unsigned key = list_select(sh, j ? list1 : list0, sh->l_len[j], r);
+                                if (threadIdx.x == 0) sh->okey[q] = key;
+                            }
+                            __syncthreads();
+                            sampled = true;
+                        }
+                    }
                 }
-                __syncthreads();
-                tile_sync(S);
-                select_ranks<L1_BINS>(sh, sh->hist, S, sh->q_rank, 4, sh->q_bin, sh->q_rem);
-                if (threadIdx.x == 0) { const unsigned src[4] = {0, 0, 0, 0}; plan_level2(sh, src); }
-                tile_sync(S);
-                // -------------------------------------------------------------- B2: 11-bit refinement
-                zero_hist(sh);
-                {
-                    const int nd = sh->n_distinct;
-                    const unsigned b0 = sh->d_bin[0], b1 = sh->d_bin[1], b2 = sh->d_bin[2], b3 = sh->d_bin[3];
+                if (!sampled) {
+                    // ---------------------------------------------------------- B1: angle histogram (tissue pixels)
+                    zero_hist(sh);
                     for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
                         const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
                         for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                             const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
                             const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
                             const uint32_t key = angle_key(px, py);
-                            const uint32_t bin = key >> L2_BITS, low = key & (L2_BINS - 1);
-                            if (mbits & (1u << i)) {
-                                if (bin == b0) atomicAdd(&sh->hist[low], 1u);
-                                if (nd > 1 && bin == b1) atomicAdd(&sh->hist[L2_BINS + low], 1u);
-                                if (nd > 2 && bin == b2) atomicAdd(&sh->hist[2 * L2_BINS + low], 1u);
-                                if (nd > 3 && bin == b3) atomicAdd(&sh->hist[3 * L2_BINS + low], 1u);
-                            }
+                            if (mbits & (1u << i)) atomicAdd(&sh->hist[key >> L2_BITS], 1u);
                         });
                     });
+                    if (threadIdx.x == 0) {
+                        unsigned lo, hi; double fr;
+                        percentile_index(n_tissue, 100.0 - a.ang_pct, lo, hi, fr);
+                        sh->q_rank[0] = lo; sh->q_rank[1] = hi;
+                        percentile_index(n_tissue, a.ang_pct, lo, hi, fr);
+                        sh->q_rank[2] = lo; sh->q_rank[3] = hi;
+                        for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
+                    }
+                    __syncthreads();
+                    tile_sync(S);
+                    select_ranks<L1_BINS>(sh, sh->hist, S, sh->q_rank, 4, sh->q_bin, sh->q_rem);
+                    if (threadIdx.x == 0) { const unsigned src[4] = {0, 0, 0, 0}; plan_level2(sh, src); }
+                    tile_sync(S);
+                    // -------------------------------------------------------------- B2: 11-bit refinement
+                    zero_hist(sh);
+                    {
+                        const int nd = sh->n_distinct;
+                        const unsigned b0 = sh->d_bin[0], b1 = sh->d_bin[1], b2 = sh->d_bin[2], b3 = sh->d_bin[3];
+                        for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                            const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                            for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
+                                const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
+                                const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
+                                const uint32_t key = angle_key(px, py);
+                                const uint32_t bin = key >> L2_BITS, low = key & (L2_BINS - 1);
+                                if (mbits & (1u << i)) {
+                                    if (bin == b0) atomicAdd(&sh->hist[low], 1u);
+                                    if (nd > 1 && bin == b1) atomicAdd(&sh->hist[L2_BINS + low], 1u);
+                                    if (nd > 2 && bin == b2) atomicAdd(&sh->hist[2 * L2_BINS + low], 1u);
+                                    if (nd > 3 && bin == b3) atomicAdd(&sh->hist[3 * L2_BINS + low], 1u);
+                                }
+                            });
+                        });
+                    }
+                    __syncthreads();
+                    tile_sync(S);
+                    for (int q = 0; q < 4; ++q)
+                        select_ranks<L2_BINS>(sh, sh->hist + sh->q_hist[q] * L2_BINS, S, &sh->q_rem[q], 1, &sh->q_key[q], &sh->q_tmp[q]);
+                    if (threadIdx.x < 4) sh->okey[threadIdx.x] = (sh->q_bin[threadIdx.x] << L2_BITS) | sh->q_key[threadIdx.x];
+                    __syncthreads();
                 }
-                __syncthreads();
-                tile_sync(S);
-                for (int q = 0; q < 4; ++q)
-                    select_ranks<L2_BINS>(sh, sh->hist + sh->q_hist[q] * L2_BINS, S, &sh->q_rem[q], 1, &sh->q_key[q], &sh->q_tmp[q]);
                 if (threadIdx.x == 0) {
                     double ang[4];
-                    for (int q = 0; q < 4; ++q) ang[q] = angle_from_key((sh->q_bin[q] << L2_BITS) | sh->q_key[q]);
+                    for (int q = 0; q < 4; ++q) ang[q] = angle_from_key(sh->okey[q]);
                     unsigned lo, hi; double fr_lo, fr_hi;
                     percentile_index(n_tissue, 100.0 - a.ang_pct, lo, hi, fr_lo);
                     percentile_index(n_tissue, a.ang_pct, lo, hi, fr_hi);
@@ -456,61 +618,147 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
         }
 
         if (a.mode >= PIPE_FIT && sh->flags == 0) {
-            // ------------------------------------------------------------------ C1: concentration histograms (all pixels)
-            if (threadIdx.x == 0) make_lasso_consts(sh->Msrc, a.lasso_lambda, sh->lk);
+            if (threadIdx.x == 0) {
+                make_lasso_consts(sh->Msrc, a.lasso_lambda, sh->lk);
+                sh->s_cnt = 0; sh->l_len[0] = sh->l_len[1] = 0; sh->l_below[0] = sh->l_below[1] = 0; sh->s_ok = 0;
+            }
             zero_hist(sh);
             const LassoK lk = sh->lk;
-            for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int) {
-                constexpr bool TAIL = decltype(tail)::value;
-                for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
-                    float c0, c1;
-                    lasso2(lk, o0, o1, o2, c0, c1);
-                    if (!TAIL || i < nvalid) {
+            unsigned c_lo, c_hi;
+            { double fr; percentile_index((unsigned)npx, a.conc_pct, c_lo, c_hi, fr); }
+            bool sampled = false;
+            if (S == 1 && npx >= 32768) {
+                // -------------------------------------------------------------- C0: concentration keys of a 1-in-16 sample
+                unsigned scnt = 0;
+                for_each_sample_group(tin, npx, gb, ge, aligned, [&](auto, const uint32_t (&w)[12], int, int) {
+                    scnt += GROUP_PX;
+                    for_each_px_od(od_rep, lane_off, w, [&](int, float o0, float o1, float o2) {
+                        float c0, c1;
+                        lasso2(lk, o0, o1, o2, c0, c1);
                         atomicAdd(&sh->hist[conc_key(c0) >> L2_BITS], 1u);
                         atomicAdd(&sh->hist[L1_BINS + (conc_key(c1) >> L2_BITS)], 1u);
-                    }
+                    });
                 });
-            });
-            if (threadIdx.x == 0) {
-                unsigned lo, hi; double fr;
-                percentile_index((unsigned)npx, a.conc_pct, lo, hi, fr);
-                sh->q_rank[0] = lo; sh->q_rank[1] = hi; sh->q_rank[2] = lo; sh->q_rank[3] = hi;
-                for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
+                scnt = warp_sum_u(scnt);
+                if ((threadIdx.x & 31) == 0 && scnt) atomicAdd(&sh->s_cnt, scnt);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const unsigned n_s = sh->s_cnt;
+                    if (n_s >= 1024u) {
+                        plan_bracket((unsigned)npx, n_s, c_lo, sh->q_rank[0], sh->q_rank[1]);
+                        sh->q_rank[2] = sh->q_rank[0]; sh->q_rank[3] = sh->q_rank[1];
+                        for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
+                        sh->s_ok = 1;
+                    }
+                }
+                __syncthreads();
+                if (sh->s_ok) {
+                    select_ranks<L1_BINS>(sh, sh->hist, 1, sh->q_rank, 2, sh->q_bin, sh->q_rem);
+                    select_ranks<L1_BINS>(sh, sh->hist + L1_BINS, 1, sh->q_rank + 2, 2, sh->q_bin + 2, sh->q_rem + 2);
+                    if (threadIdx.x < 2) {
+                        const unsigned n_s = sh->s_cnt, j = threadIdx.x;
+                        sh->brk_a[j] = sh->q_rank[2 * j] == 0 ? 0u : (sh->q_bin[2 * j] << L2_BITS);
+                        sh->brk_b[j] = sh->q_rank[2 * j + 1] >= n_s - 1 ? (1u << KEY_BITS) : ((sh->q_bin[2 * j + 1] + 1u) << L2_BITS);
+                    }
+                    __syncthreads();
+                    // ---------------------------------------------------------- C1': count below / collect inside the brackets
+                    const unsigned ka0 = sh->brk_a[0], kb0 = sh->brk_b[0], ka1 = sh->brk_a[1], kb1 = sh->brk_b[1];
+                    unsigned* list0 = sh->hist;
+                    unsigned* list1 = sh->hist + LIST_CAP;
+                    unsigned below0 = 0, below1 = 0;
+                    for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int) {
+                        constexpr bool TAIL = decltype(tail)::value;
+                        for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
+                            float c0, c1;
+                            lasso2(lk, o0, o1, o2, c0, c1);
+                            const uint32_t k0 = conc_key(c0), k1 = conc_key(c1);
+                            if (!TAIL || i < nvalid) {
+                                if (k0 < ka0) ++below0;
+                                else if (k0 < kb0) { const unsigned idx = atomicAdd(&sh->l_len[0], 1u); if (idx < LIST_CAP) list0[idx] = k0; }
+                                if (k1 < ka1) ++below1;
+                                else if (k1 < kb1) { const unsigned idx = atomicAdd(&sh->l_len[1], 1u); if (idx < LIST_CAP) list1[idx] = k1; }
+                            }
+                        });
+                    });
+                    below0 = warp_sum_u(below0); below1 = warp_sum_u(below1);
+                    if ((threadIdx.x & 31) == 0) { if (below0) atomicAdd(&sh->l_below[0], below0); if (below1) atomicAdd(&sh->l_below[1], below1); }
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        bool ok = true;
+                        for (int j = 0; j < 2; ++j)
+                            ok = ok && sh->l_len[j] <= LIST_CAP && sh->l_below[j] <= c_lo && c_hi < sh->l_below[j] + sh->l_len[j];
+                        sh->s_ok = ok ? 1 : 0;
+                    }
+                    __syncthreads();
+                    if (sh->s_ok) {
+                        for (int q = 0; q < 4; ++q) {
+                            const int j = q >> 1;
+                            const unsigned r = ((q & 1) ? c_hi : c_lo) - sh->l_below[j];
+                            const unsigned key = list_select(sh, j ? list1 : list0, sh->l_len[j], r);
+                            if (threadIdx.x == 0) sh->okey[q] = key;
+                        }
+                        __syncthreads();
+                        sampled = true;
+                    }
+                }
+                if (!sampled) zero_hist(sh);
             }
-            __syncthreads();
-            tile_sync(S);
-            select_ranks<L1_BINS>(sh, sh->hist, S, sh->q_rank, 2, sh->q_bin, sh->q_rem);
-            select_ranks<L1_BINS>(sh, sh->hist + L1_BINS, S, sh->q_rank + 2, 2, sh->q_bin + 2, sh->q_rem + 2);
-            if (threadIdx.x == 0) { const unsigned src[4] = {0, 0, 1, 1}; plan_level2(sh, src); }
-            tile_sync(S);
-            // ------------------------------------------------------------------ C2: refinement
-            zero_hist(sh);
-            {
-                const int nd = sh->n_distinct;
-                const unsigned b0 = sh->d_bin[0], b1 = sh->d_bin[1], b2 = sh->d_bin[2], b3 = sh->d_bin[3];
-                const unsigned s0 = sh->d_src[0], s1 = sh->d_src[1], s2 = sh->d_src[2], s3 = sh->d_src[3];
+            if (!sampled) {
+                // -------------------------------------------------------------- C1: concentration histograms (all pixels)
                 for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int) {
                     constexpr bool TAIL = decltype(tail)::value;
                     for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                         float c0, c1;
                         lasso2(lk, o0, o1, o2, c0, c1);
-                        const uint32_t k0 = conc_key(c0), k1 = conc_key(c1);
                         if (!TAIL || i < nvalid) {
-                            { const uint32_t k = s0 ? k1 : k0; if ((k >> L2_BITS) == b0) atomicAdd(&sh->hist[k & (L2_BINS - 1)], 1u); }
-                            if (nd > 1) { const uint32_t k = s1 ? k1 : k0; if ((k >> L2_BITS) == b1) atomicAdd(&sh->hist[L2_BINS + (k & (L2_BINS - 1))], 1u); }
-                            if (nd > 2) { const uint32_t k = s2 ? k1 : k0; if ((k >> L2_BITS) == b2) atomicAdd(&sh->hist[2 * L2_BINS + (k & (L2_BINS - 1))], 1u); }
-                            if (nd > 3) { const uint32_t k = s3 ? k1 : k0; if ((k >> L2_BITS) == b3) atomicAdd(&sh->hist[3 * L2_BINS + (k & (L2_BINS - 1))], 1u); }
+                            atomicAdd(&sh->hist[conc_key(c0) >> L2_BITS], 1u);
+                            atomicAdd(&sh->hist[L1_BINS + (conc_key(c1) >> L2_BITS)], 1u);
                         }
                     });
                 });
+                if (threadIdx.x == 0) {
+                    unsigned lo, hi; double fr;
+                    percentile_index((unsigned)npx, a.conc_pct, lo, hi, fr);
+                    sh->q_rank[0] = lo; sh->q_rank[1] = hi; sh->q_rank[2] = lo; sh->q_rank[3] = hi;
+                    for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
+                }
+                __syncthreads();
+                tile_sync(S);
+                select_ranks<L1_BINS>(sh, sh->hist, S, sh->q_rank, 2, sh->q_bin, sh->q_rem);
+                select_ranks<L1_BINS>(sh, sh->hist + L1_BINS, S, sh->q_rank + 2, 2, sh->q_bin + 2, sh->q_rem + 2);
+                if (threadIdx.x == 0) { const unsigned src[4] = {0, 0, 1, 1}; plan_level2(sh, src); }
+                tile_sync(S);
+                // ------------------------------------------------------------------ C2: refinement
+                zero_hist(sh);
+                {
+                    const int nd = sh->n_distinct;
+                    const unsigned b0 = sh->d_bin[0], b1 = sh->d_bin[1], b2 = sh->d_bin[2], b3 = sh->d_bin[3];
+                    const unsigned s0 = sh->d_src[0], s1 = sh->d_src[1], s2 = sh->d_src[2], s3 = sh->d_src[3];
+                    for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int) {
+                        constexpr bool TAIL = decltype(tail)::value;
+                        for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
+                            float c0, c1;
+                            lasso2(lk, o0, o1, o2, c0, c1);
+                            const uint32_t k0 = conc_key(c0), k1 = conc_key(c1);
+                            if (!TAIL || i < nvalid) {
+                                { const uint32_t k = s0 ? k1 : k0; if ((k >> L2_BITS) == b0) atomicAdd(&sh->hist[k & (L2_BINS - 1)], 1u); }
+                                if (nd > 1) { const uint32_t k = s1 ? k1 : k0; if ((k >> L2_BITS) == b1) atomicAdd(&sh->hist[L2_BINS + (k & (L2_BINS - 1))], 1u); }
+                                if (nd > 2) { const uint32_t k = s2 ? k1 : k0; if ((k >> L2_BITS) == b2) atomicAdd(&sh->hist[2 * L2_BINS + (k & (L2_BINS - 1))], 1u); }
+                                if (nd > 3) { const uint32_t k = s3 ? k1 : k0; if ((k >> L2_BITS) == b3) atomicAdd(&sh->hist[3 * L2_BINS + (k & (L2_BINS - 1))], 1u); }
+                            }
+                        });
+                    });
+                }
+                __syncthreads();
+                tile_sync(S);
+                for (int q = 0; q < 4; ++q)
+                    select_ranks<L2_BINS>(sh, sh->hist + sh->q_hist[q] * L2_BINS, S, &sh->q_rem[q], 1, &sh->q_key[q], &sh->q_tmp[q]);
+                if (threadIdx.x < 4) sh->okey[threadIdx.x] = (sh->q_bin[threadIdx.x] << L2_BITS) | sh->q_key[threadIdx.x];
+                __syncthreads();
             }
-            __syncthreads();
-            tile_sync(S);
-            for (int q = 0; q < 4; ++q)
-                select_ranks<L2_BINS>(sh, sh->hist + sh->q_hist[q] * L2_BINS, S, &sh->q_rem[q], 1, &sh->q_key[q], &sh->q_tmp[q]);
             if (threadIdx.x == 0) {
                 double cv[4];
-                for (int q = 0; q < 4; ++q) cv[q] = conc_from_key((sh->q_bin[q] << L2_BITS) | sh->q_key[q]);
+                for (int q = 0; q < 4; ++q) cv[q] = conc_from_key(sh->okey[q]);
                 unsigned lo, hi; double fr;
                 percentile_index((unsigned)npx, a.conc_pct, lo, hi, fr);
                 sh->maxC[0] = lerp_np(cv[0], cv[1], fr);
