@@ -55,10 +55,11 @@ int is_aligned(const void* a, const void* b, int npx) {
 }
 int pick_cluster(const sb_handle* h, int B, int npx, int requested) {
     if (requested == 1 || requested == 2 || requested == 4 || requested == 8) return requested;
-    // auto: keep ~<=128k pixels per CTA and enough clusters to fill the SMs when the batch is small
+    // auto: one CTA per tile (the fast single-pass selection path) whenever the batch can fill the SMs; clusters of
+    // 2/4/8 CTAs over DSMEM only to spread a small batch over the machine
     int S = 1;
-    while (S < 8 && ((long long)npx / S > 160 * 1024 || (long long)B * S * 1 < h->num_sms)) S *= 2;
-    if (npx / S < 16 * sb::NT) { while (S > 1 && npx / S < 16 * sb::NT) S /= 2; }
+    while (S < 8 && (long long)B * S < h->num_sms) S *= 2;
+    while (S > 1 && npx / S < 16 * sb::NT) S /= 2;
     return S;
 }
 

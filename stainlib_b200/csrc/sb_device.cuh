@@ -130,6 +130,20 @@ __device__ __forceinline__ void lasso2(const LassoK& k, float o0, float o1, floa
     c1 = both ? a1 : ((!only0 & only1) ? p1 : 0.f);
 }
 
+// Same problem when the dictionary rows have unit norm (Gram diagonal exactly 1 in fp32): with the unconstrained
+// solution infeasible, the optimum lies on one axis and is the better of the two axis optima max(u_j, 0).
+__device__ __forceinline__ void lasso2_unit(const LassoK& k, float o0, float o1, float o2, float& c0, float& c1) {
+    const float u0 = fmaf(k.m02, o2, fmaf(k.m01, o1, fmaf(k.m00, o0, -k.lam)));
+    const float u1 = fmaf(k.m12, o2, fmaf(k.m11, o1, fmaf(k.m10, o0, -k.lam)));
+    const float a0 = fmaf(k.i01, u1, k.i00 * u0);
+    const float a1 = fmaf(k.i11, u1, k.i01 * u0);
+    const bool both = (a0 > 0.f) & (a1 > 0.f);
+    const float x0 = fmaxf(u0, 0.f), x1 = fmaxf(u1, 0.f);
+    const bool pick0 = x0 >= x1;
+    c0 = both ? a0 : (pick0 ? x0 : 0.f);
+    c1 = both ? a1 : (pick0 ? 0.f : x1);
+}
+
 __host__ __device__ inline void make_lasso_consts(const double M[6], double lam, LassoK& k) {
     const double g00 = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
     const double g11 = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
@@ -309,6 +323,20 @@ __device__ inline double conc_from_key(uint32_t key) {
     if (key == 0) return 0.0;
     const double t = 1.0 + (double)key * (1.0 / 8388608.0);
     return (double)CONC_KEY_K * (t - 1.0) / (2.0 - t);
+}
+
+// Diamond coordinate d = y/(|x|+|y|) (|d| <= 1 in the half-plane x >= 0) that maps to a given angle key.
+__device__ inline double diamond_from_key(double key) { return ((1.0 + key * (1.0 / 8388608.0)) - 1.5) * 4.0; }
+// Largest float strictly below x (x finite, positive or negative).
+__device__ inline float float_below(double x) {
+    float f = (float)x;
+    if ((double)f >= x) f = nextafterf(f, -INFINITY);
+    return nextafterf(f, -INFINITY);
+}
+__device__ inline float float_above(double x) {
+    float f = (float)x;
+    if ((double)f <= x) f = nextafterf(f, INFINITY);
+    return nextafterf(f, INFINITY);
 }
 
 // numpy.percentile (linear): virtual index (n-1)*q/100; returns lo index and the interpolation weight.

@@ -27,6 +27,8 @@
 
 namespace sb {
 
+constexpr unsigned WQ_CAP = 160;   // entries per warp queue: drained to < 32 once per group, a group adds at most 128 kept pushes
+
 struct __align__(16) PipeShared {
     unsigned hist[2 * L1_BINS];      // 32 KB: 2 x 4096 (level 1) or 4 x 2048 (level 2)
     float gy[3 * 256];
@@ -42,6 +44,9 @@ struct __align__(16) PipeShared {
     unsigned lhist[256];
     unsigned l_len[2], l_below[2], l_bin, l_rem, s_cnt;
     unsigned brk_a[2], brk_b[2];
+    float fast_lo[2], fast_hi[2];    // conservative float thresholds that let most pixels skip the exact key
+    unsigned wq[NWARP][WQ_CAP];      // per-warp compaction queues of the rare pixels that need the exact key
+    int wq_overflow;
     int s_ok;
     float V[6];
     LassoK lk;
@@ -208,7 +213,7 @@ __device__ __forceinline__ void for_each_px_od(const unsigned char* tab, uint32_
 
 // ------------------------------------------------------------------------------------------ sampled-bracket selection
 // Exact order statistics in ONE full pass: a 1-in-16 sample of the groups gives a 4096-bin histogram from which a key
-// bracket [ka, kb) around each target rank is chosen (4 sigma of the binomial sampling error plus slack); the full pass
+// bracket [ka, kb) around each target rank is chosen (3 sigma of the binomial sampling error plus slack); the full pass
 // counts the keys below the bracket and appends the keys inside it to a shared-memory list; the target rank is then
 // selected inside the list.  The exact counts prove (or refute) that the rank fell inside the bracket -- on a miss or
 // a list overflow the caller falls back to the two-level histogram selection, so the result is always exact.
@@ -224,7 +229,7 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned x) {
 __device__ inline void plan_bracket(unsigned n, unsigned n_s, unsigned lo, unsigned& ra, unsigned& rb) {
     const double q = (double)lo / (double)n;
     const double pos = q * (double)n_s;
-    const double m = 4.0 * sqrt((double)n_s * q * (1.0 - q)) + 16.0;
+    const double m = 3.0 * sqrt((double)n_s * q * (1.0 - q)) + 8.0;
     const double a = floor(pos - m), b = ceil(pos + m) + 1.0;
     ra = a < 0.0 ? 0u : (unsigned)a;
     rb = b > (double)(n_s - 1) ? n_s - 1 : (unsigned)b;
@@ -261,6 +266,90 @@ __device__ __forceinline__ unsigned list_select(PipeShared* sh, const unsigned* 
         rank = sh->l_rem;
     }
     return prefix;
+}
+
+// ---------------------------------------------------------------------------------- rare-pixel compaction queues
+// In the bracket passes ~98 % of the pixels are classified by a cheap float test; the rest need the exact 23-bit key
+// and possibly a list append.  Handling them in place would make almost every warp step diverge (some lane out of 32
+// is nearly always "rare"), so each warp pushes its rare pixels (packed RGB + flags) into a 64-entry shared-memory
+// queue with one ballot, and drains the queue 32 entries at a time with all lanes busy.
+struct WarpQueue {
+    unsigned* q;
+    unsigned len;      // warp-uniform
+};
+// Pushes val for every lane with pred set.  The queue is bounded: a push that does not fit is dropped and reported,
+// which makes the caller's validation fail and the tile take the two-level histogram path instead.
+__device__ __forceinline__ void wq_push(WarpQueue& wq, bool pred, unsigned val, int* overflow) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m) {
+        const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+        const unsigned idx = wq.len + __popc(m & lt);
+        if (pred) { if (idx < WQ_CAP) wq.q[idx] = val; else *overflow = 1; }
+        wq.len = min(wq.len + __popc(m), WQ_CAP);
+    }
+}
+template <class P>
+__device__ __forceinline__ void wq_drain(WarpQueue& wq, bool final, P&& proc) {
+    while (wq.len >= 32u || (final && wq.len > 0u)) {
+        const unsigned n = wq.len < 32u ? wq.len : 32u;
+        const unsigned start = wq.len - n;
+        __syncwarp();
+        const bool has = (threadIdx.x & 31u) < n;
+        const unsigned val = has ? wq.q[start + (threadIdx.x & 31u)] : 0x00FFFFFFu;
+        wq.len = start;
+        proc(has, val);
+        __syncwarp();
+    }
+}
+// Group epilogue of the bracket passes: every lane pushes the pixels flagged in `bits` (16-bit mask over its group)
+// into the warp queue, one per round, re-reading the three bytes of each flagged pixel (they are in L1: the group was
+// just loaded).  flag_of(i) supplies bits 24.. of the queue entry.  Warp-uniform: all lanes call it every group.
+template <class FL>
+__device__ __forceinline__ void wq_push_flagged(WarpQueue& wq, unsigned bits, const uint8_t* __restrict__ group_ptr, int* overflow, FL&& flag_of) {
+    while (__ballot_sync(0xffffffffu, bits != 0u)) {
+        const bool has = bits != 0u;
+        const int i = has ? (__ffs(bits) - 1) : 0;
+        bits &= bits - 1u;
+        unsigned val = 0x00FFFFFFu;
+        if (has) {
+            const uint8_t* p = group_ptr + 3 * i;
+            val = (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16) | flag_of(i);
+        }
+        wq_push(wq, has, val, overflow);
+    }
+}
+
+// The RGB bytes of pixel i (0..15) of a group as one word (R in byte 0), i a compile-time constant after unrolling.
+__device__ __forceinline__ uint32_t pixel_word(const uint32_t (&w)[12], int i) {
+    const int q = i >> 2, p = i & 3;
+    const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+    switch (p) {
+        case 0: return __byte_perm(a, 0u, 0x4210u);
+        case 1: return __byte_perm(a, b, 0x0543u) & 0x00FFFFFFu;
+        case 2: return __byte_perm(b, c, 0x0432u) & 0x00FFFFFFu;
+        default: return __byte_perm(c, 0u, 0x4321u);
+    }
+}
+// Warp-uniform iteration over the complete groups of [gb, ge): every lane of a warp runs the same number of iterations
+// (lanes past the end get active = false and an all-white group) so warp votes are legal inside f(w, active, g).
+template <class F>
+__device__ __forceinline__ void for_each_group_uniform(const uint8_t* __restrict__ tile, int npx, int gb, int ge, bool aligned, F&& f) {
+    const int nfull = npx / GROUP_PX;
+    const int fe = ge < nfull ? ge : nfull;
+    const int lane = threadIdx.x & 31;
+    for (int g0 = gb + (int)(threadIdx.x & ~31u); g0 < fe; g0 += NT) {
+        const int g = g0 + lane;
+        const bool active = g < fe;
+        uint32_t w[12];
+        if (active) {
+            int nvalid;
+            load_group<true>(tile, npx, g, aligned, w, nvalid);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) w[i] = 0xFFFFFFFFu;
+        }
+        f(w, active, g);
+    }
 }
 
 // Like for_each_group but visits ONE complete group out of every SAMPLE_STRIDE consecutive groups, at a hashed offset
@@ -322,7 +411,8 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     const float y = gyR[r] + gyG[gg] + gyB[b];
                     const bool m = TAIL ? ((y < ybound) & (i < nvalid)) : (y < ybound);
                     const float* row = reinterpret_cast<const float*>(od_rep + lane_off);
-                    const float o0 = m ? row[r * 64] : 0.f, o1 = m ? row[gg * 64] : 0.f, o2 = m ? row[b * 64] : 0.f;
+                    const float t0 = row[r * 64], t1 = row[gg * 64], t2 = row[b * 64];
+                    const float o0 = m ? t0 : 0.f, o1 = m ? t1 : 0.f, o2 = m ? t2 : 0.f;
                     mbits |= m ? (1u << i) : 0u;
                     f[0] += o0; f[1] += o1; f[2] += o2;
                     f[3] = fmaf(o0, o0, f[3]); f[4] = fmaf(o0, o1, f[4]); f[5] = fmaf(o0, o2, f[5]);
@@ -376,7 +466,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                 bool sampled = false;
                 if (S == 1 && n_tissue >= 16384u) {
                     // ---------------------------------------------------------- B0: angle keys of a 1-in-16 sample
-                    if (threadIdx.x == 0) { sh->s_cnt = 0; sh->l_len[0] = sh->l_len[1] = 0; sh->l_below[0] = sh->l_below[1] = 0; sh->s_ok = 0; }
+                    if (threadIdx.x == 0) { sh->s_cnt = 0; sh->l_len[0] = sh->l_len[1] = 0; sh->l_below[0] = sh->l_below[1] = 0; sh->s_ok = 0; sh->wq_overflow = 0; }
                     zero_hist(sh);
                     unsigned scnt = 0;
                     for_each_sample_group(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
@@ -403,36 +493,72 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     __syncthreads();
                     if (sh->s_ok) {
                         select_ranks<L1_BINS>(sh, sh->hist, 1, sh->q_rank, 4, sh->q_bin, sh->q_rem);
-                        if (threadIdx.x < 2) {
-                            const unsigned n_s = sh->s_cnt, j = threadIdx.x;
-                            sh->brk_a[j] = sh->q_rank[2 * j] == 0 ? 0u : (sh->q_bin[2 * j] << L2_BITS);
-                            sh->brk_b[j] = sh->q_rank[2 * j + 1] >= n_s - 1 ? (1u << KEY_BITS) : ((sh->q_bin[2 * j + 1] + 1u) << L2_BITS);
+                        if (threadIdx.x == 0) {
+                            const unsigned n_s = sh->s_cnt;
+                            for (int j = 0; j < 2; ++j) {
+                                sh->brk_a[j] = sh->q_rank[2 * j] == 0 ? 0u : (sh->q_bin[2 * j] << L2_BITS);
+                                sh->brk_b[j] = sh->q_rank[2 * j + 1] >= n_s - 1 ? (1u << KEY_BITS) : ((sh->q_bin[2 * j + 1] + 1u) << L2_BITS);
+                            }
+                            // A pixel in the half-plane x > 0 whose diamond coordinate d = y/(x+|y|) lies safely between the
+                            // low bracket and the high bracket (64 key units of slack, the key arithmetic errs by < 1) is
+                            // "above bracket 0, below bracket 1" without computing its key.
+                            const double d_lo = diamond_from_key((double)sh->brk_b[0] + 64.0), d_hi = diamond_from_key((double)sh->brk_a[1] - 64.0);
+                            const bool usable = sh->brk_a[1] >= 64u && d_lo > -0.999 && d_hi < 0.999 && d_lo < d_hi;
+                            sh->fast_lo[0] = usable ? float_above(d_lo) : INFINITY;
+                            sh->fast_hi[0] = usable ? float_below(d_hi) : -INFINITY;
                         }
                         __syncthreads();
                         // ------------------------------------------------------ B1': count below / collect inside the brackets
                         const unsigned ka0 = sh->brk_a[0], kb0 = sh->brk_b[0], ka1 = sh->brk_a[1], kb1 = sh->brk_b[1];
+                        const float f_lo = sh->fast_lo[0], f_hi = sh->fast_hi[0];
                         unsigned* list0 = sh->hist;
                         unsigned* list1 = sh->hist + LIST_CAP;
                         unsigned below0 = 0, below1 = 0;
-                        for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                            const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                        // exact treatment of one pixel (packed RGB): key, below counters, list appends
+                        auto exact_px = [&](bool has, uint32_t rgb) {
+                            const float o0 = od_lookup(od_rep, rgb, lane_off, 0), o1 = od_lookup(od_rep, rgb, lane_off, 1), o2 = od_lookup(od_rep, rgb, lane_off, 2);
+                            const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
+                            const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
+                            const uint32_t key = angle_key(px, py);
+                            if (has) {
+                                if (key < ka0) ++below0;
+                                else if (key < kb0) { const unsigned idx = atomicAdd(&sh->l_len[0], 1u); if (idx < LIST_CAP) list0[idx] = key; }
+                                if (key < ka1) ++below1;
+                                else if (key < kb1) { const unsigned idx = atomicAdd(&sh->l_len[1], 1u); if (idx < LIST_CAP) list1[idx] = key; }
+                            }
+                        };
+                        WarpQueue wq{sh->wq[threadIdx.x >> 5], 0u};
+                        for_each_group_uniform(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], bool active, int g) {
+                            uint32_t mbits = 0;
+                            if (active) mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<false>(w, gyR, gyG, gyB, ybound, GROUP_PX);
+                            unsigned fastbits = 0;
                             for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                                 const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
                                 const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
-                                const uint32_t key = angle_key(px, py);
-                                if (mbits & (1u << i)) {
-                                    if (key < ka0) ++below0;
-                                    else if (key < kb0) { const unsigned idx = atomicAdd(&sh->l_len[0], 1u); if (idx < LIST_CAP) list0[idx] = key; }
-                                    if (key < ka1) ++below1;
-                                    else if (key < kb1) { const unsigned idx = atomicAdd(&sh->l_len[1], 1u); if (idx < LIST_CAP) list1[idx] = key; }
-                                }
+                                const float sd = px + fabsf(py);
+                                const bool fast = (px > 0.f) & (py > f_lo * sd) & (py < f_hi * sd);
+                                fastbits |= fast ? (1u << i) : 0u;
                             });
+                            below1 += __popc(mbits & fastbits);
+                            wq_push_flagged(wq, mbits & ~fastbits, tin + (size_t)g * (GROUP_PX * 3), &sh->wq_overflow, [](int) { return 0u; });
+                            wq_drain(wq, false, exact_px);
                         });
+                        wq_drain(wq, true, exact_px);
+                        if ((npx % GROUP_PX) != 0 && ge == G && threadIdx.x == 0) {
+                            // ragged last group: plain exact path
+                            uint32_t w[12];
+                            int nvalid;
+                            load_group<true>(tin, npx, G - 1, false, w, nvalid);
+                            const uint32_t mbits = cache_mask ? *mask_slot(od_rep, G - 1 - gb) : mask16<true>(w, gyR, gyG, gyB, ybound, nvalid);
+#pragma unroll
+                            for (int i = 0; i < GROUP_PX; ++i)
+                                if (mbits & (1u << i)) exact_px(true, pixel_word(w, i));
+                        }
                         below0 = warp_sum_u(below0); below1 = warp_sum_u(below1);
                         if ((threadIdx.x & 31) == 0) { if (below0) atomicAdd(&sh->l_below[0], below0); if (below1) atomicAdd(&sh->l_below[1], below1); }
                         __syncthreads();
                         if (threadIdx.x == 0) {
-                            bool ok = true;
+                            bool ok = sh->wq_overflow == 0;
                             for (int j = 0; j < 2; ++j)
                                 ok = ok && sh->l_len[j] <= LIST_CAP && sh->l_below[j] <= p_lo[j] && p_hi[j] < sh->l_below[j] + sh->l_len[j];
                             sh->s_ok = ok ? 1 : 0;
@@ -620,7 +746,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
         if (a.mode >= PIPE_FIT && sh->flags == 0) {
             if (threadIdx.x == 0) {
                 make_lasso_consts(sh->Msrc, a.lasso_lambda, sh->lk);
-                sh->s_cnt = 0; sh->l_len[0] = sh->l_len[1] = 0; sh->l_below[0] = sh->l_below[1] = 0; sh->s_ok = 0;
+                sh->s_cnt = 0; sh->l_len[0] = sh->l_len[1] = 0; sh->l_below[0] = sh->l_below[1] = 0; sh->s_ok = 0; sh->wq_overflow = 0;
             }
             zero_hist(sh);
             const LassoK lk = sh->lk;
@@ -659,32 +785,67 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                         const unsigned n_s = sh->s_cnt, j = threadIdx.x;
                         sh->brk_a[j] = sh->q_rank[2 * j] == 0 ? 0u : (sh->q_bin[2 * j] << L2_BITS);
                         sh->brk_b[j] = sh->q_rank[2 * j + 1] >= n_s - 1 ? (1u << KEY_BITS) : ((sh->q_bin[2 * j + 1] + 1u) << L2_BITS);
+                        // concentrations safely below / above the bracket (64 key units of slack) need no exact key
+                        sh->fast_lo[j] = sh->brk_a[j] >= 64u ? float_below(conc_from_key(sh->brk_a[j] - 64u)) : -1.f;
+                        sh->fast_hi[j] = sh->brk_b[j] + 64u < (1u << KEY_BITS) ? float_above(conc_from_key(sh->brk_b[j] + 64u)) : INFINITY;
                     }
                     __syncthreads();
                     // ---------------------------------------------------------- C1': count below / collect inside the brackets
                     const unsigned ka0 = sh->brk_a[0], kb0 = sh->brk_b[0], ka1 = sh->brk_a[1], kb1 = sh->brk_b[1];
+                    const float lo0 = sh->fast_lo[0], hi0 = sh->fast_hi[0], lo1 = sh->fast_lo[1], hi1 = sh->fast_hi[1];
                     unsigned* list0 = sh->hist;
                     unsigned* list1 = sh->hist + LIST_CAP;
                     unsigned below0 = 0, below1 = 0;
-                    for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int) {
-                        constexpr bool TAIL = decltype(tail)::value;
-                        for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
+                    auto bracket_pass = [&](auto unit) {
+                        // exact treatment of one pixel (packed RGB): a stain whose concentration the float test could not
+                        // classify gets its exact key; the arithmetic repeats the main loop's, so the same test decides.
+                        auto exact_px = [&](bool has, uint32_t v, bool recount) {
+                            const float o0 = od_lookup(od_rep, v, lane_off, 0), o1 = od_lookup(od_rep, v, lane_off, 1), o2 = od_lookup(od_rep, v, lane_off, 2);
                             float c0, c1;
-                            lasso2(lk, o0, o1, o2, c0, c1);
+                            if (decltype(unit)::value) lasso2_unit(lk, o0, o1, o2, c0, c1); else lasso2(lk, o0, o1, o2, c0, c1);
                             const uint32_t k0 = conc_key(c0), k1 = conc_key(c1);
-                            if (!TAIL || i < nvalid) {
+                            if (has && (recount || (!(c0 < lo0) && !(c0 > hi0)))) {
                                 if (k0 < ka0) ++below0;
                                 else if (k0 < kb0) { const unsigned idx = atomicAdd(&sh->l_len[0], 1u); if (idx < LIST_CAP) list0[idx] = k0; }
+                            }
+                            if (has && (recount || (!(c1 < lo1) && !(c1 > hi1)))) {
                                 if (k1 < ka1) ++below1;
                                 else if (k1 < kb1) { const unsigned idx = atomicAdd(&sh->l_len[1], 1u); if (idx < LIST_CAP) list1[idx] = k1; }
                             }
+                        };
+                        auto drain_px = [&](bool has, uint32_t v) { exact_px(has, v, false); };
+                        WarpQueue wq{sh->wq[threadIdx.x >> 5], 0u};
+                        for_each_group_uniform(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], bool active, int g) {
+                            unsigned cb0 = 0, cb1 = 0, slow = 0;
+                            for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
+                                float c0, c1;
+                                if (decltype(unit)::value) lasso2_unit(lk, o0, o1, o2, c0, c1); else lasso2(lk, o0, o1, o2, c0, c1);
+                                const bool b0 = c0 < lo0, b1 = c1 < lo1;
+                                cb0 += b0 ? 1u : 0u;
+                                cb1 += b1 ? 1u : 0u;
+                                const bool s01 = (!b0 & !(c0 > hi0)) | (!b1 & !(c1 > hi1));
+                                slow |= s01 ? (1u << i) : 0u;
+                            });
+                            if (active) { below0 += cb0; below1 += cb1; } else slow = 0;
+                            wq_push_flagged(wq, slow, tin + (size_t)g * (GROUP_PX * 3), &sh->wq_overflow, [](int) { return 0u; });
+                            wq_drain(wq, false, drain_px);
                         });
-                    });
+                        wq_drain(wq, true, drain_px);
+                        if ((npx % GROUP_PX) != 0 && ge == G && threadIdx.x == 0) {
+                            uint32_t w[12];
+                            int nvalid;
+                            load_group<true>(tin, npx, G - 1, false, w, nvalid);
+#pragma unroll
+                            for (int i = 0; i < GROUP_PX; ++i)
+                                if (i < nvalid) exact_px(true, pixel_word(w, i), true);
+                        }
+                    };
+                    if (lk.rg00 == 1.0f && lk.rg11 == 1.0f) bracket_pass(IsTail{}); else if (threadIdx.x == 0) sh->wq_overflow = 1;   // non-unit rows: robust path
                     below0 = warp_sum_u(below0); below1 = warp_sum_u(below1);
                     if ((threadIdx.x & 31) == 0) { if (below0) atomicAdd(&sh->l_below[0], below0); if (below1) atomicAdd(&sh->l_below[1], below1); }
                     __syncthreads();
                     if (threadIdx.x == 0) {
-                        bool ok = true;
+                        bool ok = sh->wq_overflow == 0;
                         for (int j = 0; j < 2; ++j)
                             ok = ok && sh->l_len[j] <= LIST_CAP && sh->l_below[j] <= c_lo && c_hi < sh->l_below[j] + sh->l_len[j];
                         sh->s_ok = ok ? 1 : 0;

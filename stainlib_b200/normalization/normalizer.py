@@ -73,6 +73,17 @@ class ExtractiveStainNormalizer(object):
         self.stain_matrix_target = vec[:6].reshape(2, 3).numpy().copy()
         self.maxC_target = vec[6:].reshape(1, 2).numpy().copy()
 
+    def _target_on_device(self, device):
+        """float64 [8] = stain_matrix_target (6) + maxC_target (2) on ``device``; uploaded once per fit (the attributes
+        may also be assigned by hand, so the cache is keyed on their current values)."""
+        vec = np.concatenate([np.asarray(self.stain_matrix_target, dtype=np.float64).reshape(6),
+                              np.asarray(self.maxC_target, dtype=np.float64).reshape(2)])
+        hit = getattr(self, "_tgt_cache", None)
+        if hit is None or hit[0] != device or not np.array_equal(hit[1], vec):
+            hit = (device, vec, torch.as_tensor(vec).to(device))
+            self._tgt_cache = hit
+        return hit[2]
+
     @property
     def target_concentrations(self):
         """normalizer.py:35 keeps the N x 2 target concentrations; nothing reads them, so they are computed on demand."""
@@ -101,8 +112,7 @@ class ExtractiveStainNormalizer(object):
             return out
         b = nv.Batch(I)
         out = b.new_like()
-        tgt = torch.as_tensor(np.concatenate([self.stain_matrix_target.reshape(6), self.maxC_target.reshape(2)]),
-                              dtype=torch.float64).to(b.dev.device)
+        tgt = self._target_on_device(b.dev.device)
         status = b.dev_tensor((b.B,), torch.int32)
         nv.check(lib.sb_normalize(b.handle, nv.ptr(b.dev), nv.ptr(out), b.B, b.H, b.W, ctypes.byref(p), nv.ptr(tgt),
                                   ctypes.c_void_p(tgt.data_ptr() + 48), None, None, nv.ptr(status), nv.stream_ptr(b.idx)))
