@@ -11,7 +11,9 @@ only collective is the one all-reduce of the fitted target statistics in fit()).
 
   value     device-resident throughput: inputs already in HBM, CUDA events on the launching stream, max over ranks.
   e2e       same metric through the public API with pinned HOST tensors: H2D + kernels + D2H inside the timed region.
-  roofline  fused tile-pipeline kernel: 6 algorithmic bytes per pixel / launch duration vs MEASURED_PEAKS.json.
+  roofline  dominant kernel of the step (tile_pipeline_kernel, read-only, 3 algorithmic B/px), timed alone with CUDA
+            events; roofline_k4 = the fused OD+recombine kernel (6 B/px); roofline_step = the whole step at 6 B/px;
+            all against MEASURED_PEAKS.json.
   cpu_baseline  the numpy/OpenCV oracle port of the reference path on the host cores, bounded sample (rank 0, N=1).
 
 --impl reference times that same CPU port (oracle/stain_oracle.py -- the reference is pure Python and cannot travel
@@ -78,26 +80,52 @@ def cpu_throughput(method, H, W, n_tiles, tiles=None):
 
 # ----------------------------------------------------------------------------------------------- clock sampling
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clock and throttle reasons DURING the timed region (NVML, every 2 ms; nvidia-smi as fallback)."""
 
     def __init__(self, index):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.mhz, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop, self._t = threading.Event(), None
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            self.mhz.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+            self._stop.wait(0.002)
+
+    def _run_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+            if len(out) >= 6 and out[0].strip().isdigit():
+                self.mhz.append(int(out[0])); self.max_mhz = int(out[1])
+                self.reasons.update(n for n, v in zip(names, out[2:]) if v.strip().lower() == "active")
+            self._stop.wait(0.05)
 
     def _run(self):
-        while not self._stop.is_set():
+        try:
+            self._run_nvml()
+        except Exception:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self._run_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
+        time.sleep(0.01)
         return self
 
     def __exit__(self, *a):
@@ -105,13 +133,10 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        if not self.samples:
+        if not self.mhz:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower() == "active" for s in self.samples)]
-        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        m = sorted(self.mhz)
+        return {"sm_mhz": m[len(m) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(m)}
 
 
 def measured_peak():
@@ -121,11 +146,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload):
-    """dram bytes per launch of the fused kernel from the committed ncu --set full summary, or None."""
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_summary.py), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
-        return json.load(open(p)).get(workload)
+        return json.load(open(p)).get(workload, {}).get(kernel)
     return None
 
 
@@ -239,28 +265,40 @@ def main():
     value = world * npx_rank * args.steps / (ms_total_max * 1e-3) / 1e6
     status_bad = int((norm.last_status != 0).sum().item())
 
-    # ---- K4 alone (the fused OD+recombine kernel of north_star)
+    # ---- the two kernels of a step, each timed alone with CUDA events on the launching stream
     import ctypes
     M_src = torch.empty(B, 2, 3, dtype=torch.float64, device="cuda")
     maxC = torch.empty(B, 2, dtype=torch.float64, device="cuda")
     p = norm._params()
     h, _ = nv.get_handle(local)
     lib = nv.load_library()
-    nv.check(lib.sb_fit(h, nv.ptr(dev_in), B, H, W, ctypes.byref(p), nv.ptr(M_src), nv.ptr(maxC), None, nv.stream_ptr(local)))
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    stats_ms = timed(lambda: nv.check(lib.sb_fit(h, nv.ptr(dev_in), B, H, W, ctypes.byref(p), nv.ptr(M_src), nv.ptr(maxC), None,
+                                                 nv.stream_ptr(local))), args.steps)
     scale = (torch.as_tensor(norm.maxC_target, device="cuda") / maxC).contiguous()
     Mt = torch.as_tensor(norm.stain_matrix_target, device="cuda").contiguous()
     out2 = torch.empty_like(dev_in)
-    for _ in range(3):
-        nv.check(lib.sb_recombine(h, nv.ptr(dev_in), nv.ptr(out2), B, H, W, nv.ptr(M_src), nv.ptr(scale), nv.ptr(Mt), 0.01, nv.stream_ptr(local)))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        nv.check(lib.sb_recombine(h, nv.ptr(dev_in), nv.ptr(out2), B, H, W, nv.ptr(M_src), nv.ptr(scale), nv.ptr(Mt), 0.01, nv.stream_ptr(local)))
-    e1.record()
-    torch.cuda.synchronize()
-    k4_ms = e0.elapsed_time(e1) / args.steps
+    k4_ms = timed(lambda: nv.check(lib.sb_recombine(h, nv.ptr(dev_in), nv.ptr(out2), B, H, W, nv.ptr(M_src), nv.ptr(scale), nv.ptr(Mt), 0.01,
+                                                    nv.stream_ptr(local))), args.steps)
     k4_match = bool(torch.equal(out2, out)) if status_bad == 0 else None
+    # plain device-to-device copy in this process, same timing method: sanity check of the box against MEASURED_PEAKS.json
+    probe = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    probe2 = torch.empty_like(probe)
+    copy_ms = timed(lambda: probe2.copy_(probe), 5)
+    hbm_probe = 2 * probe.numel() / (copy_ms * 1e-3) / 1e9
+    del probe, probe2
 
     # ---- end to end from pinned host memory through the public API
     e2e = None
@@ -284,9 +322,10 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        med_launch_ms = float(np.median(per_launch_ms))
-        achieved = npx_rank * BYTES_PER_PX / (med_launch_ms * 1e-3) / 1e9
-        k4_achieved = npx_rank * BYTES_PER_PX / (k4_ms * 1e-3) / 1e9
+        med_step_ms = float(np.median(per_launch_ms))
+        stats_gbs = npx_rank * 3.0 / (stats_ms * 1e-3) / 1e9
+        k4_gbs = npx_rank * BYTES_PER_PX / (k4_ms * 1e-3) / 1e9
+        step_gbs = npx_rank * BYTES_PER_PX / (med_step_ms * 1e-3) / 1e9
         line = {
             "metric": f"Mpixels/sec stain-normalize ({method})", "value": round(value, 1), "unit": "Mpx/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total_max / args.steps, 4),
@@ -294,17 +333,22 @@ def main():
             "dtype": "f32 per-pixel arithmetic on u8 pixels, f64 per-tile reductions", "data": "synthetic",
             "config": {"workload": desc, "tiles_per_gpu": B, "tile": [H, W], "method": method,
                        "l2_policy": f"input {host_in.numel() / 1e6:.0f} MB + output per GPU, larger than the 126 MB L2; no flush needed",
-                       "flagged_tiles": status_bad},
+                       "flagged_tiles": status_bad, "kernels_per_step": "tile_pipeline_kernel + k4_prepare_normalize_kernel + recombine_tma_kernel"},
             "clocks": clocks.summary(),
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "tile_pipeline_kernel (fused mask+moments, percentiles, LASSO, recombine)",
-                         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "peak_source": peak_src, "algorithmic_bytes_per_px": BYTES_PER_PX, "traffic": ncu_traffic(args.workload),
-                         "launch_ms_median": round(med_launch_ms, 4)},
-            "roofline_k4": {"bound": "hbm", "kernel": "recombine_kernel (fused OD+recombine alone, sb_recombine)",
-                            "achieved": round(k4_achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(k4_achieved / peak, 4),
-                            "launch_ms": round(k4_ms, 4), "bytes_equal_fused_path": k4_match},
+            # dominant kernel of the step: the fused per-tile statistics kernel (read-only: 3 algorithmic bytes per pixel)
+            "roofline": {"bound": "hbm", "kernel": "tile_pipeline_kernel (mask+moments, exact angular and concentration percentiles)",
+                         "achieved": round(stats_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(stats_gbs / peak, 4),
+                         "peak_source": peak_src, "algorithmic_bytes_per_px": 3.0, "launch_ms": round(stats_ms, 4),
+                         "share_of_step": round(stats_ms / med_step_ms, 3), "traffic": ncu_traffic(args.workload, "tile_pipeline_kernel")},
+            "roofline_k4": {"bound": "hbm", "kernel": "recombine_tma_kernel (fused OD+recombine, TMA ring)",
+                            "achieved": round(k4_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(k4_gbs / peak, 4),
+                            "algorithmic_bytes_per_px": BYTES_PER_PX, "launch_ms": round(k4_ms, 4), "share_of_step": round(k4_ms / med_step_ms, 3),
+                            "bytes_equal_transform_path": k4_match, "traffic": ncu_traffic(args.workload, "recombine_tma_kernel")},
+            "roofline_step": {"bound": "hbm", "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(step_gbs / peak, 4),
+                              "algorithmic_bytes_per_px": BYTES_PER_PX, "step_ms_median": round(med_step_ms, 4)},
+            "hbm_probe_gbs": round(hbm_probe, 1),
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
