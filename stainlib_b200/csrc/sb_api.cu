@@ -253,7 +253,7 @@ int sb_normalize_host(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int
     SB_CUDA(cudaSetDevice(h->device));
     const size_t tile_bytes = (size_t)H * W * 3;
     if (chunk_tiles <= 0) {
-        chunk_tiles = (int)(((size_t)48 << 20) / tile_bytes);
+        chunk_tiles = (int)(((size_t)12 << 20) / tile_bytes);   // 12 MB chunks: short fill/drain, still link-rate copies (tools/pcie_probe.py)
         if (chunk_tiles < 1) chunk_tiles = 1;
     }
     if (chunk_tiles > B) chunk_tiles = B;

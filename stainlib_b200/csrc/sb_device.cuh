@@ -130,18 +130,31 @@ __device__ __forceinline__ void lasso2(const LassoK& k, float o0, float o1, floa
     c1 = both ? a1 : ((!only0 & only1) ? p1 : 0.f);
 }
 
-// Same problem when the dictionary rows have unit norm (Gram diagonal exactly 1 in fp32): with the unconstrained
-// solution infeasible, the optimum lies on one axis and is the better of the two axis optima max(u_j, 0).
+// Same problem when the dictionary rows have unit norm (Gram diagonal exactly 1 in fp32), g = G01.  With u = G a:
+//   g >= 0:  a1 > 0  <=>  a0 < u0, and the optimum is  c0 = max(0, min(a0, u0))   (a1 <= 0 puts c on axis 0: max(u0, 0));
+//   g <  0:  a1 > 0  <=>  a0 > u0, and the optimum is  c0 = max(0, a0, u0)        (one 3-input FMNMX3 on sm_100);
+// symmetrically for c1.  No compares, no selects: 4 (or 2) min/max instructions per pixel.
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+enum { LASSO_GENERAL = 0, LASSO_UNIT_POS = 1, LASSO_UNIT_NEG = 2 };
+template <int LM>
+__device__ __forceinline__ void lasso2_select(float a0, float a1, float u0, float u1, float& c0, float& c1) {
+    if (LM == LASSO_UNIT_POS) { c0 = fmaxf(0.f, fminf(a0, u0)); c1 = fmaxf(0.f, fminf(a1, u1)); }
+    else { c0 = max3f(0.f, a0, u0); c1 = max3f(0.f, a1, u1); }
+}
+template <int LM>
 __device__ __forceinline__ void lasso2_unit(const LassoK& k, float o0, float o1, float o2, float& c0, float& c1) {
     const float u0 = fmaf(k.m02, o2, fmaf(k.m01, o1, fmaf(k.m00, o0, -k.lam)));
     const float u1 = fmaf(k.m12, o2, fmaf(k.m11, o1, fmaf(k.m10, o0, -k.lam)));
     const float a0 = fmaf(k.i01, u1, k.i00 * u0);
     const float a1 = fmaf(k.i11, u1, k.i01 * u0);
-    const bool both = (a0 > 0.f) & (a1 > 0.f);
-    const float x0 = fmaxf(u0, 0.f), x1 = fmaxf(u1, 0.f);
-    const bool pick0 = x0 >= x1;
-    c0 = both ? a0 : (pick0 ? x0 : 0.f);
-    c1 = both ? a1 : (pick0 ? 0.f : x1);
+    lasso2_select<LM>(a0, a1, u0, u1, c0, c1);
+}
+__host__ __device__ inline int lasso_mode_of(float rg00, float rg11, float g01) {
+    return (rg00 == 1.0f && rg11 == 1.0f) ? (g01 >= 0.f ? LASSO_UNIT_POS : LASSO_UNIT_NEG) : LASSO_GENERAL;
 }
 
 __host__ __device__ inline void make_lasso_consts(const double M[6], double lam, LassoK& k) {
@@ -191,7 +204,7 @@ struct __align__(16) K4Consts {
     float i00, i01, i11;
     float rg00, rg11, g01;
     float A[6];      // -scale_j * Mt_jk * log2(e)
-    int unit_diag, need_check;
+    int lasso_mode, need_check;   // LASSO_GENERAL / LASSO_UNIT_POS / LASSO_UNIT_NEG; need_check: 255*2^e may reach 2^23
     int mode;        // 0 = recombine, 1 = write zeros (reference divides by a zero percentile), 2 = copy the input through
 };
 
@@ -201,22 +214,30 @@ __device__ __forceinline__ float od_lookup(const unsigned char* tab, uint32_t w,
     return *reinterpret_cast<const float*>(tab + off);
 }
 
+// Same lookup with an ABSOLUTE shared-window address: the table sits at a 64 KB-aligned shared address T, and
+// lane_base = (lane << 2) | ((T >> 16) << 8), so the one PRMT yields T | value << 8 | lane << 2 -- no address add.
+struct OdAbs { uint32_t lane_base; };
+__device__ __forceinline__ float od_lookup(const OdAbs& t, uint32_t w, uint32_t /*lane_off*/, int k) {
+    const uint32_t addr = __byte_perm(w, t.lane_base, 0x6504u | (k << 4));
+    float r;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float od_lookup(const OdAbs* t, uint32_t w, uint32_t lane_off, int k) { return od_lookup(*t, w, lane_off, k); }
+
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
 
-template <bool CHECK, bool UNIT>
+template <bool CHECK, int LM>
 __device__ __forceinline__ void recombine_pair(const K4Consts& k, const float2 o0, const float2 o1, const float2 o2, uint32_t (&bits)[6]) {
     const float2 u0 = __ffma2_rn(dup(k.m[2]), o2, __ffma2_rn(dup(k.m[1]), o1, __ffma2_rn(dup(k.m[0]), o0, dup(k.nlam))));
     const float2 u1 = __ffma2_rn(dup(k.m[5]), o2, __ffma2_rn(dup(k.m[4]), o1, __ffma2_rn(dup(k.m[3]), o0, dup(k.nlam))));
     const float2 a0 = __ffma2_rn(dup(k.i01), u1, __fmul2_rn(dup(k.i00), u0));
     const float2 a1 = __ffma2_rn(dup(k.i11), u1, __fmul2_rn(dup(k.i01), u0));
     float2 c0, c1;
-    if (UNIT) {
-        const float x0a = fmaxf(u0.x, 0.f), x1a = fmaxf(u1.x, 0.f), x0b = fmaxf(u0.y, 0.f), x1b = fmaxf(u1.y, 0.f);
-        const bool ba = (a0.x > 0.f) & (a1.x > 0.f), bb = (a0.y > 0.f) & (a1.y > 0.f);
-        const bool pa = x0a >= x1a, pb = x0b >= x1b;
-        c0.x = ba ? a0.x : (pa ? x0a : 0.f); c1.x = ba ? a1.x : (pa ? 0.f : x1a);
-        c0.y = bb ? a0.y : (pb ? x0b : 0.f); c1.y = bb ? a1.y : (pb ? 0.f : x1b);
+    if (LM != LASSO_GENERAL) {
+        lasso2_select<LM>(a0.x, a1.x, u0.x, u1.x, c0.x, c1.x);
+        lasso2_select<LM>(a0.y, a1.y, u0.y, u1.y, c0.y, c1.y);
     } else {
         // general Gram diagonal: KKT form (same as lasso2 in sb_device.cuh)
         const float p0a = fmaxf(u0.x, 0.f) * k.rg00, p1a = fmaxf(u1.x, 0.f) * k.rg11;
@@ -257,33 +278,53 @@ __device__ inline void make_k4_consts(const double M[6], double lam, const doubl
     make_lasso_consts(M, lam, lk);
     k.m[0] = lk.m00; k.m[1] = lk.m01; k.m[2] = lk.m02; k.m[3] = lk.m10; k.m[4] = lk.m11; k.m[5] = lk.m12;
     k.nlam = -lk.lam; k.i00 = lk.i00; k.i01 = lk.i01; k.i11 = lk.i11; k.rg00 = lk.rg00; k.rg11 = lk.rg11; k.g01 = lk.g01;
-    k.unit_diag = (lk.rg00 == 1.0f && lk.rg11 == 1.0f) ? 1 : 0;
+    k.lasso_mode = lasso_mode_of(lk.rg00, lk.rg11, lk.g01);
     const double LOG2E = 1.4426950408889634;
-    bool finite = true, need = false;
+    bool finite = true;
     for (int j = 0; j < 2; ++j) {
         finite = finite && isfinite(scale[j]);
-        for (int c = 0; c < 3; ++c) {
-            const double v = -scale[j] * Mt[3 * j + c] * LOG2E;
-            k.A[3 * j + c] = (float)v;
-            need = need || !(v <= 0.0);
-        }
+        for (int c = 0; c < 3; ++c) k.A[3 * j + c] = (float)(-scale[j] * Mt[3 * j + c] * LOG2E);
+    }
+    // The magic-add uint8 wrap is exact while 255 * 2^e < 2^23.  With a negative target-matrix entry some A is positive
+    // and e can exceed log2(255); bound it from the largest concentration any uint8 pixel can have (OD <= ln 255):
+    //   g >= 0: G_jj c_j <= u_j;   g < 0: c_0 <= max(u_0 / G_00, i00 u_0 + i01 u_1) with i01 > 0 (and symmetrically).
+    const double ODMAX = 5.541263545158426;
+    const double g00 = M[0] * M[0] + M[1] * M[1] + M[2] * M[2], g11 = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
+    const double g01 = M[0] * M[3] + M[1] * M[4] + M[2] * M[5], det = g00 * g11 - g01 * g01;
+    double U[2];
+    for (int j = 0; j < 2; ++j) {
+        double s = -lam;
+        for (int c = 0; c < 3; ++c) s += (M[3 * j + c] > 0.0 ? M[3 * j + c] : 0.0) * ODMAX;
+        U[j] = s > 0.0 ? s : 0.0;
+    }
+    double cb[2] = {U[0] / g00, U[1] / g11};
+    if (g01 < 0.0) {
+        const double b0 = (g11 * U[0] - g01 * U[1]) / det, b1 = (g00 * U[1] - g01 * U[0]) / det;
+        cb[0] = b0 > cb[0] ? b0 : cb[0];
+        cb[1] = b1 > cb[1] ? b1 : cb[1];
+    }
+    bool need = false;
+    for (int c = 0; c < 3; ++c) {
+        const double a0 = k.A[c] > 0.f ? (double)k.A[c] : 0.0, a1 = k.A[3 + c] > 0.f ? (double)k.A[3 + c] : 0.0;
+        const double emax = 8.0 + cb[0] * a0 + cb[1] * a1;
+        need = need || !(emax < 22.0) || !isfinite(k.A[c]) || !isfinite(k.A[3 + c]);
     }
     k.need_check = need ? 1 : 0;
     k.mode = finite ? 0 : 1;
 }
 
 // 16 pixels (12 packed words) -> 16 recombined pixels.
-template <bool CHECK, bool UNIT>
-__device__ __forceinline__ void recombine_words(const K4Consts& k, const unsigned char* tab, const uint32_t (&w)[12], uint32_t (&o)[12], uint32_t lane_off) {
+template <bool CHECK, int LM, class TAB>
+__device__ __forceinline__ void recombine_words(const K4Consts& k, const TAB tab, const uint32_t (&w)[12], uint32_t (&o)[12], uint32_t lane_off) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
         // pixels: p0=(a0,a1,a2) p1=(a3,b0,b1) p2=(b2,b3,c0) p3=(c1,c2,c3)
         uint32_t b01[6], b23[6];
-        recombine_pair<CHECK, UNIT>(k, f2(od_lookup(tab, wa, lane_off, 0), od_lookup(tab, wa, lane_off, 3)),
+        recombine_pair<CHECK, LM>(k, f2(od_lookup(tab, wa, lane_off, 0), od_lookup(tab, wa, lane_off, 3)),
                                     f2(od_lookup(tab, wa, lane_off, 1), od_lookup(tab, wb, lane_off, 0)),
                                     f2(od_lookup(tab, wa, lane_off, 2), od_lookup(tab, wb, lane_off, 1)), b01);
-        recombine_pair<CHECK, UNIT>(k, f2(od_lookup(tab, wb, lane_off, 2), od_lookup(tab, wc, lane_off, 1)),
+        recombine_pair<CHECK, LM>(k, f2(od_lookup(tab, wb, lane_off, 2), od_lookup(tab, wc, lane_off, 1)),
                                     f2(od_lookup(tab, wb, lane_off, 3), od_lookup(tab, wc, lane_off, 2)),
                                     f2(od_lookup(tab, wc, lane_off, 0), od_lookup(tab, wc, lane_off, 3)), b23);
         o[3 * q] = pack4(b01[0], b01[1], b01[2], b01[3]);

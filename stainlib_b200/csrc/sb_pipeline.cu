@@ -159,6 +159,7 @@ __device__ inline void plan_level2(PipeShared* sh, const unsigned src[4]) {
 // Runs f over this CTA's share [gb, ge) of the tile's 16-pixel groups.  Complete groups go through the main loop with
 // TAIL = false_type (no validity checks); the single ragged group of a tile whose pixel count is not a multiple of 16
 // is handled by one thread with TAIL = true_type.  f(tail, w, nvalid, g) sees the raw 12 words of the group.
+template <int LM> struct LassoMode { static constexpr int value = LM; };
 struct NoTail { static constexpr bool value = false; };
 struct IsTail { static constexpr bool value = true; };
 
@@ -802,7 +803,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                         auto exact_px = [&](bool has, uint32_t v, bool recount) {
                             const float o0 = od_lookup(od_rep, v, lane_off, 0), o1 = od_lookup(od_rep, v, lane_off, 1), o2 = od_lookup(od_rep, v, lane_off, 2);
                             float c0, c1;
-                            if (decltype(unit)::value) lasso2_unit(lk, o0, o1, o2, c0, c1); else lasso2(lk, o0, o1, o2, c0, c1);
+                            lasso2_unit<decltype(unit)::value>(lk, o0, o1, o2, c0, c1);
                             const uint32_t k0 = conc_key(c0), k1 = conc_key(c1);
                             if (has && (recount || (!(c0 < lo0) && !(c0 > hi0)))) {
                                 if (k0 < ka0) ++below0;
@@ -819,7 +820,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                             unsigned cb0 = 0, cb1 = 0, slow = 0;
                             for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                                 float c0, c1;
-                                if (decltype(unit)::value) lasso2_unit(lk, o0, o1, o2, c0, c1); else lasso2(lk, o0, o1, o2, c0, c1);
+                                lasso2_unit<decltype(unit)::value>(lk, o0, o1, o2, c0, c1);
                                 const bool b0 = c0 < lo0, b1 = c1 < lo1;
                                 cb0 += b0 ? 1u : 0u;
                                 cb1 += b1 ? 1u : 0u;
@@ -840,7 +841,10 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                                 if (i < nvalid) exact_px(true, pixel_word(w, i), true);
                         }
                     };
-                    if (lk.rg00 == 1.0f && lk.rg11 == 1.0f) bracket_pass(IsTail{}); else if (threadIdx.x == 0) sh->wq_overflow = 1;   // non-unit rows: robust path
+                    const int lm = lasso_mode_of(lk.rg00, lk.rg11, lk.g01);
+                    if (lm == LASSO_UNIT_POS) bracket_pass(LassoMode<LASSO_UNIT_POS>{});
+                    else if (lm == LASSO_UNIT_NEG) bracket_pass(LassoMode<LASSO_UNIT_NEG>{});
+                    else if (threadIdx.x == 0) sh->wq_overflow = 1;   // non-unit rows: robust path
                     below0 = warp_sum_u(below0); below1 = warp_sum_u(below1);
                     if ((threadIdx.x & 31) == 0) { if (below0) atomicAdd(&sh->l_below[0], below0); if (below1) atomicAdd(&sh->l_below[1], below1); }
                     __syncthreads();

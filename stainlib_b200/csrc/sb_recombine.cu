@@ -7,15 +7,16 @@
 //   * all multiply-adds run two pixels at a time on the packed f32x2 pipe (FFMA2 / FADD2.RD, sm_100 only);
 //   * the "value >= 2^23" / NaN guard of the unclipped uint8 wrap is hoisted to a block-uniform template flag: it is
 //     only compiled in when the target matrix has a negative entry (otherwise 255*exp(.) <= 255 always);
-//   * with row-normalised stain matrices (unit Gram diagonal) the single-active-stain case of the LASSO reduces to
-//     "keep the larger of max(u0,0), max(u1,0)".
+//   * with row-normalised stain matrices (unit Gram diagonal) the whole LASSO case analysis collapses to
+//     c_j = max(0, min(a_j, u_j)) (or one 3-input max when the stain vectors have a negative dot product): no compares;
+//   * in the TMA kernel the table sits at a 64 KB-aligned shared address, so the PRMT output IS the LDS address.
 #include <cstdlib>
 #include "sb_kernels.h"
 
 namespace sb {
 
 constexpr int RT = 256;                       // threads per CTA
-template <bool CHECK, bool UNIT>
+template <bool CHECK, int LM>
 __device__ __forceinline__ void recombine_loop(const PointArgs& a, const K4Consts& k, const unsigned char* tab, int tile) {
     const uint8_t* __restrict__ tin = a.in + (size_t)tile * a.npx * 3;
     uint8_t* __restrict__ tout = a.out + (size_t)tile * a.npx * 3;
@@ -26,7 +27,7 @@ __device__ __forceinline__ void recombine_loop(const PointArgs& a, const K4Const
         uint32_t w[12], o[12];
         int nvalid;
         load_group<false>(tin, a.npx, g, aligned, w, nvalid);
-        recombine_words<CHECK, UNIT>(k, tab, w, o, lane_off);
+        recombine_words<CHECK, LM>(k, tab, w, o, lane_off);
         store_group(tout, a.npx, g, aligned, o);
     }
 }
@@ -53,10 +54,14 @@ __global__ void __launch_bounds__(RT, 3) recombine_v2_kernel(PointArgs a, const 
         }
         return;
     }
-    if (k.need_check) {
-        if (k.unit_diag) recombine_loop<true, true>(a, k, od_rep, tile); else recombine_loop<true, false>(a, k, od_rep, tile);
-    } else {
-        if (k.unit_diag) recombine_loop<false, true>(a, k, od_rep, tile); else recombine_loop<false, false>(a, k, od_rep, tile);
+    const unsigned char* tab = od_rep;
+    switch ((k.need_check ? 3 : 0) + k.lasso_mode) {
+        case 0: recombine_loop<false, LASSO_GENERAL>(a, k, tab, tile); break;
+        case 1: recombine_loop<false, LASSO_UNIT_POS>(a, k, tab, tile); break;
+        case 2: recombine_loop<false, LASSO_UNIT_NEG>(a, k, tab, tile); break;
+        case 3: recombine_loop<true, LASSO_GENERAL>(a, k, tab, tile); break;
+        case 4: recombine_loop<true, LASSO_UNIT_POS>(a, k, tab, tile); break;
+        default: recombine_loop<true, LASSO_UNIT_NEG>(a, k, tab, tile); break;
     }
 }
 
@@ -120,7 +125,7 @@ __global__ void k4_prepare_normalize_kernel(int B, const double* __restrict__ M_
     if (st != 0) {
         for (int j = 0; j < 6; ++j) { k.m[j] = 0.f; k.A[j] = 0.f; }
         k.nlam = k.i00 = k.i01 = k.i11 = k.rg00 = k.rg11 = k.g01 = 0.f;
-        k.unit_diag = k.need_check = 0;
+        k.lasso_mode = k.need_check = 0;
         k.mode = 2;
     } else {
         double M[6], Mt[6], sc[2];
@@ -132,26 +137,43 @@ __global__ void k4_prepare_normalize_kernel(int B, const double* __restrict__ M_
     out[tile] = k;
 }
 
-template <bool CHECK, bool UNIT>
-__device__ __forceinline__ void recombine_group_smem(const K4Consts& k, const unsigned char* tab, uint4* grp, uint32_t lane_off) {
+template <bool CHECK, int LM>
+__device__ __forceinline__ void recombine_group_smem(const K4Consts& k, const OdAbs tab, uint4* grp) {
     const uint4 va = grp[0], vb = grp[1], vc = grp[2];
     const uint32_t w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
     uint32_t o[12];
-    recombine_words<CHECK, UNIT>(k, tab, w, o, lane_off);
+    recombine_words<CHECK, LM>(k, tab, w, o, 0u);
     grp[0] = make_uint4(o[0], o[1], o[2], o[3]);
     grp[1] = make_uint4(o[4], o[5], o[6], o[7]);
     grp[2] = make_uint4(o[8], o[9], o[10], o[11]);
 }
 
-template <int TT, int NSTAGE>
-__global__ void __launch_bounds__(TT + 32, 1) recombine_tma_kernel(PointArgs a, const K4Consts* __restrict__ consts, int chunks_per_tile, long long total_chunks) {
+// Shared-memory plan of the TMA kernel.  The CTA asks for the whole 227 KB; the 64 KB lane-replicated OD table is put
+// at the 64 KB-aligned address inside the window (so lookups need no address add), the mbarriers at the window start,
+// and the ring slots fill the space in front of and behind the table.
+constexpr int K4_SMEM_BYTES = 227 * 1024;
+constexpr int K4_BAR_BYTES = 256;
+
+// Template parameters: NG consumer groups of GT threads (+ one producer warp), NSTAGE ring slots of GT*48 bytes.  Group
+// g recombines the CTA's chunks g, g+NG, ...: two groups of 15 warps keep 30 warps resident (the 16-pixel body needs
+// 56 registers when the compiler is held to that occupancy) and work on different slots at different phases.
+template <int GT, int NG, int NSTAGE>
+__global__ void __launch_bounds__(GT * NG + 32, 1) recombine_tma_kernel(PointArgs a, const K4Consts* __restrict__ consts, int chunks_per_tile, long long total_chunks) {
+    constexpr int TT = GT * NG;
     constexpr int TT_ALL = TT + 32;
-    constexpr int CHUNK_BYTES = TT * 48;
+    constexpr int CHUNK_BYTES = GT * 48;
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* od_rep = smem;                                   // 64 KB lane-replicated OD table
-    unsigned char* stage0 = smem + OD_REP_BYTES;                    // NSTAGE x CHUNK_BYTES
-    uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + NSTAGE * CHUNK_BYTES);   // TMA load landed
-    uint64_t* done = full + NSTAGE;                                                // all compute threads wrote the stage back
+    const uint32_t base = smem_u32(smem);
+    const uint32_t tab_addr = (base + 0xFFFFu) & ~0xFFFFu;
+    unsigned char* od_rep = smem + (tab_addr - base);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                            // TMA load landed
+    uint64_t* done = full + NSTAGE;                                                // all compute warps wrote the stage back
+    const int n_front = tab_addr - base >= (uint32_t)K4_BAR_BYTES ? (int)((tab_addr - base - K4_BAR_BYTES) / CHUNK_BYTES) : 0;
+    const int n_back = ((int)K4_SMEM_BYTES - (int)(tab_addr - base) - OD_REP_BYTES) / CHUNK_BYTES;
+    if (n_front + n_back < NSTAGE || tab_addr - base < (uint32_t)K4_BAR_BYTES) __trap();   // launch_tma_variant sized the window for this
+    auto stage_ptr = [&](int s) -> unsigned char* {
+        return s < n_front ? smem + K4_BAR_BYTES + (size_t)s * CHUNK_BYTES : od_rep + OD_REP_BYTES + (size_t)(s - n_front) * CHUNK_BYTES;
+    };
     const size_t tile_bytes = (size_t)a.npx * 3;
     const long long c_begin = total_chunks * blockIdx.x / gridDim.x, c_end = total_chunks * (blockIdx.x + 1) / gridDim.x;
     const int n_local = (int)(c_end - c_begin);
@@ -164,7 +186,7 @@ __global__ void __launch_bounds__(TT + 32, 1) recombine_tma_kernel(PointArgs a, 
     };
 
     if (threadIdx.x == TT) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], TT / 32); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], GT / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -179,14 +201,14 @@ __global__ void __launch_bounds__(TT + 32, 1) recombine_tma_kernel(PointArgs a, 
                 int tile; size_t off; uint32_t bytes;
                 chunk_geom(c_begin + i, tile, off, bytes);
                 mbar_expect_tx(&full[i], bytes);
-                bulk_load(stage0 + (size_t)i * CHUNK_BYTES, a.in + (size_t)tile * tile_bytes + off, bytes, &full[i]);
+                bulk_load(stage_ptr(i), a.in + (size_t)tile * tile_bytes + off, bytes, &full[i]);
             }
             for (int i = 0; i < n_local; ++i) {
                 const int s = i % NSTAGE;
                 int tile; size_t off; uint32_t bytes;
                 chunk_geom(c_begin + i, tile, off, bytes);
                 mbar_wait(&done[s], (uint32_t)((i / NSTAGE) & 1));          // stage s holds the finished output of chunk i
-                bulk_store(a.out + (size_t)tile * tile_bytes + off, stage0 + (size_t)s * CHUNK_BYTES, bytes);
+                bulk_store(a.out + (size_t)tile * tile_bytes + off, stage_ptr(s), bytes);
                 // refill the stage of chunk i-1 once its store has finished reading shared memory
                 if (i >= 1 && i - 1 + NSTAGE < n_local) {
                     asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -194,7 +216,7 @@ __global__ void __launch_bounds__(TT + 32, 1) recombine_tma_kernel(PointArgs a, 
                     int t2; size_t o2; uint32_t b2;
                     chunk_geom(c_begin + i - 1 + NSTAGE, t2, o2, b2);
                     mbar_expect_tx(&full[ps], b2);
-                    bulk_load(stage0 + (size_t)ps * CHUNK_BYTES, a.in + (size_t)t2 * tile_bytes + o2, b2, &full[ps]);
+                    bulk_load(stage_ptr(ps), a.in + (size_t)t2 * tile_bytes + o2, b2, &full[ps]);
                 }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -202,50 +224,58 @@ __global__ void __launch_bounds__(TT + 32, 1) recombine_tma_kernel(PointArgs a, 
         return;
     }
     // ---------------------------------------------------------------------- compute warps
-    const uint32_t lane_off = (threadIdx.x & 31) << 2;
+    const OdAbs tab{((threadIdx.x & 31u) << 2) | ((tab_addr >> 16) << 8)};
     const bool copy_only = a.debug_copy != 0;
-    int i = 0;
+    const int gidx = threadIdx.x / GT, tig = threadIdx.x - gidx * GT;
+    int i = gidx;
     while (i < n_local) {
-        // run of chunks that belong to one tile: constants are loaded once per run
-        const int tile = (int)((c_begin + i) / chunks_per_tile);
-        const int first_in_tile = (int)((c_begin + i) % chunks_per_tile);
-        int run = chunks_per_tile - first_in_tile;
-        if (run > n_local - i) run = n_local - i;
-        const K4Consts k = consts[tile];
-        const int variant = (copy_only || k.mode == 2) ? 5 : (k.mode == 1 ? 4 : (k.need_check ? 2 : 0) + (k.unit_diag ? 1 : 0));
-        for (int j = 0; j < run; ++j, ++i) {
-            const int s = i % NSTAGE;
-            const uint32_t parity = (uint32_t)((i / NSTAGE) & 1);
-            const size_t off = (size_t)(first_in_tile + j) * CHUNK_BYTES;
-            const size_t rem = tile_bytes - off;
-            const uint32_t bytes = (uint32_t)(rem < (size_t)CHUNK_BYTES ? rem : (size_t)CHUNK_BYTES);
-            unsigned char* buf = stage0 + (size_t)s * CHUNK_BYTES;
-            mbar_wait(&full[s], parity);
-            if (threadIdx.x * 48u < bytes) {
-                uint4* grp = reinterpret_cast<uint4*>(buf + threadIdx.x * 48u);
-                switch (variant) {
-                    case 0: recombine_group_smem<false, false>(k, od_rep, grp, lane_off); break;
-                    case 1: recombine_group_smem<false, true>(k, od_rep, grp, lane_off); break;
-                    case 2: recombine_group_smem<true, false>(k, od_rep, grp, lane_off); break;
-                    case 3: recombine_group_smem<true, true>(k, od_rep, grp, lane_off); break;
-                    case 4: grp[0] = grp[1] = grp[2] = make_uint4(0, 0, 0, 0); break;
-                    default: break;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk store
+      // run of this group's chunks that belong to one tile: constants are loaded once per run
+      const int i0 = i;
+      const int tile = (int)((c_begin + i0) / chunks_per_tile);
+      const int first_in_tile = (int)((c_begin + i0) - (long long)tile * chunks_per_tile);
+      int i_last = i0 + (chunks_per_tile - 1 - first_in_tile);
+      if (i_last > n_local - 1) i_last = n_local - 1;
+      const K4Consts k = consts[tile];
+      const int variant = (copy_only || k.mode == 2) ? 7 : (k.mode == 1 ? 6 : (k.need_check ? 3 : 0) + k.lasso_mode);
+      for (; i <= i_last; i += NG) {
+        const size_t off = (size_t)(first_in_tile + (i - i0)) * CHUNK_BYTES;
+        const int s = i % NSTAGE;
+        const uint32_t parity = (uint32_t)((i / NSTAGE) & 1);
+        const size_t rem = tile_bytes - off;
+        const uint32_t bytes = (uint32_t)(rem < (size_t)CHUNK_BYTES ? rem : (size_t)CHUNK_BYTES);
+        unsigned char* buf = stage_ptr(s);
+        mbar_wait(&full[s], parity);
+        if (tig * 48u < bytes) {
+            uint4* grp = reinterpret_cast<uint4*>(buf + tig * 48u);
+            switch (variant) {
+                case 0: recombine_group_smem<false, LASSO_GENERAL>(k, tab, grp); break;
+                case 1: recombine_group_smem<false, LASSO_UNIT_POS>(k, tab, grp); break;
+                case 2: recombine_group_smem<false, LASSO_UNIT_NEG>(k, tab, grp); break;
+                case 3: recombine_group_smem<true, LASSO_GENERAL>(k, tab, grp); break;
+                case 4: recombine_group_smem<true, LASSO_UNIT_POS>(k, tab, grp); break;
+                case 5: recombine_group_smem<true, LASSO_UNIT_NEG>(k, tab, grp); break;
+                case 6: grp[0] = grp[1] = grp[2] = make_uint4(0, 0, 0, 0); break;
+                default: break;
             }
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(&done[s]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk store
         }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&done[s]);
+      }
     }
 }
 
-template <int TT, int NSTAGE>
+template <int GT, int NG, int NSTAGE>
 static int launch_tma_variant(const PointArgs& a, int num_sms, cudaStream_t stream, const K4Consts* consts) {
-    constexpr int CHUNK_BYTES = TT * 48;
-    const int smem_bytes = OD_REP_BYTES + NSTAGE * CHUNK_BYTES + 2 * NSTAGE * 8;
+    constexpr int CHUNK_BYTES = GT * 48;
+    static_assert(GT % 32 == 0 && GT * NG + 32 <= 1024, "block size");
+    // the table must sit on a 64 KB boundary of the shared window wherever the window starts: take the whole 227 KB
+    static_assert(OD_REP_BYTES + NSTAGE * CHUNK_BYTES + 1024 + K4_BAR_BYTES <= K4_SMEM_BYTES, "ring does not fit");
+    static_assert(2 * NSTAGE * 8 <= K4_BAR_BYTES, "barrier area");
+    const int smem_bytes = K4_SMEM_BYTES;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(recombine_tma_kernel<TT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(recombine_tma_kernel<GT, NG, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
@@ -254,7 +284,7 @@ static int launch_tma_variant(const PointArgs& a, int num_sms, cudaStream_t stre
     const long long total = (long long)cpt * a.B;
     int grid = num_sms;
     if ((long long)grid > total) grid = (int)total;
-    recombine_tma_kernel<TT, NSTAGE><<<grid, TT + 32, smem_bytes, stream>>>(a, consts, cpt, total);
+    recombine_tma_kernel<GT, NG, NSTAGE><<<grid, GT * NG + 32, smem_bytes, stream>>>(a, consts, cpt, total);
     return (int)cudaGetLastError();
 }
 
@@ -262,13 +292,11 @@ static int launch_tma_variant(const PointArgs& a, int num_sms, cudaStream_t stre
 // vectors at a 16-byte aligned address, register-staged kernel otherwise.
 static int launch_k4(const PointArgs& a, int num_sms, cudaStream_t stream, const K4Consts* consts, bool use_tma) {
     if (use_tma) {
-        // ring geometry: 512 compute threads x 6 slots of 24 KB (chunks divide 256^2 and 512^2 tiles evenly); the sweep in
-        // profiles/r01_k4_ring_sweep.txt shows 512x6, 640x5 and 768x4 within 2 % of each other
-        static int variant = -1;
-        if (variant < 0) { const char* v = getenv("SB_K4_TT"); variant = v ? atoi(v) : 512; }
-        if (variant == 640) return launch_tma_variant<640, 5>(a, num_sms, stream, consts);
-        if (variant == 768) return launch_tma_variant<768, 4>(a, num_sms, stream, consts);
-        return launch_tma_variant<512, 6>(a, num_sms, stream, consts);
+        // ring geometry: 512 compute threads x 6 slots of 24 KB (chunks divide 256^2 and 512^2 tiles evenly); two slots sit
+        // in front of the 64 KB-aligned table, four behind it
+        // (measured alternatives, 1024 x 512^2 tiles: 2 groups x 480 threads 0.420 ms, 3 x 320 0.358 ms, 3 x 256 0.404 ms,
+        //  1 x 512 0.357 ms -- more resident warps do not help, the kernel is issue-bound, not latency-bound)
+        return launch_tma_variant<512, 1, 6>(a, num_sms, stream, consts);
     }
     static bool attr = false;
     if (!attr) {
