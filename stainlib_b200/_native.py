@@ -38,6 +38,8 @@ class SbParams(ctypes.Structure):
         ("dl_lambda", ctypes.c_double),
         ("dl_iters", ctypes.c_int),
         ("cluster_size", ctypes.c_int),
+        ("dl_sample_iters", ctypes.c_int),
+        ("dl_anderson", ctypes.c_int),
     ]
 
 

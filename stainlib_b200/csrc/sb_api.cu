@@ -76,6 +76,8 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
     a.ybound = mask_ybound_f(p->luminosity_threshold);
     a.ang_pct = p->angular_percentile; a.lasso_lambda = p->lasso_lambda; a.conc_pct = p->conc_percentile;
     a.dl_lambda = p->dl_lambda; a.dl_iters = p->dl_iters;
+    a.dl_sample_iters = p->dl_sample_iters < 0 ? 0 : p->dl_sample_iters;
+    a.dl_anderson = p->dl_anderson < 0 ? 0 : (p->dl_anderson > sb::AA_MAX ? sb::AA_MAX : p->dl_anderson);
     a.Mt = Mt; a.maxCt = maxCt;
     if (mode != sb::PIPE_NORMALIZE) {
         a.mode = mode; a.M_out = M; a.maxC_out = maxC; a.status = status;
@@ -118,8 +120,10 @@ void sb_default_params(sb_params* p) {
     p->lasso_lambda = 0.01;
     p->conc_percentile = 99.0;
     p->dl_lambda = 0.1;
-    p->dl_iters = 50;
+    p->dl_iters = 8;
     p->cluster_size = 0;
+    p->dl_sample_iters = 12;
+    p->dl_anderson = 4;
 }
 
 int sb_version(void) { return 100; }

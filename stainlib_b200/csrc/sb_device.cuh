@@ -430,6 +430,88 @@ __device__ inline void jacobi_eig3(const double a_in[6], double w[3], double v[3
     w[0] = a[0][0]; w[1] = a[1][1]; w[2] = a[2][2];
 }
 
+// ------------------------------------------------------------------------------------------------ Anderson acceleration
+// The Vahadane dictionary iteration D <- F(D) (sparse-code, accumulate, one block-coordinate update) converges linearly
+// at ~0.83 per pass; Anderson acceleration (type II, memory m <= AA_MAX) of the 6-component fixed-point map reaches
+// the same fixed point in a fifth of the passes.  Single thread, fp64.  Mirrored by oracle/stain_oracle.py
+// (anderson_step): residual growth drops the history; the extrapolated point is projected back onto
+// {D >= 0, ||d_j|| <= 1}; a singular or non-finite solve falls back to the plain iterate.
+constexpr int AA_MAX = 4;
+struct AAState {
+    double x[AA_MAX + 1][6];
+    double r[AA_MAX + 1][6];
+    double last;
+    int n;
+};
+__device__ inline void aa_reset(AAState& s) { s.n = 0; s.last = -1.0; }
+// D: current iterate (in) / next iterate (out); FD = F(D).
+__device__ inline void aa_step(AAState& s, int m, double* D, const double* FD) {
+    double r[6], rn = 0.0;
+    for (int k = 0; k < 6; ++k) { r[k] = FD[k] - D[k]; rn += r[k] * r[k]; }
+    rn = sqrt(rn);
+    if (m <= 0) { for (int k = 0; k < 6; ++k) D[k] = FD[k]; return; }
+    if (s.last >= 0.0 && rn > s.last) s.n = 0;          // the last extrapolation made things worse: restart
+    s.last = rn;
+    if (s.n == m + 1) {
+        for (int i = 0; i < m; ++i)
+            for (int k = 0; k < 6; ++k) { s.x[i][k] = s.x[i + 1][k]; s.r[i][k] = s.r[i + 1][k]; }
+        s.n = m;
+    }
+    for (int k = 0; k < 6; ++k) { s.x[s.n][k] = D[k]; s.r[s.n][k] = r[k]; }
+    s.n += 1;
+    const int h = s.n - 1;
+    bool ok = h >= 1;
+    double xn[6];
+    if (ok) {
+        double G[AA_MAX][AA_MAX + 1];
+        double tr = 0.0;
+        for (int i = 0; i < h; ++i) {
+            for (int j = 0; j < h; ++j) {
+                double g = 0.0;
+                for (int k = 0; k < 6; ++k) g += (s.r[i + 1][k] - s.r[i][k]) * (s.r[j + 1][k] - s.r[j][k]);
+                G[i][j] = g;
+            }
+            double b = 0.0;
+            for (int k = 0; k < 6; ++k) b += (s.r[i + 1][k] - s.r[i][k]) * r[k];
+            G[i][h] = b;
+            tr += G[i][i];
+        }
+        ok = tr > 0.0 && isfinite(tr);
+        for (int i = 0; i < h; ++i) G[i][i] += 1e-10 * tr;
+        // Gaussian elimination with partial pivoting on the augmented h x (h+1) system
+        for (int c = 0; c < h && ok; ++c) {
+            int piv = c;
+            for (int i = c + 1; i < h; ++i) if (fabs(G[i][c]) > fabs(G[piv][c])) piv = i;
+            if (!(fabs(G[piv][c]) > 0.0)) { ok = false; break; }
+            if (piv != c) for (int j = c; j <= h; ++j) { const double t = G[c][j]; G[c][j] = G[piv][j]; G[piv][j] = t; }
+            for (int i = c + 1; i < h; ++i) {
+                const double f = G[i][c] / G[c][c];
+                for (int j = c; j <= h; ++j) G[i][j] -= f * G[c][j];
+            }
+        }
+        double gam[AA_MAX];
+        for (int i = h - 1; i >= 0 && ok; --i) {
+            double v = G[i][h];
+            for (int j = i + 1; j < h; ++j) v -= G[i][j] * gam[j];
+            gam[i] = v / G[i][i];
+        }
+        if (ok) {
+            for (int k = 0; k < 6; ++k) {
+                double v = D[k] + r[k];
+                for (int i = 0; i < h; ++i) v -= gam[i] * ((s.x[i + 1][k] - s.x[i][k]) + (s.r[i + 1][k] - s.r[i][k]));
+                xn[k] = v > 0.0 ? v : 0.0;
+                ok = ok && isfinite(v);
+            }
+            for (int j = 0; j < 2 && ok; ++j) {
+                const double nrm = sqrt(xn[3 * j] * xn[3 * j] + xn[3 * j + 1] * xn[3 * j + 1] + xn[3 * j + 2] * xn[3 * j + 2]);
+                const double sc = 1.0 / (nrm > 1.0 ? nrm : 1.0);
+                for (int k = 0; k < 3; ++k) xn[3 * j + k] *= sc;
+            }
+        }
+    }
+    for (int k = 0; k < 6; ++k) D[k] = ok ? xn[k] : FD[k];
+}
+
 // ------------------------------------------------------------------------------------------------ block reductions
 __device__ __forceinline__ double warp_sum(double x) {
 #pragma unroll

@@ -35,7 +35,7 @@ struct PipeArgs {
     int mode, method, cluster_size;
     float ybound;         // tissue <=> sum_c gy[c][v_c] < ybound
     double ang_pct, lasso_lambda, conc_pct, dl_lambda;
-    int dl_iters;
+    int dl_iters, dl_sample_iters, dl_anderson;
     const double* Mt;     // [2,3] device
     const double* maxCt;  // [2]   device
     double* M_out;        // [B,2,3] or null

@@ -52,6 +52,7 @@ struct __align__(16) PipeShared {
     LassoK lk;
     int flags;
     double D[6];                     // Vahadane dictionary, rows = atoms
+    AAState aa;                      // Anderson history of the dictionary iteration (thread 0)
     double Msrc[6];
     double maxC[2];
 };
@@ -355,13 +356,21 @@ __device__ __forceinline__ void for_each_group_uniform(const uint8_t* __restrict
 
 // Like for_each_group but visits ONE complete group out of every SAMPLE_STRIDE consecutive groups, at a hashed offset
 // inside the block (a fixed offset would alias with the row length and sample vertical stripes of the image).
+// The sample is defined on the TILE's group index, so it does not depend on how a cluster splits the tile.
+__device__ __forceinline__ int sample_group_of_block(int j) { return j * SAMPLE_STRIDE + (int)(((uint32_t)j * 2654435761u) >> 28); }
+__device__ __forceinline__ bool is_sample_group(int g, int nfull) {
+    const int j = g / SAMPLE_STRIDE;
+    return j < nfull / SAMPLE_STRIDE && g == sample_group_of_block(j);
+}
 template <class F>
 __device__ __forceinline__ void for_each_sample_group(const uint8_t* __restrict__ tile, int npx, int gb, int ge, bool aligned, F&& f) {
     const int nfull = npx / GROUP_PX;
-    const int fe = ge < nfull ? ge : nfull;
-    const int nblk = (fe - gb) / SAMPLE_STRIDE;
-    for (int j = threadIdx.x; j < nblk; j += NT) {
-        const int g = gb + j * SAMPLE_STRIDE + (int)(((uint32_t)j * 2654435761u) >> 28);
+    const int jb = gb / SAMPLE_STRIDE;
+    int je = (ge + SAMPLE_STRIDE - 1) / SAMPLE_STRIDE;
+    if (je > nfull / SAMPLE_STRIDE) je = nfull / SAMPLE_STRIDE;
+    for (int j = jb + (int)threadIdx.x; j < je; j += NT) {
+        const int g = sample_group_of_block(j);
+        if (g < gb || g >= ge) continue;
         uint32_t w[12];
         int nvalid;
         load_group<true>(tile, npx, g, aligned, w, nvalid);
@@ -665,64 +674,87 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                 make_lasso_consts(sh->D, a.dl_lambda, sh->lk);
             }
             __syncthreads();
-            // V0: tissue mask -> one bit per pixel (reused by every iteration)
-            unsigned cnt_tissue = 0;
-            for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                const uint32_t mbits = mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
-                cnt_tissue += __popc(mbits);
-                if (cache_mask) *mask_slot(od_rep, g - gb) = (unsigned short)mbits;
-            });
-            for (int it = 0; it < a.dl_iters; ++it) {
-                const LassoK lk = sh->lk;
+            // V0: tissue mask -> one bit per pixel (reused by every iteration); tissue counts of the tile and of its sample
+            {
+                unsigned cnt_tissue = 0, cnt_sample = 0;
+                const int nfull = npx / GROUP_PX;
+                for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                    const uint32_t mbits = mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                    cnt_tissue += __popc(mbits);
+                    if (is_sample_group(g, nfull)) cnt_sample += __popc(mbits);
+                    if (cache_mask) *mask_slot(od_rep, g - gb) = (unsigned short)mbits;
+                });
                 double acc[9];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) acc[i] = 0.0;
-                const unsigned cnt = cnt_tissue;
-                for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                    const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
-                    float f[9];
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) f[i] = 0.f;
-                    for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
-                        float c0, c1;
-                        lasso2(lk, o0, o1, o2, c0, c1);
-                        const bool m = (mbits & (1u << i)) != 0;
-                        c0 = m ? c0 : 0.f; c1 = m ? c1 : 0.f;
-                        f[0] = fmaf(c0, c0, f[0]); f[1] = fmaf(c0, c1, f[1]); f[2] = fmaf(c1, c1, f[2]);
-                        f[3] = fmaf(o0, c0, f[3]); f[4] = fmaf(o1, c0, f[4]); f[5] = fmaf(o2, c0, f[5]);
-                        f[6] = fmaf(o0, c1, f[6]); f[7] = fmaf(o1, c1, f[7]); f[8] = fmaf(o2, c1, f[8]);
-                    });
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
-                });
-                block_reduce10(sh, pbuf, acc, cnt);
+                acc[0] = (double)cnt_sample;
+                block_reduce10(sh, pbuf, acc, cnt_tissue);
                 tile_sync(S);
                 cluster_total10(sh, pbuf, S);
                 pbuf ^= 1;
-                n_tissue = (unsigned)sh->tot[9];
-                if (threadIdx.x == 0) {
-                    const double* t = sh->tot;
-                    if (t[9] < 1.0) sh->flags |= SB_STATUS_EMPTY_MASK;
-                    // Mairal et al. 2010 Alg. 2, one block-coordinate sweep; D rows = atoms.
-                    const double Aj[2][2] = {{t[0], t[1]}, {t[1], t[2]}};
-                    for (int j = 0; j < 2; ++j) {
-                        if (Aj[j][j] > 1e-12) {
-                            double u[3], nrm = 0.0;
-                            for (int k = 0; k < 3; ++k) {
-                                const double Da = sh->D[k] * Aj[0][j] + sh->D[3 + k] * Aj[1][j];
-                                u[k] = (t[3 + 3 * j + k] - Da) / Aj[j][j] + sh->D[3 * j + k];
-                                u[k] = u[k] > 0.0 ? u[k] : 0.0;
-                                nrm += u[k] * u[k];
+            }
+            n_tissue = (unsigned)sh->tot[9];
+            const bool use_sample = a.dl_sample_iters > 0 && sh->tot[0] >= 1024.0;
+            __syncthreads();
+            if (threadIdx.x == 0 && n_tissue < 1u) sh->flags |= SB_STATUS_EMPTY_MASK;
+            __syncthreads();
+            // phase 0: warm start on the 1-in-16 sample; phase 1: full passes.  Without a usable sample: 4 more full passes.
+            for (int phase = use_sample ? 0 : 1; phase < 2 && sh->flags == 0; ++phase) {
+                const int n_it = phase == 0 ? a.dl_sample_iters : a.dl_iters + ((a.dl_sample_iters > 0 && !use_sample) ? 4 : 0);
+                if (threadIdx.x == 0) aa_reset(sh->aa);
+                for (int it = 0; it < n_it; ++it) {
+                    const LassoK lk = sh->lk;
+                    double acc[9];
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+                    auto accumulate = [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                        const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                        float f[9];
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) f[i] = 0.f;
+                        for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
+                            float c0, c1;
+                            lasso2(lk, o0, o1, o2, c0, c1);
+                            const bool m = (mbits & (1u << i)) != 0;
+                            c0 = m ? c0 : 0.f; c1 = m ? c1 : 0.f;
+                            f[0] = fmaf(c0, c0, f[0]); f[1] = fmaf(c0, c1, f[1]); f[2] = fmaf(c1, c1, f[2]);
+                            f[3] = fmaf(o0, c0, f[3]); f[4] = fmaf(o1, c0, f[4]); f[5] = fmaf(o2, c0, f[5]);
+                            f[6] = fmaf(o0, c1, f[6]); f[7] = fmaf(o1, c1, f[7]); f[8] = fmaf(o2, c1, f[8]);
+                        });
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
+                    };
+                    if (phase == 0) for_each_sample_group(tin, npx, gb, ge, aligned, accumulate);
+                    else for_each_group<true>(tin, npx, gb, ge, aligned, accumulate);
+                    block_reduce10(sh, pbuf, acc, 0u);
+                    tile_sync(S);
+                    cluster_total10(sh, pbuf, S);
+                    pbuf ^= 1;
+                    if (threadIdx.x == 0) {
+                        const double* t = sh->tot;
+                        // Mairal et al. 2010 Alg. 2, one block-coordinate sweep; D rows = atoms.
+                        double FD[6];
+                        for (int k = 0; k < 6; ++k) FD[k] = sh->D[k];
+                        const double Aj[2][2] = {{t[0], t[1]}, {t[1], t[2]}};
+                        for (int j = 0; j < 2; ++j) {
+                            if (Aj[j][j] > 1e-12) {
+                                double u[3], nrm = 0.0;
+                                for (int k = 0; k < 3; ++k) {
+                                    const double Da = FD[k] * Aj[0][j] + FD[3 + k] * Aj[1][j];
+                                    u[k] = (t[3 + 3 * j + k] - Da) / Aj[j][j] + FD[3 * j + k];
+                                    u[k] = u[k] > 0.0 ? u[k] : 0.0;
+                                    nrm += u[k] * u[k];
+                                }
+                                nrm = sqrt(nrm);
+                                const double sc = 1.0 / (nrm > 1.0 ? nrm : 1.0);
+                                for (int k = 0; k < 3; ++k) FD[3 * j + k] = u[k] * sc;
                             }
-                            nrm = sqrt(nrm);
-                            const double sc = 1.0 / (nrm > 1.0 ? nrm : 1.0);
-                            for (int k = 0; k < 3; ++k) sh->D[3 * j + k] = u[k] * sc;
                         }
+                        aa_step(sh->aa, a.dl_anderson, sh->D, FD);
+                        make_lasso_consts(sh->D, a.dl_lambda, sh->lk);
                     }
-                    make_lasso_consts(sh->D, a.dl_lambda, sh->lk);
+                    __syncthreads();
                 }
-                __syncthreads();
-                if (sh->flags) break;
             }
             if (threadIdx.x == 0 && sh->flags == 0) {
                 // vahadane_stain_extractor.py:38-43: H first, rows normalised

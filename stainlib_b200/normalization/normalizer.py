@@ -40,8 +40,10 @@ class ExtractiveStainNormalizer(object):
 
     def _params(self):
         kw = dict(self._kw)
-        if self._method == nv.SB_METHOD_VAHADANE and "dl_iters" not in kw:
-            kw["dl_iters"] = VahadaneStainExtractor.n_iter
+        if self._method == nv.SB_METHOD_VAHADANE:
+            kw.setdefault("dl_iters", VahadaneStainExtractor.n_iter)
+            kw.setdefault("dl_sample_iters", VahadaneStainExtractor.n_sample_iter)
+            kw.setdefault("dl_anderson", VahadaneStainExtractor.anderson)
         return nv.default_params(self._method, **kw)
 
     def _fit_local(self, target):
@@ -91,9 +93,10 @@ class ExtractiveStainNormalizer(object):
             return None
         return get_concentrations(self._target, self.stain_matrix_target)
 
-    def transform(self, I, chunk_tiles=0):
+    def transform(self, I, chunk_tiles=0, out=None):
         """Transform an image (normalizer.py:39-50).  Output is not clipped: like the reference's astype(np.uint8) it
-        wraps modulo 256."""
+        wraps modulo 256.  ``out`` (host batches only): a preallocated, ideally pinned, uint8 tensor of I's shape to
+        receive the result, so that a streaming caller does not allocate pinned memory per call."""
         assert is_uint8_image(I), "Image should be RGB uint8."
         lib = nv.load_library()
         p = self._params()
@@ -101,7 +104,9 @@ class ExtractiveStainNormalizer(object):
             # host batch: chunked, overlapped H2D / kernel / D2H inside the C library
             h, idx = nv.get_handle()
             src = I.contiguous()
-            out = torch.empty_like(src, pin_memory=src.is_pinned())
+            if out is None:
+                out = torch.empty_like(src, pin_memory=src.is_pinned())
+            assert out.shape == src.shape and out.dtype == torch.uint8 and not out.is_cuda and out.is_contiguous()
             status = torch.empty(src.shape[0], dtype=torch.int32)
             Mt = np.ascontiguousarray(self.stain_matrix_target, dtype=np.float64)
             Ct = np.ascontiguousarray(self.maxC_target, dtype=np.float64)
