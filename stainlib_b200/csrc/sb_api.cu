@@ -74,6 +74,7 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
     a.method = p->method;
     a.cluster_size = pick_cluster(h, B, a.npx, p->cluster_size);
     a.ybound = mask_ybound_f(p->luminosity_threshold);
+    for (int c = 0; c < 3; ++c) a.ycoef[c] = (float)SB_RGB2LAB_COEFFS[3 + c];
     a.ang_pct = p->angular_percentile; a.lasso_lambda = p->lasso_lambda; a.conc_pct = p->conc_percentile;
     a.dl_lambda = p->dl_lambda; a.dl_iters = p->dl_iters;
     a.dl_sample_iters = p->dl_sample_iters < 0 ? 0 : p->dl_sample_iters;
@@ -149,6 +150,16 @@ int sb_create(int device, sb_handle** out) {
     cudaDeviceProp prop;
     SB_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return SB_ERR_NO_DEVICE;   // kernels are built for sm_100a only
+    // Per-call scratch (per-tile constants, statistics) comes from the device's stream-ordered pool.  By default the pool
+    // hands its memory back to the driver at every synchronisation, which makes the first launch after each sync pay a
+    // fresh allocation (measured 1-60 ms); keep the memory cached instead.
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     sb_handle* h = new sb_handle();
     h->device = device;
     h->num_sms = prop.multiProcessorCount;

@@ -228,6 +228,17 @@ __device__ __forceinline__ float od_lookup(const OdAbs* t, uint32_t w, uint32_t 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
 
+// Two pixels at a time on the packed f32x2 pipe (each half is bitwise the scalar lasso2_unit of that pixel).
+template <int LM>
+__device__ __forceinline__ void lasso2_unit_pair(const LassoK& k, const float2 o0, const float2 o1, const float2 o2, float2& c0, float2& c1) {
+    const float2 u0 = __ffma2_rn(dup(k.m02), o2, __ffma2_rn(dup(k.m01), o1, __ffma2_rn(dup(k.m00), o0, dup(-k.lam))));
+    const float2 u1 = __ffma2_rn(dup(k.m12), o2, __ffma2_rn(dup(k.m11), o1, __ffma2_rn(dup(k.m10), o0, dup(-k.lam))));
+    const float2 a0 = __ffma2_rn(dup(k.i01), u1, __fmul2_rn(dup(k.i00), u0));
+    const float2 a1 = __ffma2_rn(dup(k.i11), u1, __fmul2_rn(dup(k.i01), u0));
+    lasso2_select<LM>(a0.x, a1.x, u0.x, u1.x, c0.x, c1.x);
+    lasso2_select<LM>(a0.y, a1.y, u0.y, u1.y, c0.y, c1.y);
+}
+
 template <bool CHECK, int LM>
 __device__ __forceinline__ void recombine_pair(const K4Consts& k, const float2 o0, const float2 o1, const float2 o2, uint32_t (&bits)[6]) {
     const float2 u0 = __ffma2_rn(dup(k.m[2]), o2, __ffma2_rn(dup(k.m[1]), o1, __ffma2_rn(dup(k.m[0]), o0, dup(k.nlam))));

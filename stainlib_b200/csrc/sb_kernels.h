@@ -33,7 +33,8 @@ struct PipeArgs {
     int aligned;          // tile base addresses and tile size are multiples of 16 bytes
     Tables tab;
     int mode, method, cluster_size;
-    float ybound;         // tissue <=> sum_c gy[c][v_c] < ybound
+    float ybound;         // tissue <=> sum_c ycoef[c] * gamma[v_c] < ybound
+    float ycoef[3];       // the Y row of cv2's fixed-point RGB->XYZ matrix (871, 2929, 296)
     double ang_pct, lasso_lambda, conc_pct, dl_lambda;
     int dl_iters, dl_sample_iters, dl_anderson;
     const double* Mt;     // [2,3] device

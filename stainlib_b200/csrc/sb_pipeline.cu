@@ -31,7 +31,6 @@ constexpr unsigned WQ_CAP = 160;   // entries per warp queue: drained to < 32 on
 
 struct __align__(16) PipeShared {
     unsigned hist[2 * L1_BINS];      // 32 KB: 2 x 4096 (level 1) or 4 x 2048 (level 2)
-    float gy[3 * 256];
     double red[NWARP][10];
     double part[2][12];              // this CTA's partial sums (double-buffered; read by cluster peers)
     double tot[12];
@@ -182,23 +181,56 @@ __device__ __forceinline__ void for_each_group(const uint8_t* __restrict__ tile,
     }
 }
 
-// One bit per pixel of the tissue mask, 16 bits per group, stored in bytes 128..255 of the OD-table rows.
-__device__ __forceinline__ unsigned short* mask_slot(unsigned char* od_rep, int gl) {
-    return reinterpret_cast<unsigned short*>(od_rep + ((gl >> 6) << 8) + 128 + ((gl & 63) << 1));
+// The lookup table of this kernel holds one {od[v], gamma[v]} PAIR per lane in each 256-byte row: one PRMT builds the
+// offset (value << 8 | lane << 3) and ONE conflict-free LDS.64 returns the optical density and the linearised sRGB
+// value the tissue test needs (LDS.32 at the same address returns the density alone).
+__device__ __forceinline__ void fill_odg_rep(unsigned char* rep, const float* od, const unsigned short* gamma, int nthreads) {
+    for (int i = threadIdx.x; i < 256 * 32; i += nthreads)
+        *reinterpret_cast<float2*>(rep + (i >> 5) * OD_ROW_BYTES + (i & 31) * 8) = make_float2(od[i >> 5], (float)gamma[i >> 5]);
 }
+__device__ __forceinline__ float2 odg_lookup(const unsigned char* tab, uint32_t w, uint32_t lane_off, int k) {
+    const uint32_t off = __byte_perm(w, lane_off, 0x6504u | (k << 4));
+    return *reinterpret_cast<const float2*>(tab + off);
+}
+// Tissue <=> cv2's L channel below the threshold <=> 871 g[R] + 2929 g[G] + 296 g[B] < ybound (integers < 2^24: the
+// fp32 FMAs are exact, so this is the bit-exact mask of stain_utils.py:32-48).
+struct YCoef { float r, g, b, bound; };
+__device__ __forceinline__ float tissue_y(const YCoef& c, float gr, float gg, float gb) { return fmaf(c.b, gb, fmaf(c.g, gg, c.r * gr)); }
 
-// 16-bit tissue mask of a group from the pre-weighted luminance tables (integer-exact collapse of cv2's L channel).
+__device__ __forceinline__ uint32_t set_lt(float a, float b) { uint32_t d; asm("set.lt.u32.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ uint32_t set_gt(float a, float b) { uint32_t d; asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ uint32_t set_le(float a, float b) { uint32_t d; asm("set.le.u32.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ float min3f(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+
+// One bit per pixel of the tissue mask, 16 bits per group, for the Vahadane iterations (the 32 KB histogram buffer is
+// idle until the concentration passes).  Macenko needs the mask in two passes only and recomputes it: gamma arrives
+// with the density in the same LDS.64.
+__device__ __forceinline__ unsigned short* mask_slot(unsigned* hist, int gl) { return reinterpret_cast<unsigned short*>(hist) + gl; }
+constexpr int MASK_CAP_GROUPS = 2 * L1_BINS * 2;   // 16-bit slots in the histogram buffer = 262,144 pixels per CTA
+
+// Densities AND gammas of the 16 pixels of a group: f(i, {od_r, g_r}, {od_g, g_g}, {od_b, g_b}).
+template <class F>
+__device__ __forceinline__ void for_each_px_odg(const unsigned char* tab, uint32_t lane_off, const uint32_t (&w)[12], F&& f) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        f(4 * q + 0, odg_lookup(tab, a, lane_off, 0), odg_lookup(tab, a, lane_off, 1), odg_lookup(tab, a, lane_off, 2));
+        f(4 * q + 1, odg_lookup(tab, a, lane_off, 3), odg_lookup(tab, b, lane_off, 0), odg_lookup(tab, b, lane_off, 1));
+        f(4 * q + 2, odg_lookup(tab, b, lane_off, 2), odg_lookup(tab, b, lane_off, 3), odg_lookup(tab, c, lane_off, 0));
+        f(4 * q + 3, odg_lookup(tab, c, lane_off, 1), odg_lookup(tab, c, lane_off, 2), odg_lookup(tab, c, lane_off, 3));
+    }
+}
+// 16-bit tissue mask of a group.
 template <bool TAIL>
-__device__ __forceinline__ uint32_t mask16(const uint32_t (&w)[12], const float* gyR, const float* gyG, const float* gyB, float ybound, int nvalid) {
+__device__ __forceinline__ uint32_t mask16(const unsigned char* tab, uint32_t lane_off, const uint32_t (&w)[12], const YCoef& yc, int nvalid) {
     uint32_t mbits = 0;
-    for_each_px(w, [&](int i, uint32_t r, uint32_t g, uint32_t b) {
-        const float y = gyR[r] + gyG[g] + gyB[b];
-        const bool m = TAIL ? ((y < ybound) & (i < nvalid)) : (y < ybound);
-        mbits |= m ? (1u << i) : 0u;
+    for_each_px_odg(tab, lane_off, w, [&](int i, float2 r, float2 g, float2 b) {
+        uint32_t m = set_lt(tissue_y(yc, r.y, g.y, b.y), yc.bound);
+        if (TAIL && i >= nvalid) m = 0u;
+        mbits |= m & (1u << i);
     });
     return mbits;
 }
-constexpr int MASK_CAP_GROUPS = 256 * 64;   // 16-bit slots available in the table rows = 262,144 pixels per CTA
 
 // OD of the three channels of the 16 pixels of a group through the replicated table: calls f(i, od_r, od_g, od_b).
 template <class F>
@@ -211,6 +243,36 @@ __device__ __forceinline__ void for_each_px_od(const unsigned char* tab, uint32_
         f(4 * q + 2, od_lookup(tab, b, lane_off, 2), od_lookup(tab, b, lane_off, 3), od_lookup(tab, c, lane_off, 0));
         f(4 * q + 3, od_lookup(tab, c, lane_off, 1), od_lookup(tab, c, lane_off, 2), od_lookup(tab, c, lane_off, 3));
     }
+}
+// Same, two pixels at a time for the packed f32x2 pipe: f(i0, {od_r(i0), od_r(i0+1)}, {od_g ..}, {od_b ..}).
+template <class F>
+__device__ __forceinline__ void for_each_pair_od(const unsigned char* tab, uint32_t lane_off, const uint32_t (&w)[12], F&& f) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        f(4 * q + 0, f2(od_lookup(tab, a, lane_off, 0), od_lookup(tab, a, lane_off, 3)), f2(od_lookup(tab, a, lane_off, 1), od_lookup(tab, b, lane_off, 0)),
+          f2(od_lookup(tab, a, lane_off, 2), od_lookup(tab, b, lane_off, 1)));
+        f(4 * q + 2, f2(od_lookup(tab, b, lane_off, 2), od_lookup(tab, c, lane_off, 1)), f2(od_lookup(tab, b, lane_off, 3), od_lookup(tab, c, lane_off, 2)),
+          f2(od_lookup(tab, c, lane_off, 0), od_lookup(tab, c, lane_off, 3)));
+    }
+}
+
+// Pass A inner step: if (y < bound) { n += 1; s += od; S += od x od }  -- ten predicated instructions, no selects.
+__device__ __forceinline__ void accum_if_tissue(float y, float bound, float o0, float o1, float o2, float (&f)[9], unsigned& cnt) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.lt.f32 p, %10, %11;\n\t"
+        "@p add.f32 %0, %0, %12;\n\t"
+        "@p add.f32 %1, %1, %13;\n\t"
+        "@p add.f32 %2, %2, %14;\n\t"
+        "@p fma.rn.f32 %3, %12, %12, %3;\n\t"
+        "@p fma.rn.f32 %4, %12, %13, %4;\n\t"
+        "@p fma.rn.f32 %5, %12, %14, %5;\n\t"
+        "@p fma.rn.f32 %6, %13, %13, %6;\n\t"
+        "@p fma.rn.f32 %7, %13, %14, %7;\n\t"
+        "@p fma.rn.f32 %8, %14, %14, %8;\n\t"
+        "@p add.u32 %9, %9, 1;\n\t}"
+        : "+f"(f[0]), "+f"(f[1]), "+f"(f[2]), "+f"(f[3]), "+f"(f[4]), "+f"(f[5]), "+f"(f[6]), "+f"(f[7]), "+f"(f[8]), "+r"(cnt)
+        : "f"(y), "f"(bound), "f"(o0), "f"(o1), "f"(o2));
 }
 
 // ------------------------------------------------------------------------------------------ sampled-bracket selection
@@ -297,28 +359,26 @@ __device__ __forceinline__ void wq_drain(WarpQueue& wq, bool final, P&& proc) {
         const unsigned start = wq.len - n;
         __syncwarp();
         const bool has = (threadIdx.x & 31u) < n;
-        const unsigned val = has ? wq.q[start + (threadIdx.x & 31u)] : 0x00FFFFFFu;
+        const unsigned val = has ? wq.q[start + (threadIdx.x & 31u)] : 0u;
         wq.len = start;
         proc(has, val);
         __syncwarp();
     }
 }
-// Group epilogue of the bracket passes: every lane pushes the pixels flagged in `bits` (16-bit mask over its group)
-// into the warp queue, one per round, re-reading the three bytes of each flagged pixel (they are in L1: the group was
-// just loaded).  flag_of(i) supplies bits 24.. of the queue entry.  Warp-uniform: all lanes call it every group.
-template <class FL>
-__device__ __forceinline__ void wq_push_flagged(WarpQueue& wq, unsigned bits, const uint8_t* __restrict__ group_ptr, int* overflow, FL&& flag_of) {
+// Group epilogue of the bracket passes: every lane pushes the POSITIONS (pixel index in the tile) of the pixels flagged
+// in `bits` (16-bit mask over its group) into the warp queue, one per round; the drain loads the three bytes of each
+// queued pixel with all 32 lanes busy (they are in L1/L2: the group was just read).  Warp-uniform: all lanes call it.
+__device__ __forceinline__ void wq_push_flagged(WarpQueue& wq, unsigned bits, unsigned first_px, int* overflow) {
     while (__ballot_sync(0xffffffffu, bits != 0u)) {
         const bool has = bits != 0u;
-        const int i = has ? (__ffs(bits) - 1) : 0;
+        const unsigned val = first_px + (unsigned)(__ffs(bits) - 1);
         bits &= bits - 1u;
-        unsigned val = 0x00FFFFFFu;
-        if (has) {
-            const uint8_t* p = group_ptr + 3 * i;
-            val = (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16) | flag_of(i);
-        }
         wq_push(wq, has, val, overflow);
     }
+}
+__device__ __forceinline__ uint32_t load_px(const uint8_t* __restrict__ tile, unsigned px) {
+    const uint8_t* p = tile + (size_t)px * 3;
+    return (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16);
 }
 
 // The RGB bytes of pixel i (0..15) of a group as one word (R in byte 0), i a compile-time constant after unrolling.
@@ -378,6 +438,7 @@ __device__ __forceinline__ void for_each_sample_group(const uint8_t* __restrict_
     }
 }
 
+template <int METHOD>
 __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* od_rep = smem_raw;                                        // 64 KB: OD table + mask bits
@@ -390,14 +451,12 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
     const int gb = (int)(((long long)G * crank) / S), ge = (int)(((long long)G * (crank + 1)) / S);
     const size_t tile_bytes = (size_t)npx * 3;
     const bool aligned = a.aligned != 0;
-    const float ybound = a.ybound;
-    const uint32_t lane_off = (threadIdx.x & 31) << 2;
-    const bool cache_mask = (ge - gb) <= MASK_CAP_GROUPS;   // else the mask is recomputed in every pass that needs it
+    const uint32_t lane_off = (threadIdx.x & 31) << 3;      // {od, gamma} pairs: 8 bytes per lane
+    const YCoef yc{a.ycoef[0], a.ycoef[1], a.ycoef[2], a.ybound};
+    const bool cache_mask = (ge - gb) <= MASK_CAP_GROUPS;   // Vahadane only; else the mask is recomputed in every iteration
 
-    fill_od_rep(od_rep, a.tab.od, NT);
-    for (int i = threadIdx.x; i < 768; i += NT) sh->gy[i] = a.tab.gy[i];
+    fill_odg_rep(od_rep, a.tab.od, a.tab.gamma, NT);
     __syncthreads();
-    const float* gyR = sh->gy, *gyG = sh->gy + 256, *gyB = sh->gy + 512;
     int pbuf = 0;   // parity of sh->part
 
     for (int tile = cluster_id; tile < a.B; tile += n_clusters) {
@@ -405,31 +464,22 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
         unsigned n_tissue = 0;
         if (threadIdx.x == 0) { sh->flags = 0; }
 
-        if (a.method == SB_METHOD_MACENKO) {
+        if (METHOD == SB_METHOD_MACENKO) {
             // ------------------------------------------------------------------ A: mask + moments
             double acc[9];
 #pragma unroll
             for (int i = 0; i < 9; ++i) acc[i] = 0.0;
             unsigned cnt = 0;
-            for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+            for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int) {
                 constexpr bool TAIL = decltype(tail)::value;
                 float f[9];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) f[i] = 0.f;
-                uint32_t mbits = 0;
-                for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
-                    const float y = gyR[r] + gyG[gg] + gyB[b];
-                    const bool m = TAIL ? ((y < ybound) & (i < nvalid)) : (y < ybound);
-                    const float* row = reinterpret_cast<const float*>(od_rep + lane_off);
-                    const float t0 = row[r * 64], t1 = row[gg * 64], t2 = row[b * 64];
-                    const float o0 = m ? t0 : 0.f, o1 = m ? t1 : 0.f, o2 = m ? t2 : 0.f;
-                    mbits |= m ? (1u << i) : 0u;
-                    f[0] += o0; f[1] += o1; f[2] += o2;
-                    f[3] = fmaf(o0, o0, f[3]); f[4] = fmaf(o0, o1, f[4]); f[5] = fmaf(o0, o2, f[5]);
-                    f[6] = fmaf(o1, o1, f[6]); f[7] = fmaf(o1, o2, f[7]); f[8] = fmaf(o2, o2, f[8]);
+                for_each_px_odg(od_rep, lane_off, w, [&](int i, float2 r, float2 g, float2 b) {
+                    float y = tissue_y(yc, r.y, g.y, b.y);
+                    if (TAIL && i >= nvalid) y = yc.bound;
+                    accum_if_tissue(y, yc.bound, r.x, g.x, b.x, f, cnt);
                 });
-                cnt += __popc(mbits);
-                if (cache_mask) *mask_slot(od_rep, g - gb) = (unsigned short)mbits;
 #pragma unroll
                 for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
             });
@@ -479,13 +529,11 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     if (threadIdx.x == 0) { sh->s_cnt = 0; sh->l_len[0] = sh->l_len[1] = 0; sh->l_below[0] = sh->l_below[1] = 0; sh->s_ok = 0; sh->wq_overflow = 0; }
                     zero_hist(sh);
                     unsigned scnt = 0;
-                    for_each_sample_group(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                        const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
-                        scnt += __popc(mbits);
-                        for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
-                            const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
-                            const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
-                            if (mbits & (1u << i)) atomicAdd(&sh->hist[angle_key(px, py) >> L2_BITS], 1u);
+                    for_each_sample_group(tin, npx, gb, ge, aligned, [&](auto, const uint32_t (&w)[12], int, int) {
+                        for_each_px_odg(od_rep, lane_off, w, [&](int, float2 r, float2 g, float2 b) {
+                            const float px = fmaf(b.x, v02, fmaf(g.x, v01, r.x * v00));
+                            const float py = fmaf(b.x, v12, fmaf(g.x, v11, r.x * v10));
+                            if (tissue_y(yc, r.y, g.y, b.y) < yc.bound) { ++scnt; atomicAdd(&sh->hist[angle_key(px, py) >> L2_BITS], 1u); }
                         });
                     });
                     scnt = warp_sum_u(scnt);
@@ -538,28 +586,32 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                             }
                         };
                         WarpQueue wq{sh->wq[threadIdx.x >> 5], 0u};
+                        auto drain_px = [&](bool has, uint32_t pos) { exact_px(has, load_px(tin, pos)); };
+                        const float nf_lo = -f_lo;
                         for_each_group_uniform(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], bool active, int g) {
-                            uint32_t mbits = 0;
-                            if (active) mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<false>(w, gyR, gyG, gyB, ybound, GROUP_PX);
-                            unsigned fastbits = 0;
-                            for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
-                                const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
-                                const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
+                            // inactive lanes hold an all-white group: no tissue bit is set for it
+                            uint32_t mbits = 0, fastbits = 0;
+                            for_each_px_odg(od_rep, lane_off, w, [&](int i, float2 r, float2 gg, float2 b) {
+                                const float px = fmaf(b.x, v02, fmaf(gg.x, v01, r.x * v00));
+                                const float py = fmaf(b.x, v12, fmaf(gg.x, v11, r.x * v10));
                                 const float sd = px + fabsf(py);
-                                const bool fast = (px > 0.f) & (py > f_lo * sd) & (py < f_hi * sd);
-                                fastbits |= fast ? (1u << i) : 0u;
+                                // inside (f_lo, f_hi) in the half-plane x > 0  <=>  min(py - f_lo sd, f_hi sd - py, px) > 0
+                                const float mn = min3f(fmaf(nf_lo, sd, py), fmaf(f_hi, sd, -py), px);
+                                mbits |= set_lt(tissue_y(yc, r.y, gg.y, b.y), yc.bound) & (1u << i);
+                                fastbits |= set_gt(mn, 0.f) & (1u << i);
                             });
+                            if (!active) mbits = 0;
                             below1 += __popc(mbits & fastbits);
-                            wq_push_flagged(wq, mbits & ~fastbits, tin + (size_t)g * (GROUP_PX * 3), &sh->wq_overflow, [](int) { return 0u; });
-                            wq_drain(wq, false, exact_px);
+                            wq_push_flagged(wq, mbits & ~fastbits, (unsigned)g * GROUP_PX, &sh->wq_overflow);
+                            wq_drain(wq, false, drain_px);
                         });
-                        wq_drain(wq, true, exact_px);
+                        wq_drain(wq, true, drain_px);
                         if ((npx % GROUP_PX) != 0 && ge == G && threadIdx.x == 0) {
                             // ragged last group: plain exact path
                             uint32_t w[12];
                             int nvalid;
                             load_group<true>(tin, npx, G - 1, false, w, nvalid);
-                            const uint32_t mbits = cache_mask ? *mask_slot(od_rep, G - 1 - gb) : mask16<true>(w, gyR, gyG, gyB, ybound, nvalid);
+                            const uint32_t mbits = mask16<true>(od_rep, lane_off, w, yc, nvalid);
 #pragma unroll
                             for (int i = 0; i < GROUP_PX; ++i)
                                 if (mbits & (1u << i)) exact_px(true, pixel_word(w, i));
@@ -590,7 +642,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     // ---------------------------------------------------------- B1: angle histogram (tissue pixels)
                     zero_hist(sh);
                     for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                        const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                        const uint32_t mbits = mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
                         for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                             const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
                             const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
@@ -617,7 +669,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                         const int nd = sh->n_distinct;
                         const unsigned b0 = sh->d_bin[0], b1 = sh->d_bin[1], b2 = sh->d_bin[2], b3 = sh->d_bin[3];
                         for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                            const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                            const uint32_t mbits = mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
                             for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                                 const float px = fmaf(o2, v02, fmaf(o1, v01, o0 * v00));
                                 const float py = fmaf(o2, v12, fmaf(o1, v11, o0 * v10));
@@ -679,10 +731,10 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                 unsigned cnt_tissue = 0, cnt_sample = 0;
                 const int nfull = npx / GROUP_PX;
                 for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                    const uint32_t mbits = mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                    const uint32_t mbits = mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
                     cnt_tissue += __popc(mbits);
                     if (is_sample_group(g, nfull)) cnt_sample += __popc(mbits);
-                    if (cache_mask) *mask_slot(od_rep, g - gb) = (unsigned short)mbits;
+                    if (cache_mask) *mask_slot(sh->hist, g - gb) = (unsigned short)mbits;
                 });
                 double acc[9];
 #pragma unroll
@@ -708,7 +760,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
 #pragma unroll
                     for (int i = 0; i < 9; ++i) acc[i] = 0.0;
                     auto accumulate = [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                        const uint32_t mbits = cache_mask ? *mask_slot(od_rep, g - gb) : mask16<decltype(tail)::value>(w, gyR, gyG, gyB, ybound, nvalid);
+                        const uint32_t mbits = cache_mask ? *mask_slot(sh->hist, g - gb) : mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
                         float f[9];
 #pragma unroll
                         for (int i = 0; i < 9; ++i) f[i] = 0.f;
@@ -830,12 +882,15 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     unsigned* list1 = sh->hist + LIST_CAP;
                     unsigned below0 = 0, below1 = 0;
                     auto bracket_pass = [&](auto unit) {
+                        constexpr int LM = decltype(unit)::value;
                         // exact treatment of one pixel (packed RGB): a stain whose concentration the float test could not
-                        // classify gets its exact key; the arithmetic repeats the main loop's, so the same test decides.
+                        // classify gets its exact key.  The concentrations come from the SAME packed arithmetic as in the
+                        // main loop (the pixel is duplicated into both halves), so the same float test decides in both places.
                         auto exact_px = [&](bool has, uint32_t v, bool recount) {
                             const float o0 = od_lookup(od_rep, v, lane_off, 0), o1 = od_lookup(od_rep, v, lane_off, 1), o2 = od_lookup(od_rep, v, lane_off, 2);
-                            float c0, c1;
-                            lasso2_unit<decltype(unit)::value>(lk, o0, o1, o2, c0, c1);
+                            float2 cc0, cc1;
+                            lasso2_unit_pair<LM>(lk, dup(o0), dup(o1), dup(o2), cc0, cc1);
+                            const float c0 = cc0.x, c1 = cc1.x;
                             const uint32_t k0 = conc_key(c0), k1 = conc_key(c1);
                             if (has && (recount || (!(c0 < lo0) && !(c0 > hi0)))) {
                                 if (k0 < ka0) ++below0;
@@ -846,21 +901,22 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                                 else if (k1 < kb1) { const unsigned idx = atomicAdd(&sh->l_len[1], 1u); if (idx < LIST_CAP) list1[idx] = k1; }
                             }
                         };
-                        auto drain_px = [&](bool has, uint32_t v) { exact_px(has, v, false); };
+                        auto drain_px = [&](bool has, uint32_t pos) { exact_px(has, load_px(tin, pos), false); };
                         WarpQueue wq{sh->wq[threadIdx.x >> 5], 0u};
                         for_each_group_uniform(tin, npx, gb, ge, aligned, [&](const uint32_t (&w)[12], bool active, int g) {
                             unsigned cb0 = 0, cb1 = 0, slow = 0;
-                            for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
-                                float c0, c1;
-                                lasso2_unit<decltype(unit)::value>(lk, o0, o1, o2, c0, c1);
-                                const bool b0 = c0 < lo0, b1 = c1 < lo1;
-                                cb0 += b0 ? 1u : 0u;
-                                cb1 += b1 ? 1u : 0u;
-                                const bool s01 = (!b0 & !(c0 > hi0)) | (!b1 & !(c1 > hi1));
-                                slow |= s01 ? (1u << i) : 0u;
+                            for_each_pair_od(od_rep, lane_off, w, [&](int i, float2 o0, float2 o1, float2 o2) {
+                                float2 c0, c1;
+                                lasso2_unit_pair<LM>(lk, o0, o1, o2, c0, c1);
+                                // all-ones masks: below the bracket / above it, per stain; a pixel is "slow" when either stain is in neither
+                                const uint32_t l0a = set_lt(c0.x, lo0), h0a = set_gt(c0.x, hi0), l1a = set_lt(c1.x, lo1), h1a = set_gt(c1.x, hi1);
+                                const uint32_t l0b = set_lt(c0.y, lo0), h0b = set_gt(c0.y, hi0), l1b = set_lt(c1.y, lo1), h1b = set_gt(c1.y, hi1);
+                                cb0 -= l0a; cb0 -= l0b; cb1 -= l1a; cb1 -= l1b;
+                                slow |= ~((l0a | h0a) & (l1a | h1a)) & (1u << i);
+                                slow |= ~((l0b | h0b) & (l1b | h1b)) & (2u << i);
                             });
                             if (active) { below0 += cb0; below1 += cb1; } else slow = 0;
-                            wq_push_flagged(wq, slow, tin + (size_t)g * (GROUP_PX * 3), &sh->wq_overflow, [](int) { return 0u; });
+                            wq_push_flagged(wq, slow, (unsigned)g * GROUP_PX, &sh->wq_overflow);
                             wq_drain(wq, false, drain_px);
                         });
                         wq_drain(wq, true, drain_px);
@@ -972,11 +1028,12 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
     }
 }
 
-int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream) {
+template <int METHOD>
+static int launch_tile_pipeline_t(const PipeArgs& a, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     const size_t smem = OD_REP_BYTES + sizeof(PipeShared);
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tile_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tile_pipeline_kernel<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
@@ -995,7 +1052,14 @@ int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream) {
     attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, tile_pipeline_kernel, a);
+    return (int)cudaLaunchKernelEx(&cfg, tile_pipeline_kernel<METHOD>, a);
+}
+
+// One instantiation per extraction method: the Macenko and Vahadane chains share only the concentration passes, and a
+// single kernel holding both is allocated registers for the worse of the two.
+int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream) {
+    return a.method == SB_METHOD_MACENKO ? launch_tile_pipeline_t<SB_METHOD_MACENKO>(a, num_sms, stream)
+                                         : launch_tile_pipeline_t<SB_METHOD_VAHADANE>(a, num_sms, stream);
 }
 
 }  // namespace sb
