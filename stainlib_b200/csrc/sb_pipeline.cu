@@ -281,7 +281,22 @@ __device__ __forceinline__ void accum_if_tissue(float y, float bound, float o0, 
 // counts the keys below the bracket and appends the keys inside it to a shared-memory list; the target rank is then
 // selected inside the list.  The exact counts prove (or refute) that the rank fell inside the bracket -- on a miss or
 // a list overflow the caller falls back to the two-level histogram selection, so the result is always exact.
-constexpr unsigned LIST_CAP = L1_BINS;      // two lists alias the 32 KB histogram buffer
+// Two lists alias the 32 KB histogram buffer, 16 KB each.  A bracket that spans at most 2^16 keys (the dense middle of a
+// big tile) stores 16-bit offsets from its start, 8192 entries; a wider one (sparse tails) stores the 4096 full keys.
+constexpr unsigned LIST_BYTES = L1_BINS * 4;
+constexpr unsigned LIST_SPAN = 65536u;
+struct KeyList {
+    void* base;
+    unsigned start;     // bracket start (offset origin of the narrow form)
+    bool wide;
+    __device__ __forceinline__ unsigned cap() const { return wide ? LIST_BYTES / 4 : LIST_BYTES / 2; }
+    __device__ __forceinline__ void put(unsigned idx, unsigned key) const {
+        if (wide) static_cast<unsigned*>(base)[idx] = key; else static_cast<unsigned short*>(base)[idx] = (unsigned short)(key - start);
+    }
+    __device__ __forceinline__ unsigned get(unsigned idx) const {
+        return wide ? static_cast<const unsigned*>(base)[idx] : start + static_cast<const unsigned short*>(base)[idx];
+    }
+};
 constexpr int SAMPLE_STRIDE = 16;
 
 __device__ __forceinline__ unsigned warp_sum_u(unsigned x) {
@@ -299,14 +314,16 @@ __device__ inline void plan_bracket(unsigned n, unsigned n_s, unsigned lo, unsig
     rb = b > (double)(n_s - 1) ? n_s - 1 : (unsigned)b;
 }
 
-// rank-th smallest (0-based) of list[0..len): three 8-bit radix levels with a 256-bin histogram; whole block calls.
-__device__ __forceinline__ unsigned list_select(PipeShared* sh, const unsigned* list, unsigned len, unsigned rank) {
+// rank-th smallest (0-based) key of list[0..len): 8-bit radix levels (two for offsets, three for full keys) with a
+// 256-bin histogram; whole block calls.
+__device__ __forceinline__ unsigned list_select(PipeShared* sh, const KeyList& list, unsigned len, unsigned rank) {
     unsigned prefix = 0, mask = 0;
-    for (int shift = 16; shift >= 0; shift -= 8) {
+    const unsigned origin = list.wide ? 0u : list.start;
+    for (int shift = list.wide ? 16 : 8; shift >= 0; shift -= 8) {
         if (threadIdx.x < 256) sh->lhist[threadIdx.x] = 0;
         __syncthreads();
         for (unsigned i = threadIdx.x; i < len; i += NT) {
-            const unsigned k = list[i];
+            const unsigned k = list.get(i) - origin;
             if ((k & mask) == prefix) atomicAdd(&sh->lhist[(k >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -329,7 +346,7 @@ __device__ __forceinline__ unsigned list_select(PipeShared* sh, const unsigned* 
         mask |= 255u << shift;
         rank = sh->l_rem;
     }
-    return prefix;
+    return origin + prefix;
 }
 
 // ---------------------------------------------------------------------------------- rare-pixel compaction queues
@@ -552,10 +569,11 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     if (sh->s_ok) {
                         select_ranks<L1_BINS>(sh, sh->hist, 1, sh->q_rank, 4, sh->q_bin, sh->q_rem);
                         if (threadIdx.x == 0) {
-                            const unsigned n_s = sh->s_cnt;
                             for (int j = 0; j < 2; ++j) {
-                                sh->brk_a[j] = sh->q_rank[2 * j] == 0 ? 0u : (sh->q_bin[2 * j] << L2_BITS);
-                                sh->brk_b[j] = sh->q_rank[2 * j + 1] >= n_s - 1 ? (1u << KEY_BITS) : ((sh->q_bin[2 * j + 1] + 1u) << L2_BITS);
+                                // (a rank clamped to the sample's first / last element brackets at that element's bin: keys outside
+                                //  are still counted exactly, and the validation below catches a target rank that fell outside)
+                                sh->brk_a[j] = sh->q_bin[2 * j] << L2_BITS;
+                                sh->brk_b[j] = (sh->q_bin[2 * j + 1] + 1u) << L2_BITS;
                             }
                             // A pixel in the half-plane x > 0 whose diamond coordinate d = y/(x+|y|) lies safely between the
                             // low bracket and the high bracket (64 key units of slack, the key arithmetic errs by < 1) is
@@ -569,8 +587,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                         // ------------------------------------------------------ B1': count below / collect inside the brackets
                         const unsigned ka0 = sh->brk_a[0], kb0 = sh->brk_b[0], ka1 = sh->brk_a[1], kb1 = sh->brk_b[1];
                         const float f_lo = sh->fast_lo[0], f_hi = sh->fast_hi[0];
-                        unsigned* list0 = sh->hist;
-                        unsigned* list1 = sh->hist + LIST_CAP;
+                        const KeyList list0{sh->hist, ka0, kb0 - ka0 > LIST_SPAN}, list1{sh->hist + L1_BINS, ka1, kb1 - ka1 > LIST_SPAN};
                         unsigned below0 = 0, below1 = 0;
                         // exact treatment of one pixel (packed RGB): key, below counters, list appends
                         auto exact_px = [&](bool has, uint32_t rgb) {
@@ -580,9 +597,9 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                             const uint32_t key = angle_key(px, py);
                             if (has) {
                                 if (key < ka0) ++below0;
-                                else if (key < kb0) { const unsigned idx = atomicAdd(&sh->l_len[0], 1u); if (idx < LIST_CAP) list0[idx] = key; }
+                                else if (key < kb0) { const unsigned idx = atomicAdd(&sh->l_len[0], 1u); if (idx < list0.cap()) list0.put(idx, key); }
                                 if (key < ka1) ++below1;
-                                else if (key < kb1) { const unsigned idx = atomicAdd(&sh->l_len[1], 1u); if (idx < LIST_CAP) list1[idx] = key; }
+                                else if (key < kb1) { const unsigned idx = atomicAdd(&sh->l_len[1], 1u); if (idx < list1.cap()) list1.put(idx, key); }
                             }
                         };
                         WarpQueue wq{sh->wq[threadIdx.x >> 5], 0u};
@@ -622,7 +639,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                         if (threadIdx.x == 0) {
                             bool ok = sh->wq_overflow == 0;
                             for (int j = 0; j < 2; ++j)
-                                ok = ok && sh->l_len[j] <= LIST_CAP && sh->l_below[j] <= p_lo[j] && p_hi[j] < sh->l_below[j] + sh->l_len[j];
+                                ok = ok && sh->l_len[j] <= (j ? list1 : list0).cap() && sh->l_below[j] <= p_lo[j] && p_hi[j] < sh->l_below[j] + sh->l_len[j];
                             sh->s_ok = ok ? 1 : 0;
                         }
                         __syncthreads();
@@ -759,25 +776,53 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     double acc[9];
 #pragma unroll
                     for (int i = 0; i < 9; ++i) acc[i] = 0.0;
-                    auto accumulate = [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                        const uint32_t mbits = cache_mask ? *mask_slot(sh->hist, g - gb) : mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
-                        float f[9];
+                    // Sparse-code the tissue pixels of a group and add their a a^T / x a^T terms.  Atoms on the unit sphere (the
+                    // usual case: the norm constraint is active) take the compare-free LASSO two pixels at a time on the packed
+                    // f32x2 pipe with packed accumulators; atoms inside the ball take the general KKT form.
+                    // Partial sums stay in fp32 for the thread's whole share of the pass (<= a few thousand non-negative terms,
+                    // relative error ~1e-6, far below the 1e-5 the dictionary is converged to) and enter the fixed-order fp64
+                    // block reduction once per pass: the fp64 accumulators would not fit the register budget of this loop.
+                    float2 f[9];
 #pragma unroll
-                        for (int i = 0; i < 9; ++i) f[i] = 0.f;
+                    for (int i = 0; i < 9; ++i) f[i] = make_float2(0.f, 0.f);
+                    auto accumulate_general = [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                        const uint32_t mbits = cache_mask ? *mask_slot(sh->hist, g - gb) : mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
                         for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                             float c0, c1;
                             lasso2(lk, o0, o1, o2, c0, c1);
                             const bool m = (mbits & (1u << i)) != 0;
                             c0 = m ? c0 : 0.f; c1 = m ? c1 : 0.f;
-                            f[0] = fmaf(c0, c0, f[0]); f[1] = fmaf(c0, c1, f[1]); f[2] = fmaf(c1, c1, f[2]);
-                            f[3] = fmaf(o0, c0, f[3]); f[4] = fmaf(o1, c0, f[4]); f[5] = fmaf(o2, c0, f[5]);
-                            f[6] = fmaf(o0, c1, f[6]); f[7] = fmaf(o1, c1, f[7]); f[8] = fmaf(o2, c1, f[8]);
+                            f[0].x = fmaf(c0, c0, f[0].x); f[1].x = fmaf(c0, c1, f[1].x); f[2].x = fmaf(c1, c1, f[2].x);
+                            f[3].x = fmaf(o0, c0, f[3].x); f[4].x = fmaf(o1, c0, f[4].x); f[5].x = fmaf(o2, c0, f[5].x);
+                            f[6].x = fmaf(o0, c1, f[6].x); f[7].x = fmaf(o1, c1, f[7].x); f[8].x = fmaf(o2, c1, f[8].x);
                         });
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
                     };
-                    if (phase == 0) for_each_sample_group(tin, npx, gb, ge, aligned, accumulate);
-                    else for_each_group<true>(tin, npx, gb, ge, aligned, accumulate);
+                    auto accumulate_unit = [&](auto unit) {
+                        return [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
+                            constexpr int LM = decltype(unit)::value;
+                            const uint32_t mbits = cache_mask ? *mask_slot(sh->hist, g - gb) : mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
+                            for_each_pair_od(od_rep, lane_off, w, [&](int i, float2 o0, float2 o1, float2 o2) {
+                                float2 c0, c1;
+                                lasso2_unit_pair<LM>(lk, o0, o1, o2, c0, c1);
+                                const bool ma = (mbits & (1u << i)) != 0, mb = (mbits & (2u << i)) != 0;
+                                c0.x = ma ? c0.x : 0.f; c1.x = ma ? c1.x : 0.f;
+                                c0.y = mb ? c0.y : 0.f; c1.y = mb ? c1.y : 0.f;
+                                f[0] = __ffma2_rn(c0, c0, f[0]); f[1] = __ffma2_rn(c0, c1, f[1]); f[2] = __ffma2_rn(c1, c1, f[2]);
+                                f[3] = __ffma2_rn(o0, c0, f[3]); f[4] = __ffma2_rn(o1, c0, f[4]); f[5] = __ffma2_rn(o2, c0, f[5]);
+                                f[6] = __ffma2_rn(o0, c1, f[6]); f[7] = __ffma2_rn(o1, c1, f[7]); f[8] = __ffma2_rn(o2, c1, f[8]);
+                            });
+                        };
+                    };
+                    auto run_pass = [&](auto&& body) {
+                        if (phase == 0) for_each_sample_group(tin, npx, gb, ge, aligned, body);
+                        else for_each_group<true>(tin, npx, gb, ge, aligned, body);
+                    };
+                    const int lm = lasso_mode_of(lk.rg00, lk.rg11, lk.g01);
+                    if (lm == LASSO_UNIT_POS) run_pass(accumulate_unit(LassoMode<LASSO_UNIT_POS>{}));
+                    else if (lm == LASSO_UNIT_NEG) run_pass(accumulate_unit(LassoMode<LASSO_UNIT_NEG>{}));
+                    else run_pass(accumulate_general);
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) acc[i] = (double)f[i].x + (double)f[i].y;
                     block_reduce10(sh, pbuf, acc, 0u);
                     tile_sync(S);
                     cluster_total10(sh, pbuf, S);
@@ -867,9 +912,9 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     select_ranks<L1_BINS>(sh, sh->hist, 1, sh->q_rank, 2, sh->q_bin, sh->q_rem);
                     select_ranks<L1_BINS>(sh, sh->hist + L1_BINS, 1, sh->q_rank + 2, 2, sh->q_bin + 2, sh->q_rem + 2);
                     if (threadIdx.x < 2) {
-                        const unsigned n_s = sh->s_cnt, j = threadIdx.x;
-                        sh->brk_a[j] = sh->q_rank[2 * j] == 0 ? 0u : (sh->q_bin[2 * j] << L2_BITS);
-                        sh->brk_b[j] = sh->q_rank[2 * j + 1] >= n_s - 1 ? (1u << KEY_BITS) : ((sh->q_bin[2 * j + 1] + 1u) << L2_BITS);
+                        const unsigned j = threadIdx.x;
+                        sh->brk_a[j] = sh->q_bin[2 * j] << L2_BITS;
+                        sh->brk_b[j] = (sh->q_bin[2 * j + 1] + 1u) << L2_BITS;
                         // concentrations safely below / above the bracket (64 key units of slack) need no exact key
                         sh->fast_lo[j] = sh->brk_a[j] >= 64u ? float_below(conc_from_key(sh->brk_a[j] - 64u)) : -1.f;
                         sh->fast_hi[j] = sh->brk_b[j] + 64u < (1u << KEY_BITS) ? float_above(conc_from_key(sh->brk_b[j] + 64u)) : INFINITY;
@@ -878,8 +923,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     // ---------------------------------------------------------- C1': count below / collect inside the brackets
                     const unsigned ka0 = sh->brk_a[0], kb0 = sh->brk_b[0], ka1 = sh->brk_a[1], kb1 = sh->brk_b[1];
                     const float lo0 = sh->fast_lo[0], hi0 = sh->fast_hi[0], lo1 = sh->fast_lo[1], hi1 = sh->fast_hi[1];
-                    unsigned* list0 = sh->hist;
-                    unsigned* list1 = sh->hist + LIST_CAP;
+                    const KeyList list0{sh->hist, ka0, kb0 - ka0 > LIST_SPAN}, list1{sh->hist + L1_BINS, ka1, kb1 - ka1 > LIST_SPAN};
                     unsigned below0 = 0, below1 = 0;
                     auto bracket_pass = [&](auto unit) {
                         constexpr int LM = decltype(unit)::value;
@@ -894,11 +938,11 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                             const uint32_t k0 = conc_key(c0), k1 = conc_key(c1);
                             if (has && (recount || (!(c0 < lo0) && !(c0 > hi0)))) {
                                 if (k0 < ka0) ++below0;
-                                else if (k0 < kb0) { const unsigned idx = atomicAdd(&sh->l_len[0], 1u); if (idx < LIST_CAP) list0[idx] = k0; }
+                                else if (k0 < kb0) { const unsigned idx = atomicAdd(&sh->l_len[0], 1u); if (idx < list0.cap()) list0.put(idx, k0); }
                             }
                             if (has && (recount || (!(c1 < lo1) && !(c1 > hi1)))) {
                                 if (k1 < ka1) ++below1;
-                                else if (k1 < kb1) { const unsigned idx = atomicAdd(&sh->l_len[1], 1u); if (idx < LIST_CAP) list1[idx] = k1; }
+                                else if (k1 < kb1) { const unsigned idx = atomicAdd(&sh->l_len[1], 1u); if (idx < list1.cap()) list1.put(idx, k1); }
                             }
                         };
                         auto drain_px = [&](bool has, uint32_t pos) { exact_px(has, load_px(tin, pos), false); };
@@ -939,7 +983,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     if (threadIdx.x == 0) {
                         bool ok = sh->wq_overflow == 0;
                         for (int j = 0; j < 2; ++j)
-                            ok = ok && sh->l_len[j] <= LIST_CAP && sh->l_below[j] <= c_lo && c_hi < sh->l_below[j] + sh->l_len[j];
+                            ok = ok && sh->l_len[j] <= (j ? list1 : list0).cap() && sh->l_below[j] <= c_lo && c_hi < sh->l_below[j] + sh->l_len[j];
                         sh->s_ok = ok ? 1 : 0;
                     }
                     __syncthreads();
