@@ -51,7 +51,8 @@ typedef struct sb_params {
     double lasso_lambda;         /* 0.01  stain_utils.py:69 (get_concentrations regularizer)                       */
     double conc_percentile;      /* 99    normalizer.py:36,47                                                      */
     double dl_lambda;            /* 0.1   vahadane_stain_extractor.py:19 (trainDL lambda1)                         */
-    int    dl_iters;             /* 8     full-batch dictionary-learning passes (reference: 1 s wall-clock budget) */
+    int    dl_iters;             /* 10    at most this many full-batch dictionary-learning passes (they stop at a     */
+                                 /*       residual of 2e-6; the reference runs for 1 s of wall-clock time)           */
     int    cluster_size;         /* CTAs cooperating on one tile: 0 = auto, else 1/2/4/8                            */
     int    dl_sample_iters;      /* 12    warm-start passes over a 1-in-16 sample of the tile before the full      */
                                  /*       passes (skipped, and 4 full passes added, when the sample has < 1024     */

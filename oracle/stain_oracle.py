@@ -213,8 +213,11 @@ def vahadane_finish(dictionary):
 # Accelerated full-batch learner -- the schedule the CUDA path runs by default.  Same fixed point as
 # ``train_dl_fullbatch`` (the plain iteration contracts at ~0.83 per pass: 50 passes leave 1e-5), reached in a fifth of
 # the passes: (1) warm start on a deterministic 1-in-16 sample of the tile's 16-pixel groups, (2) Anderson acceleration
-# (type II, memory 4) of the 6-component map D -> F(D), restarted whenever the residual grows.
+# (type II, memory 4) of the 6-component map D -> F(D), restarted whenever the residual grows; the full passes start
+# with the difference history of the sample passes.
 DL_SAMPLE_STRIDE = 16
+DL_SAMPLE_TOL = 1e-4       # the sample passes stop once ||F(D) - D|| falls below this (their own sampling error is ~3e-3)
+DL_FULL_TOL = 2e-6         # the full passes stop here (a few times the fp32 noise floor of the CUDA path's sums)
 DL_GROUP_PX = 16
 
 
@@ -229,42 +232,42 @@ def dl_sample_indices(npx):
 
 class AndersonState(object):
     def __init__(self):
-        self.x, self.r, self.last = [], [], -1.0
+        self.dx, self.dr, self.px, self.pr, self.last = [], [], None, None, -1.0
 
 
 def anderson_step(st, m, D, FD):
-    """One safeguarded Anderson step (csrc/sb_device.cuh: aa_step).  D: current iterate, FD = F(D); returns the next."""
+    """One safeguarded Anderson step (csrc/sb_device.cuh: aa_step).  D: current iterate, FD = F(D); returns the next.
+    History = the last <= m difference columns dx = x_{i+1}-x_i, dr = r_{i+1}-r_i; solve (dr^T dr + 1e-10 tr I) g = dr^T r
+    by Gaussian elimination without pivoting (the matrix is symmetric positive definite)."""
     x, fx = D.reshape(-1).copy(), FD.reshape(-1)
     r = fx - x
     rn = float(np.sqrt((r * r).sum()))
     if m <= 0:
         return FD.copy()
     if st.last >= 0.0 and rn > st.last:
-        st.x, st.r = [], []
+        st.dx, st.dr, st.px, st.pr = [], [], None, None
     st.last = rn
-    if len(st.x) == m + 1:
-        st.x.pop(0)
-        st.r.pop(0)
-    st.x.append(x)
-    st.r.append(r.copy())
-    h = len(st.x) - 1
+    if st.px is not None:
+        st.dx.append(x - st.px)
+        st.dr.append(r - st.pr)
+        if len(st.dx) > m:
+            st.dx.pop(0)
+            st.dr.pop(0)
+    st.px, st.pr = x, r.copy()
+    h = len(st.dx)
     if h < 1:
         return FD.copy()
-    dR = [st.r[i + 1] - st.r[i] for i in range(h)]
-    dX = [st.x[i + 1] - st.x[i] for i in range(h)]
+    dR, dX = st.dr, st.dx
     G = np.array([[float((dR[i] * dR[j]).sum()) for j in range(h)] + [float((dR[i] * r).sum())] for i in range(h)])
     tr = float(np.trace(G[:, :h]))
     if not (tr > 0.0 and np.isfinite(tr)):
         return FD.copy()
     G[np.arange(h), np.arange(h)] += 1e-10 * tr
-    for c in range(h):                                   # Gaussian elimination with partial pivoting
-        piv = c + int(np.argmax(np.abs(G[c:, c])))
-        if not abs(G[piv, c]) > 0.0:
+    for c in range(h):
+        if not G[c, c] > 0.0:
             return FD.copy()
-        if piv != c:
-            G[[c, piv]] = G[[piv, c]]
         for i in range(c + 1, h):
-            G[i, c:] -= (G[i, c] / G[c, c]) * G[c, c:]
+            G[i, c + 1:] -= (G[i, c] / G[c, c]) * G[c, c + 1:]
     gam = np.zeros(h)
     for i in range(h - 1, -1, -1):
         gam[i] = (G[i, h] - (G[i, i + 1:h] * gam[i + 1:]).sum()) / G[i, i]
@@ -280,22 +283,28 @@ def _dl_map(X, D, lam):
     return _dict_update(D, Al @ Al.T, X @ Al.T)
 
 
-def train_dl_accel(X, Xs, lam=0.1, n_iter=8, n_sample_iter=12, anderson=4):
-    """X: m x n tissue OD columns; Xs: the tissue columns that fall in the sample (may be None)."""
+def train_dl_accel(X, Xs, lam=0.1, n_iter=10, n_sample_iter=12, anderson=4):
+    """X: m x n tissue OD columns; Xs: the tissue columns that fall in the sample (may be None).  The full passes
+    inherit the Anderson difference history of the sample passes (same Jacobian to first order)."""
     D = normalize_matrix_rows(RUIFROK_HE).T.copy()
     use_sample = n_sample_iter > 0 and Xs is not None and Xs.shape[1] >= 1024
     phases = ([(Xs, n_sample_iter)] if use_sample else []) + [(X, n_iter + (4 if (n_sample_iter > 0 and not use_sample) else 0))]
+    st = AndersonState()
     for data, n_it in phases:
-        st = AndersonState()
+        st.px, st.pr, st.last = None, None, -1.0          # keep dx / dr across the sample -> full switch
         for _ in range(n_it):
-            D = anderson_step(st, anderson, D, _dl_map(data, D, lam))
+            FD = _dl_map(data, D, lam)
+            stop = anderson > 0 and float(np.sqrt(((FD - D) ** 2).sum())) < (DL_FULL_TOL if data is X else DL_SAMPLE_TOL)
+            D = anderson_step(st, anderson, D, FD)
+            if stop:
+                break
     return D
 
 
 def vahadane_stain_matrix(I, luminosity_threshold=0.8, regularizer=0.1, n_iter=None, solver="accel", seed=0,
                           n_sample_iter=12, anderson=4):
     """``VahadaneStainExtractor.get_stain_matrix`` -- ``vahadane_stain_extractor.py:19-43`` with ``spams.trainDL``
-    replaced by one of the restatements above: "accel" (default: what the CUDA path runs, n_iter=8 full passes),
+    replaced by one of the restatements above: "accel" (default: what the CUDA path runs, at most n_iter=10 full passes),
     "fullbatch" (plain alternating minimisation, n_iter=50) or "online" (SPAMS-like, seeded)."""
     assert is_uint8_image(I), "Image should be RGB uint8."
     tissue_mask = get_tissue_mask(I, luminosity_threshold=luminosity_threshold).reshape((-1,))
@@ -304,7 +313,7 @@ def vahadane_stain_matrix(I, luminosity_threshold=0.8, regularizer=0.1, n_iter=N
     if solver == "accel":
         si = dl_sample_indices(OD_all.shape[0])
         si = si[tissue_mask[si]]
-        D = train_dl_accel(OD.T, OD_all[si].T, lam=regularizer, n_iter=8 if n_iter is None else n_iter,
+        D = train_dl_accel(OD.T, OD_all[si].T, lam=regularizer, n_iter=10 if n_iter is None else n_iter,
                            n_sample_iter=n_sample_iter, anderson=anderson)
     elif solver == "fullbatch":
         D = train_dl_fullbatch(OD.T, lam=regularizer, n_iter=50 if n_iter is None else n_iter)

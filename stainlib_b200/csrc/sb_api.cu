@@ -121,7 +121,7 @@ void sb_default_params(sb_params* p) {
     p->lasso_lambda = 0.01;
     p->conc_percentile = 99.0;
     p->dl_lambda = 0.1;
-    p->dl_iters = 8;
+    p->dl_iters = 10;
     p->cluster_size = 0;
     p->dl_sample_iters = 12;
     p->dl_anderson = 4;

@@ -448,78 +448,107 @@ __device__ inline void jacobi_eig3(const double a_in[6], double w[3], double v[3
 // (anderson_step): residual growth drops the history; the extrapolated point is projected back onto
 // {D >= 0, ||d_j|| <= 1}; a singular or non-finite solve falls back to the plain iterate.
 constexpr int AA_MAX = 4;
+// Lives in shared memory; one thread steps it.  The history is kept as difference columns (circular) with their Gram
+// matrix maintained incrementally, so a step costs a few hundred fp64 operations with compile-time addressing.
 struct AAState {
-    double x[AA_MAX + 1][6];
-    double r[AA_MAX + 1][6];
+    double dx[AA_MAX][6], dr[AA_MAX][6];   // x_{i+1} - x_i and r_{i+1} - r_i of the last <= m steps
+    double G[AA_MAX][AA_MAX];              // dr^T dr
+    double px[6], pr[6];                   // previous iterate and its residual
+    double W[AA_MAX][AA_MAX + 1];          // elimination scratch
     double last;
-    int n;
+    int nd, head, have_prev;
 };
-__device__ inline void aa_reset(AAState& s) { s.n = 0; s.last = -1.0; }
+__device__ inline void aa_reset(AAState& s) { s.nd = 0; s.head = 0; s.have_prev = 0; s.last = -1.0; }
+// Switch to a related map (sample -> full tile): keep the difference columns, forget the last iterate and residual norm.
+__device__ inline void aa_carry(AAState& s) { s.have_prev = 0; s.last = -1.0; }
 // D: current iterate (in) / next iterate (out); FD = F(D).
 __device__ inline void aa_step(AAState& s, int m, double* D, const double* FD) {
     double r[6], rn = 0.0;
+#pragma unroll
     for (int k = 0; k < 6; ++k) { r[k] = FD[k] - D[k]; rn += r[k] * r[k]; }
     rn = sqrt(rn);
-    if (m <= 0) { for (int k = 0; k < 6; ++k) D[k] = FD[k]; return; }
-    if (s.last >= 0.0 && rn > s.last) s.n = 0;          // the last extrapolation made things worse: restart
-    s.last = rn;
-    if (s.n == m + 1) {
-        for (int i = 0; i < m; ++i)
-            for (int k = 0; k < 6; ++k) { s.x[i][k] = s.x[i + 1][k]; s.r[i][k] = s.r[i + 1][k]; }
-        s.n = m;
+    bool ok = m > 0;
+    if (ok) {
+        if (s.last >= 0.0 && rn > s.last) { s.nd = 0; s.head = 0; s.have_prev = 0; }   // the last step made things worse: restart
+        s.last = rn;
+        if (s.have_prev) {
+            const int c = s.head;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { s.dx[c][k] = D[k] - s.px[k]; s.dr[c][k] = r[k] - s.pr[k]; }
+            if (s.nd < m) s.nd += 1;
+            s.head = (c + 1 == m) ? 0 : c + 1;
+#pragma unroll
+            for (int j = 0; j < AA_MAX; ++j) {
+                if (j < s.nd) {
+                    double g = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) g += s.dr[c][k] * s.dr[j][k];
+                    s.G[c][j] = g; s.G[j][c] = g;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { s.px[k] = D[k]; s.pr[k] = r[k]; }
+        s.have_prev = 1;
+        ok = s.nd >= 1;
     }
-    for (int k = 0; k < 6; ++k) { s.x[s.n][k] = D[k]; s.r[s.n][k] = r[k]; }
-    s.n += 1;
-    const int h = s.n - 1;
-    bool ok = h >= 1;
     double xn[6];
     if (ok) {
-        double G[AA_MAX][AA_MAX + 1];
+        const int nd = s.nd;
         double tr = 0.0;
-        for (int i = 0; i < h; ++i) {
-            for (int j = 0; j < h; ++j) {
-                double g = 0.0;
-                for (int k = 0; k < 6; ++k) g += (s.r[i + 1][k] - s.r[i][k]) * (s.r[j + 1][k] - s.r[j][k]);
-                G[i][j] = g;
-            }
-            double b = 0.0;
-            for (int k = 0; k < 6; ++k) b += (s.r[i + 1][k] - s.r[i][k]) * r[k];
-            G[i][h] = b;
-            tr += G[i][i];
-        }
+#pragma unroll
+        for (int i = 0; i < AA_MAX; ++i) if (i < nd) tr += s.G[i][i];
         ok = tr > 0.0 && isfinite(tr);
-        for (int i = 0; i < h; ++i) G[i][i] += 1e-10 * tr;
-        // Gaussian elimination with partial pivoting on the augmented h x (h+1) system
-        for (int c = 0; c < h && ok; ++c) {
-            int piv = c;
-            for (int i = c + 1; i < h; ++i) if (fabs(G[i][c]) > fabs(G[piv][c])) piv = i;
-            if (!(fabs(G[piv][c]) > 0.0)) { ok = false; break; }
-            if (piv != c) for (int j = c; j <= h; ++j) { const double t = G[c][j]; G[c][j] = G[piv][j]; G[piv][j] = t; }
-            for (int i = c + 1; i < h; ++i) {
-                const double f = G[i][c] / G[c][c];
-                for (int j = c; j <= h; ++j) G[i][j] -= f * G[c][j];
+        // [G + 1e-10 tr I | dr^T r], padded with identity rows to a fixed 4 x 5 system
+#pragma unroll
+        for (int i = 0; i < AA_MAX; ++i) {
+#pragma unroll
+            for (int j = 0; j < AA_MAX; ++j)
+                s.W[i][j] = (i < nd && j < nd) ? s.G[i][j] + (i == j ? 1e-10 * tr : 0.0) : (i == j ? 1.0 : 0.0);
+            double b = 0.0;
+            if (i < nd) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) b += s.dr[i][k] * r[k];
+            }
+            s.W[i][AA_MAX] = b;
+        }
+        // Gaussian elimination (symmetric positive definite after the regularisation: no pivoting) and back substitution
+#pragma unroll
+        for (int c = 0; c < AA_MAX; ++c) {
+            const double piv = s.W[c][c];
+            ok = ok && piv > 0.0;
+#pragma unroll
+            for (int i = c + 1; i < AA_MAX; ++i) {
+                const double f = s.W[i][c] / piv;
+#pragma unroll
+                for (int j = c + 1; j <= AA_MAX; ++j) s.W[i][j] -= f * s.W[c][j];
             }
         }
         double gam[AA_MAX];
-        for (int i = h - 1; i >= 0 && ok; --i) {
-            double v = G[i][h];
-            for (int j = i + 1; j < h; ++j) v -= G[i][j] * gam[j];
-            gam[i] = v / G[i][i];
+#pragma unroll
+        for (int i = AA_MAX - 1; i >= 0; --i) {
+            double v = s.W[i][AA_MAX];
+#pragma unroll
+            for (int j = i + 1; j < AA_MAX; ++j) v -= s.W[i][j] * gam[j];
+            gam[i] = v / s.W[i][i];
         }
-        if (ok) {
-            for (int k = 0; k < 6; ++k) {
-                double v = D[k] + r[k];
-                for (int i = 0; i < h; ++i) v -= gam[i] * ((s.x[i + 1][k] - s.x[i][k]) + (s.r[i + 1][k] - s.r[i][k]));
-                xn[k] = v > 0.0 ? v : 0.0;
-                ok = ok && isfinite(v);
-            }
-            for (int j = 0; j < 2 && ok; ++j) {
-                const double nrm = sqrt(xn[3 * j] * xn[3 * j] + xn[3 * j + 1] * xn[3 * j + 1] + xn[3 * j + 2] * xn[3 * j + 2]);
-                const double sc = 1.0 / (nrm > 1.0 ? nrm : 1.0);
-                for (int k = 0; k < 3; ++k) xn[3 * j + k] *= sc;
-            }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double v = D[k] + r[k];
+#pragma unroll
+            for (int i = 0; i < AA_MAX; ++i) if (i < nd) v -= gam[i] * (s.dx[i][k] + s.dr[i][k]);
+            xn[k] = v > 0.0 ? v : 0.0;
+            ok = ok && isfinite(v);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double nrm = sqrt(xn[3 * j] * xn[3 * j] + xn[3 * j + 1] * xn[3 * j + 1] + xn[3 * j + 2] * xn[3 * j + 2]);
+            const double sc = 1.0 / (nrm > 1.0 ? nrm : 1.0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) xn[3 * j + k] *= sc;
         }
     }
+#pragma unroll
     for (int k = 0; k < 6; ++k) D[k] = ok ? xn[k] : FD[k];
 }
 

@@ -27,6 +27,8 @@
 
 namespace sb {
 
+constexpr double DL_SAMPLE_TOL = 1e-4;   // residual norm at which the Vahadane sample passes stop (oracle: DL_SAMPLE_TOL)
+constexpr double DL_FULL_TOL = 2e-6;     // ... and the full passes (a few times the fp32 noise floor of the sums)
 constexpr unsigned WQ_CAP = 160;   // entries per warp queue: drained to < 32 once per group, a group adds at most 128 kept pushes
 
 struct __align__(16) PipeShared {
@@ -52,6 +54,7 @@ struct __align__(16) PipeShared {
     int flags;
     double D[6];                     // Vahadane dictionary, rows = atoms
     AAState aa;                      // Anderson history of the dictionary iteration (thread 0)
+    int dl_stop;                     // the current phase has converged (residual below DL_SAMPLE_TOL / DL_FULL_TOL)
     double Msrc[6];
     double maxC[2];
 };
@@ -770,7 +773,9 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
             // phase 0: warm start on the 1-in-16 sample; phase 1: full passes.  Without a usable sample: 4 more full passes.
             for (int phase = use_sample ? 0 : 1; phase < 2 && sh->flags == 0; ++phase) {
                 const int n_it = phase == 0 ? a.dl_sample_iters : a.dl_iters + ((a.dl_sample_iters > 0 && !use_sample) ? 4 : 0);
-                if (threadIdx.x == 0) aa_reset(sh->aa);
+                // The full passes inherit the difference history of the sample passes: the sample map has (nearly) the same
+                // Jacobian, so the first full steps are already quasi-Newton steps; only the residual bookkeeping restarts.
+                if (threadIdx.x == 0) { if (phase == 0 || !use_sample) aa_reset(sh->aa); else aa_carry(sh->aa); sh->dl_stop = 0; }
                 for (int it = 0; it < n_it; ++it) {
                     const LassoK lk = sh->lk;
                     double acc[9];
@@ -847,10 +852,17 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                                 for (int k = 0; k < 3; ++k) FD[3 * j + k] = u[k] * sc;
                             }
                         }
+                        // The sample only has to deliver a starting point within its own sampling error (~3e-3) and a
+                        // difference history that is still far above the fp32 noise of the sums: stop it at 1e-4.
+                        double rn2 = 0.0;
+                        for (int k = 0; k < 6; ++k) rn2 += (FD[k] - sh->D[k]) * (FD[k] - sh->D[k]);
+                        const double tol = phase == 0 ? DL_SAMPLE_TOL : DL_FULL_TOL;
+                        if (a.dl_anderson > 0 && rn2 < tol * tol) sh->dl_stop = 1;      // this step is still applied, then the phase ends
                         aa_step(sh->aa, a.dl_anderson, sh->D, FD);
                         make_lasso_consts(sh->D, a.dl_lambda, sh->lk);
                     }
                     __syncthreads();
+                    if (sh->dl_stop) break;
                 }
             }
             if (threadIdx.x == 0 && sh->flags == 0) {

@@ -4,7 +4,7 @@
 sparse-NMF started from the Ruifrok H/E vectors: alternations of closed-form sparse coding and one block-coordinate
 dictionary update -- ``n_sample_iter`` warm-start passes over a 1-in-16 sample of the tile, then ``n_iter`` passes over
 every tissue pixel, the 6-component fixed-point map Anderson-accelerated with memory ``anderson``
-(``n_sample_iter=0, anderson=0`` is the plain iteration).  See DESIGN.md for the parity definition."""
+(both phases stop early once the residual is small; ``n_sample_iter=0, anderson=0`` with a fixed ``n_iter`` is the plain iteration).  See DESIGN.md for the parity definition."""
 from stainlib_b200 import _native as nv
 from stainlib_b200.extraction.macenko_stain_extractor import _extract
 from stainlib_b200.utils.stain_utils import ABCStainExtractor, is_uint8_image
@@ -12,7 +12,7 @@ from stainlib_b200.utils.stain_utils import ABCStainExtractor, is_uint8_image
 
 class VahadaneStainExtractor(ABCStainExtractor):
     last_status = None
-    n_iter = 8
+    n_iter = 10
     n_sample_iter = 12
     anderson = 4
 

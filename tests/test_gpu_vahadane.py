@@ -66,7 +66,7 @@ def test_vahadane_batch_and_clusters(sb):
 
 @pytest.mark.parametrize("size,seed", [(256, 0), (256, 7), (512, 3), (128, 5), ((200, 333), 11)])
 def test_vahadane_accelerated_vs_oracle(sb, size, seed):
-    """Default schedule (12 sample passes + 8 full passes, Anderson memory 4) against the CPU restatement of the same
+    """Default schedule (sample passes, then full passes to a residual of 2e-6, Anderson memory 4) against the CPU restatement of the same
     schedule, and against the converged plain iteration (the fixed point both approximate)."""
     H, W = (size, size) if isinstance(size, int) else size
     I = synth_tile(seed, H, W)
