@@ -37,9 +37,14 @@ WORKLOADS = {
     "macenko512": ("macenko", 1024, 512, 512, "config[1]: 1024 synthetic 512x512 H&E tiles, Macenko normalize"),
     "macenko256": ("macenko", 4096, 256, 256, "4096 synthetic 256x256 tiles, Macenko normalize (config[4] tile size)"),
     "macenko1024": ("macenko", 256, 1024, 1024, "256 synthetic 1024x1024 tiles, Macenko normalize"),
-    "vahadane1024": ("vahadane", 256, 1024, 1024, "config[2] tile size: 1024x1024 tiles, Vahadane sparse-NMF normalize (256 per GPU)"),
+    "vahadane1024": ("vahadane", 256, 1024, 1024, "config[2] tile size: 1024x1024 tiles, Vahadane sparse-NMF normalize (256 per GPU; --tiles 4096 = the full config)"),
     "vahadane512": ("vahadane", 1024, 512, 512, "1024 synthetic 512x512 tiles, Vahadane sparse-NMF normalize"),
+    # config[4]: 100k 256x256 tiles in total, split over the ranks (strong scaling)
+    "stream256": ("macenko", 100000, 256, 256, "config[4]: WSI-scale stream, 100000 synthetic 256x256 tiles in total, Macenko normalize"),
+    # config[3]: HedLightColorAugmenter (per-tile sigma/bias) then ReinhardStainNormalizer, 1024 tiles of 512x512 per GPU
+    "hed_reinhard512": ("hed_reinhard", 1024, 512, 512, "config[3]: HedLightColorAugmenter + Reinhard normalize, 1024 synthetic 512x512 tiles per GPU"),
 }
+STRONG = {"stream256"}
 BYTES_PER_PX = 6.0   # 3 B read + 3 B written
 
 
@@ -51,12 +56,21 @@ def _cpu_init(method, tgt):
     import cv2
     cv2.setNumThreads(1)
     from oracle import stain_oracle as so
-    n = so.ExtractiveStainNormalizer(method)      # vahadane: the same accelerated schedule the CUDA path runs
+    if method == "hed_reinhard":
+        n = so.ReinhardStainNormalizer()
+    else:
+        n = so.ExtractiveStainNormalizer(method)      # vahadane: the same accelerated schedule the CUDA path runs
     n.fit(tgt)
     _CPU["n"] = n
+    _CPU["method"] = method
 
 
 def _cpu_one(tile):
+    if _CPU["method"] == "hed_reinhard":
+        from oracle import stain_oracle as so
+        rs = np.random.RandomState(int(tile[0, 0, 0]) + 1)
+        aug = so.hed_augment(tile, rs.uniform(-0.1, 0.1, 3), rs.uniform(-0.1, 0.1, 3))   # HedLight ranges (augmenter.py:366-368)
+        return int(_CPU["n"].transform(aug)[0, 0, 0])
     return int(_CPU["n"].transform(tile)[0, 0, 0])
 
 
@@ -171,7 +185,8 @@ def run_reference(args, method, B, H, W, desc):
         secs += dt
     value = float(np.mean(vals)) if vals else 0.0
     line = {
-        "impl": "reference", "metric": f"Mpixels/sec stain-normalize ({method})", "value": round(value, 3), "unit": "Mpx/s",
+        "impl": "reference", "metric": "Mpixels/sec HED-light augment + Reinhard normalize" if method == "hed_reinhard" else f"Mpixels/sec stain-normalize ({method})",
+        "value": round(value, 3), "unit": "Mpx/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * secs / max(args.steps, 1), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "tiles_per_step": per_step, "tile": [H, W]},
@@ -182,6 +197,110 @@ def run_reference(args, method, B, H, W, desc):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- config[3]: HED + Reinhard
+def run_hed_reinhard(args, B, H, W, desc, rank, world, local, cpu):
+    """One step = HedLightColorAugmenter.transform (per-tile sigma / bias drawn on the host as augmenter.py:333-344 does)
+    followed by ReinhardStainNormalizer.transform (normalizer.py:70-94) over this rank's tiles."""
+    import torch
+    import torch.distributed as dist
+    import stainlib_b200 as sb
+    from stainlib_b200 import _native as nv
+    from stainlib_b200.augmentation.augmenter import HedLightColorAugmenter
+    from stainlib_b200.synth import synth_tile, synth_batch
+
+    hed = HedLightColorAugmenter()
+    rein = sb.ReinhardStainNormalizer()
+    rein.fit(synth_tile(1, H, W, kind="target") if rank == 0 else None)
+    np.random.seed(rank)
+    sig = np.random.uniform(-0.1, 0.1, size=(B, 3))
+    bias = np.random.uniform(-0.1, 0.1, size=(B, 3))
+    pool = torch.from_numpy(synth_batch(5000 + 64 * rank, min(B, 64), H, W))
+    host_in = pool.repeat(-(-B // pool.shape[0]), 1, 1, 1)[:B].contiguous().pin_memory()
+    dev_in = host_in.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+    npx_rank = B * H * W
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(x):
+        return rein.transform(hed.transform(x, sigmas=sig, biases=bias))
+
+    for _ in range(args.warmup):
+        out = step(dev_in)
+    barrier()
+    l0 = nv.launch_count(local)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local) as clocks:
+        ev[0].record()
+        for i in range(args.steps):
+            out = step(dev_in)
+            ev[i + 1].record()
+        barrier()
+    launches = nv.launch_count(local) - l0
+    t = torch.tensor([ev[0].elapsed_time(ev[-1])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * npx_rank * args.steps / (ms_total * 1e-3) / 1e6
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    hed_ms = timed(lambda: hed.transform(dev_in, sigmas=sig, biases=bias), args.steps)
+    mid = hed.transform(dev_in, sigmas=sig, biases=bias)
+    rein_ms = timed(lambda: rein.transform(mid), args.steps)
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            host_out = step(host_in)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            host_out = step(host_in)                    # host tensor in -> host tensor out
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(world * npx_rank * args.steps / float(tt.item()) / 1e6, 1), "unit": "Mpx/s",
+               "h2d_bytes_per_step": int(world * host_in.numel()), "d2h_bytes_per_step": int(world * host_out.numel()),
+               "matches_device_path": bool(torch.equal(host_out, out.cpu()))}
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        step_ms = ms_total / args.steps
+        gbs = lambda ms, bpp: npx_rank * bpp / (ms * 1e-3) / 1e9
+        line = {
+            "metric": "Mpixels/sec HED-light augment + Reinhard normalize", "value": round(value, 1), "unit": "Mpx/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "integer LAB (exact), f32/f64 per-tile tables", "data": "synthetic",
+            "config": {"workload": desc, "tiles_per_gpu": B, "tile": [H, W], "l2_policy": "805 MB input per GPU, larger than the 126 MB L2"},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            # dominant kernel: lab_tile_kernel (Reinhard transform: percentile + LAB statistics + recolour, 6 algorithmic B/px)
+            "roofline": {"bound": "hbm", "kernel": "lab_tile_kernel (Reinhard transform)", "achieved": round(gbs(rein_ms, 6.0), 1), "peak": peak,
+                         "unit": "GB/s", "frac": round(gbs(rein_ms, 6.0) / peak, 4), "peak_source": peak_src, "algorithmic_bytes_per_px": 6.0,
+                         "launch_ms": round(rein_ms, 4), "share_of_step": round(rein_ms / step_ms, 3), "traffic": None},
+            "roofline_hed": {"bound": "hbm", "kernel": "byte_sum_kernel + hed_kernel (HED augment)", "achieved": round(gbs(hed_ms, 6.0), 1), "peak": peak,
+                             "unit": "GB/s", "frac": round(gbs(hed_ms, 6.0) / peak, 4), "algorithmic_bytes_per_px": 6.0, "launch_ms": round(hed_ms, 4),
+                             "share_of_step": round(hed_ms / step_ms, 3), "traffic": None},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -198,16 +317,18 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     method, B, H, W, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    strong = args.workload in STRONG and not args.tiles
     if args.tiles:
         B = args.tiles
+    elif strong:                                       # fixed total, contiguous shard per rank
+        B = (B * (rank + 1)) // world - (B * rank) // world
     if args.impl == "reference":
         return run_reference(args, method, B, H, W, desc)
     if args.warmup < 3:
         args.warmup = 3                                # timing rule: at least 3 warm-up steps
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
 
     # CPU baseline first (rank 0, N=1): fork-based pool must run before CUDA is initialised in this process
     cpu = None
@@ -216,7 +337,8 @@ def main():
         v, cores, dt = cpu_throughput(method, H, W, n_sample)
         cpu = {"value": round(v, 3), "unit": "Mpx/s", "cores": cores, "kind": "port",
                "sample": f"{n_sample} tiles of {H}x{W} ({dt:.1f} s wall), one process per core; numpy/OpenCV oracle port of "
-                         "normalizer.py:39-50 with closed-form LASSO in place of spams.lasso"}
+                         + ("augmenter.py:276-331 (skimage 0.17 rgb2hed/hed2rgb restated) + normalizer.py:70-94" if method == "hed_reinhard" else
+                            "normalizer.py:39-50 with closed-form LASSO in place of spams.lasso")}
 
     import torch
     import torch.distributed as dist
@@ -227,6 +349,9 @@ def main():
     import stainlib_b200 as sb
     from stainlib_b200 import _native as nv
     from stainlib_b200.synth import synth_tile, synth_batch
+
+    if method == "hed_reinhard":
+        return run_hed_reinhard(args, B, H, W, desc, rank, world, local, cpu)
 
     kw = {"cluster_size": args.cluster} if args.cluster else {}
     norm = sb.ExtractiveStainNormalizer(method, **kw)
@@ -262,7 +387,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total_max = float(t.item())
-    value = world * npx_rank * args.steps / (ms_total_max * 1e-3) / 1e6
+    npx_all = torch.tensor([npx_rank], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(npx_all)
+    npx_all = float(npx_all.item())                     # pixels per step over all ranks (weak: world x shard; strong: the fixed total)
+    value = npx_all * args.steps / (ms_total_max * 1e-3) / 1e6
     status_bad = int((norm.last_status != 0).sum().item())
 
     # ---- the two kernels of a step, each timed alone with CUDA events on the launching stream
@@ -303,12 +432,13 @@ def main():
     # ---- end to end from pinned host memory through the public API
     e2e = None
     if not args.no_e2e:
+        e2e_steps = args.steps if B * H * W * 3 <= (2 << 30) else max(2, min(args.steps, 3))   # huge batches: few steps
         host_out = torch.empty_like(host_in).pin_memory()     # result buffer reused across steps (as a streaming caller would)
-        for _ in range(3):
+        for _ in range(3 if e2e_steps == args.steps else 1):
             norm.transform(host_in, out=host_out)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             norm.transform(host_in, out=host_out)       # synchronous: returns when the last byte is back on the host
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -317,8 +447,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         same = bool(torch.equal(host_out, out.cpu()))
-        e2e = {"value": round(world * npx_rank * args.steps / dt / 1e6, 1), "unit": "Mpx/s",
-               "h2d_bytes_per_step": int(world * host_in.numel()), "d2h_bytes_per_step": int(world * host_out.numel() + world * 4 * B),
+        e2e = {"value": round(npx_all * e2e_steps / dt / 1e6, 1), "unit": "Mpx/s", "steps": e2e_steps,
+               "h2d_bytes_per_step": int(npx_all * 3), "d2h_bytes_per_step": int(npx_all * 3 + world * 4 * B),
                "matches_device_path": same}
 
     if rank == 0:
@@ -330,7 +460,7 @@ def main():
         line = {
             "metric": f"Mpixels/sec stain-normalize ({method})", "value": round(value, 1), "unit": "Mpx/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total_max / args.steps, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32 per-pixel arithmetic on u8 pixels, f64 per-tile reductions", "data": "synthetic",
             "config": {"workload": desc, "tiles_per_gpu": B, "tile": [H, W], "method": method,
                        "l2_policy": f"input {host_in.numel() / 1e6:.0f} MB + output per GPU, larger than the 126 MB L2; no flush needed",
