@@ -266,12 +266,18 @@ def run_hed_reinhard(args, B, H, W, desc, rank, world, local, cpu):
 
     e2e = None
     if not args.no_e2e:
+        host_out = torch.empty_like(host_in).pin_memory()
+
+        def e2e_step():                                 # pinned host -> device, both operators on the device, -> pinned host
+            x = host_in.cuda(non_blocking=True)
+            host_out.copy_(step(x), non_blocking=True)
+            torch.cuda.synchronize()
         for _ in range(2):
-            host_out = step(host_in)
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            host_out = step(host_in)                    # host tensor in -> host tensor out
+            e2e_step()
         torch.cuda.synchronize()
         tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:

@@ -37,6 +37,7 @@ struct LabArgs {
 struct __align__(16) LabShared {
     unsigned hist[3][256];
     unsigned short gamma[256];
+    unsigned short gam2[256];       // gamma[smap[v]]: brightness standardisation folded into the linearisation table (per tile)
     unsigned short cbrt[3072];
     int yf[512];
     unsigned char invg[4096];
@@ -49,19 +50,22 @@ struct __align__(16) LabShared {
 };
 
 __device__ __forceinline__ void lab_forward(const LabShared* sh, int r, int g, int b, int& L, int& A, int& Bc) {
-    const int R = sh->gamma[r], G = sh->gamma[g], Bl = sh->gamma[b];
+    // r, g, b are the RAW bytes: gam2 applies the tile's brightness standardisation and the sRGB linearisation at once
+    const int R = sh->gam2[r], G = sh->gam2[g], Bl = sh->gam2[b];
     const int fX = sh->cbrt[(R * 1777 + G * 1541 + Bl * 778 + 2048) >> 12];
     const int fY = sh->cbrt[(R * 871 + G * 2929 + Bl * 296 + 2048) >> 12];
     const int fZ = sh->cbrt[(R * 73 + G * 448 + Bl * 3575 + 2048) >> 12];
     L = (SB_LAB_LSCALE * fY + SB_LAB_LSHIFT + 16384) >> 15;
     A = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
     Bc = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
-    L = min(max(L, 0), 255); A = min(max(A, 0), 255); Bc = min(max(Bc, 0), 255);
+    // no saturation needed: over all 2^24 colours L is in [0,255], a in [42,226], b in [20,223] (tests/test_oracle_lab.py)
 }
 
 __device__ __forceinline__ int ab_to_xz(int t) {
-    // inverse companding in fixed point, C truncating division
-    return t <= 3390 ? (t * 108) / 841 - 290 : (((t * t) / 16384) * t) / 16384;
+    // inverse companding in fixed point, C truncating division.  t <= 20545, so the cubic branch stays below 2^31 and,
+    // being positive, divides by shifting; the linear branch (very dark colours, possibly negative t) is rare
+    if (t > 3390) return (int)((((unsigned)(t * t) >> 14) * (unsigned)t) >> 14);
+    return (t * 108) / 841 - 290;
 }
 
 __device__ __forceinline__ void lab_inverse(const LabShared* sh, int L, int A, int Bc, int& r, int& g, int& b) {
@@ -133,9 +137,15 @@ __global__ void __launch_bounds__(NT, 2) lab_tile_kernel(LabArgs a) {
             __syncthreads();
             if (threadIdx.x == 0) sh->p = hist_percentile(sh->hist[0], 3ull * (unsigned long long)npx, 90.0);
             __syncthreads();
-            if (threadIdx.x < 256) sh->smap[threadIdx.x] = trunc_clip_u8((double)threadIdx.x * 255.0 / sh->p);
+            if (threadIdx.x < 256) {
+                const unsigned char m = trunc_clip_u8((double)threadIdx.x * 255.0 / sh->p);
+                sh->smap[threadIdx.x] = m;
+                sh->gam2[threadIdx.x] = sh->gamma[m];
+                sh->hist[0][threadIdx.x] = 0;
+            }
             __syncthreads();
-            for (int i = threadIdx.x; i < 256; i += NT) sh->hist[0][i] = 0;
+        } else if (tile == (int)blockIdx.x) {
+            if (threadIdx.x < 256) sh->gam2[threadIdx.x] = sh->gamma[threadIdx.x];
             __syncthreads();
         }
         // ---- pass 2: LAB histograms of the (standardised) tile
@@ -143,7 +153,6 @@ __global__ void __launch_bounds__(NT, 2) lab_tile_kernel(LabArgs a) {
             uint32_t w[12]; int nvalid;
             load_group<true>(tin, npx, g, aligned, w, nvalid);
             for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
-                if (reinhard) { r = sh->smap[r]; gg = sh->smap[gg]; b = sh->smap[b]; }
                 int L, A, Bc;
                 lab_forward(sh, r, gg, b, L, A, Bc);
                 if (i < nvalid) {
@@ -201,7 +210,6 @@ __global__ void __launch_bounds__(NT, 2) lab_tile_kernel(LabArgs a) {
             load_group<false>(tin, npx, g, aligned, w, nvalid);
             uint32_t ob[48];
             for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
-                if (reinhard) { r = sh->smap[r]; gg = sh->smap[gg]; b = sh->smap[b]; }
                 int L, A, Bc;
                 lab_forward(sh, r, gg, b, L, A, Bc);
                 int L2, A2, B2;
