@@ -95,6 +95,28 @@ int sb_normalize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, i
                  const double* M_target, const double* maxC_target, double* M_src, double* maxC_src,
                  int32_t* status, void* stream);
 
+/* Slide-level fit: ExtractiveStainNormalizer.fit (normalizer.py:27-36) of a SET of tiles treated as ONE image (the
+ * target slide), possibly sharded over ranks.  Each pass produces statistics that ADD across launches and ranks; the
+ * caller all-reduces them and does the small serial steps (covariance + eigenvectors, rank selection in the
+ * histograms, stain matrix) on the host between passes -- stainlib_b200/normalization/slide_fit.py is that host side.
+ *   sb_slide_moments     masked OD moments: partials double [sb_slide_grid()][10] = (sum od[3], sum od x od[6] (00,01,02,
+ *                        11,12,22), n) per CTA; add the rows.
+ *   sb_slide_angle_hist  level 1: hist[4096] += counts of the top 12 bits of the 23-bit angle key of every tissue pixel,
+ *                        V (HOST double[6]) = the two leading eigenvectors (rows); level 2: hist[q*2048 + low 11 bits]
+ *                        += for keys whose level-1 bin is bins[q] (HOST unsigned[4]).
+ *   sb_slide_conc_hist   the same for the concentrations of ALL pixels under M (HOST double[6]): level 1 fills
+ *                        hist[0..4095] (stain 0) and hist[4096..8191] (stain 1); level 2 refines bins[0], bins[1] of
+ *                        stain 0 and bins[2], bins[3] of stain 1.
+ * hist: device unsigned long long [8192], accumulated (zero it before the first launch of a pass).  Keys map back to
+ * values as in csrc/sb_device.cuh (angle_from_key, conc_from_key). */
+int sb_slide_grid(sb_handle* h, int B, int H, int W);
+int sb_slide_moments(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold,
+                     double* partials, void* stream);
+int sb_slide_angle_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold,
+                        const double* V, int level, const unsigned* bins, unsigned long long* hist, void* stream);
+int sb_slide_conc_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, const double* M, double lasso_lambda,
+                       int level, const unsigned* bins, unsigned long long* hist, void* stream);
+
 /* Same as sb_normalize but rgb_in / rgb_out / status are HOST buffers (pinned for full speed): the call streams
  * tile chunks H2D -> kernels -> D2H on internal streams with double buffering and returns after the last byte has
  * landed in rgb_out (synchronous).  M_target / maxC_target are HOST doubles here. */

@@ -260,6 +260,66 @@ int sb_normalize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, i
                         (cudaStream_t)stream);
 }
 
+static int slide_args(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double thr, sb::SlideArgs& a) {
+    int rc = check_image_args(h, rgb, B, H, W);
+    if (rc) return rc;
+    a = sb::SlideArgs{};
+    a.in = rgb; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb, rgb, a.npx);
+    a.tab = h->tab; a.ybound = mask_ybound_f(thr);
+    for (int c = 0; c < 3; ++c) a.ycoef[c] = (float)SB_RGB2LAB_COEFFS[3 + c];
+    return SB_OK;
+}
+
+int sb_slide_grid(sb_handle* h, int B, int H, int W) {
+    if (!h || B <= 0 || H <= 0 || W <= 0) return SB_ERR_ARG;
+    sb::SlideArgs a{};
+    a.B = B; a.npx = H * W;
+    return sb::slide_grid(a, h->num_sms);
+}
+
+int sb_slide_moments(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold,
+                     double* partials, void* stream) {
+    sb::SlideArgs a;
+    int rc = slide_args(h, rgb, B, H, W, luminosity_threshold, a);
+    if (rc) return rc;
+    if (!partials) return SB_ERR_ARG;
+    a.sums = partials;
+    cudaError_t e = (cudaError_t)sb::launch_slide_pass(a, 0, sb::slide_grid(a, h->num_sms), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "slide moments launch");
+    h->launches += 1;
+    return SB_OK;
+}
+
+int sb_slide_angle_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold,
+                        const double* V, int level, const unsigned* bins, unsigned long long* hist, void* stream) {
+    sb::SlideArgs a;
+    int rc = slide_args(h, rgb, B, H, W, luminosity_threshold, a);
+    if (rc) return rc;
+    if (!V || !hist || (level != 1 && level != 2) || (level == 2 && !bins)) return SB_ERR_ARG;
+    for (int k = 0; k < 6; ++k) a.V[k] = (float)V[k];
+    for (int k = 0; k < 4; ++k) a.bins[k] = level == 2 ? bins[k] : 0u;
+    a.hist = hist;
+    cudaError_t e = (cudaError_t)sb::launch_slide_pass(a, level, sb::slide_grid(a, h->num_sms), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "slide angle histogram launch");
+    h->launches += 1;
+    return SB_OK;
+}
+
+int sb_slide_conc_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, const double* M, double lasso_lambda,
+                       int level, const unsigned* bins, unsigned long long* hist, void* stream) {
+    sb::SlideArgs a;
+    int rc = slide_args(h, rgb, B, H, W, 0.8, a);
+    if (rc) return rc;
+    if (!M || !hist || (level != 1 && level != 2) || (level == 2 && !bins)) return SB_ERR_ARG;
+    sb::make_lasso_consts(M, lasso_lambda, a.lk);
+    for (int k = 0; k < 4; ++k) a.bins[k] = level == 2 ? bins[k] : 0u;
+    a.hist = hist;
+    cudaError_t e = (cudaError_t)sb::launch_slide_pass(a, 2 + level, sb::slide_grid(a, h->num_sms), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "slide concentration histogram launch");
+    h->launches += 1;
+    return SB_OK;
+}
+
 int sb_normalize_host(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const sb_params* p,
                       const double* M_target, const double* maxC_target, int32_t* status, int chunk_tiles) {
     int rc = check_image_args(h, rgb_in, B, H, W);

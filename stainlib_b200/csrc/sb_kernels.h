@@ -46,6 +46,21 @@ struct PipeArgs {
 
 int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream);
 
+// ---- slide-level fit passes (sb_pipeline.cu): 0 moments, 1/2 angle histograms (level 1/2), 3/4 concentration histograms
+struct SlideArgs {
+    const uint8_t* in;
+    int B, npx, aligned;
+    Tables tab;
+    float ybound, ycoef[3];
+    float V[6];                 // projection plane (passes 1, 2): rows = the two leading eigenvectors
+    LassoK lk;                  // passes 3, 4
+    unsigned bins[4];           // level-1 bins refined by passes 2 and 4
+    double* sums;               // pass 0: [grid][10] per-CTA partials (n last)
+    unsigned long long* hist;   // passes 1-4: [8192] counters, accumulated (+=)
+};
+int slide_grid(const SlideArgs& a, int num_sms);
+int launch_slide_pass(const SlideArgs& a, int pass, int grid, cudaStream_t stream);
+
 // ---- pointwise kernels (sb_pointwise.cu)
 struct PointArgs {
     const uint8_t* in;

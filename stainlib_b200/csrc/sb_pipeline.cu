@@ -1118,4 +1118,151 @@ int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream) {
                                          : launch_tile_pipeline_t<SB_METHOD_VAHADANE>(a, num_sms, stream);
 }
 
+// ------------------------------------------------------------------------------------------ slide-level (multi-tile) fit
+// ExtractiveStainNormalizer.fit (normalizer.py:27-36) of a SET of tiles treated as one image (a whole slide, possibly
+// sharded over ranks): the statistics of the tile chain above are produced as batch-wide sums that add across CTAs,
+// launches and ranks -- moments, then two-level key histograms for the exact order statistics -- and the small serial
+// steps (covariance, eigenvectors, rank selection, stain matrix) run on the host between the passes
+// (stainlib_b200/normalization/slide_fit.py).  Five streaming passes over the target tiles; fit is once per slide.
+constexpr int SLIDE_NT = 256;
+constexpr int SLIDE_CHUNK_GROUPS = 4096;      // work item = 65,536 pixels of one tile
+
+template <int PASS>
+__global__ void __launch_bounds__(SLIDE_NT, 2) slide_pass_kernel(SlideArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* od_rep = smem_raw;
+    unsigned* hist = reinterpret_cast<unsigned*>(smem_raw + OD_REP_BYTES);          // 8192 counters
+    __shared__ double red[SLIDE_NT / 32][10];
+    const uint32_t lane_off = (threadIdx.x & 31) << 3;
+    const YCoef yc{a.ycoef[0], a.ycoef[1], a.ycoef[2], a.ybound};
+    for (int i = threadIdx.x; i < 256 * 32; i += SLIDE_NT)
+        *reinterpret_cast<float2*>(od_rep + (i >> 5) * OD_ROW_BYTES + (i & 31) * 8) = make_float2(a.tab.od[i >> 5], (float)a.tab.gamma[i >> 5]);
+    for (int i = threadIdx.x; i < 2 * L1_BINS; i += SLIDE_NT) hist[i] = 0;
+    __syncthreads();
+    const int npx = a.npx;
+    const int G = (npx + GROUP_PX - 1) / GROUP_PX;
+    const int cpt = (G + SLIDE_CHUNK_GROUPS - 1) / SLIDE_CHUNK_GROUPS;
+    const long long total = (long long)cpt * a.B;
+    const float v00 = a.V[0], v01 = a.V[1], v02 = a.V[2], v10 = a.V[3], v11 = a.V[4], v12 = a.V[5];
+    const LassoK lk = a.lk;
+    const unsigned b0 = a.bins[0], b1 = a.bins[1], b2 = a.bins[2], b3 = a.bins[3];
+    double acc[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+    unsigned long long cnt = 0;
+    for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+        const int tile = (int)(item / cpt);
+        const int g0 = (int)(item % cpt) * SLIDE_CHUNK_GROUPS;
+        const int g1 = min(g0 + SLIDE_CHUNK_GROUPS, G);
+        const uint8_t* __restrict__ tin = a.in + (size_t)tile * npx * 3;
+        for (int g = g0 + threadIdx.x; g < g1; g += SLIDE_NT) {
+            uint32_t w[12];
+            int nvalid;
+            load_group<false>(tin, npx, g, a.aligned != 0, w, nvalid);
+            if (PASS == 0) {
+                float f[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) f[i] = 0.f;
+                unsigned c = 0;
+                for_each_px_odg(od_rep, lane_off, w, [&](int i, float2 r, float2 gg, float2 b) {
+                    float y = tissue_y(yc, r.y, gg.y, b.y);
+                    if (i >= nvalid) y = yc.bound;
+                    accum_if_tissue(y, yc.bound, r.x, gg.x, b.x, f, c);
+                });
+                cnt += c;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
+            } else if (PASS == 1 || PASS == 2) {
+                for_each_px_odg(od_rep, lane_off, w, [&](int i, float2 r, float2 gg, float2 b) {
+                    const float px = fmaf(b.x, v02, fmaf(gg.x, v01, r.x * v00));
+                    const float py = fmaf(b.x, v12, fmaf(gg.x, v11, r.x * v10));
+                    if (i < nvalid && tissue_y(yc, r.y, gg.y, b.y) < yc.bound) {
+                        const uint32_t key = angle_key(px, py);
+                        const uint32_t bin = key >> L2_BITS, low = key & (L2_BINS - 1);
+                        if (PASS == 1) atomicAdd(&hist[bin], 1u);
+                        else {
+                            if (bin == b0) atomicAdd(&hist[low], 1u);
+                            if (bin == b1) atomicAdd(&hist[L2_BINS + low], 1u);
+                            if (bin == b2) atomicAdd(&hist[2 * L2_BINS + low], 1u);
+                            if (bin == b3) atomicAdd(&hist[3 * L2_BINS + low], 1u);
+                        }
+                    }
+                });
+            } else {
+                for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
+                    float c0, c1;
+                    lasso2(lk, o0, o1, o2, c0, c1);
+                    if (i < nvalid) {
+                        const uint32_t k0 = conc_key(c0), k1 = conc_key(c1);
+                        if (PASS == 3) { atomicAdd(&hist[k0 >> L2_BITS], 1u); atomicAdd(&hist[L1_BINS + (k1 >> L2_BITS)], 1u); }
+                        else {
+                            if ((k0 >> L2_BITS) == b0) atomicAdd(&hist[k0 & (L2_BINS - 1)], 1u);
+                            if ((k0 >> L2_BITS) == b1) atomicAdd(&hist[L2_BINS + (k0 & (L2_BINS - 1))], 1u);
+                            if ((k1 >> L2_BITS) == b2) atomicAdd(&hist[2 * L2_BINS + (k1 & (L2_BINS - 1))], 1u);
+                            if ((k1 >> L2_BITS) == b3) atomicAdd(&hist[3 * L2_BINS + (k1 & (L2_BINS - 1))], 1u);
+                        }
+                    }
+                });
+            }
+        }
+        if (PASS != 0) {
+            // shared counters are 32-bit: a CTA flushes after every work item (65,536 pixels)
+            __syncthreads();
+            for (int i = threadIdx.x; i < 2 * L1_BINS; i += SLIDE_NT) {
+                const unsigned v = hist[i];
+                if (v) { atomicAdd(&a.hist[i], (unsigned long long)v); hist[i] = 0; }
+            }
+            __syncthreads();
+        }
+    }
+    if (PASS == 0) {
+        // per-CTA partial sums, added on the host in CTA order (fixed order for a fixed grid)
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc[i] = warp_sum(acc[i]);
+        const double c = warp_sum((double)cnt);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) red[warp][i] = acc[i];
+            red[warp][9] = c;
+        }
+        __syncthreads();
+        if (threadIdx.x < 10) {
+            double t = 0.0;
+            for (int wv = 0; wv < SLIDE_NT / 32; ++wv) t += red[wv][threadIdx.x];
+            a.sums[(size_t)blockIdx.x * 10 + threadIdx.x] = t;
+        }
+    }
+}
+
+int slide_grid(const SlideArgs& a, int num_sms) {
+    const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
+    const long long total = (long long)((G + SLIDE_CHUNK_GROUPS - 1) / SLIDE_CHUNK_GROUPS) * a.B;
+    const long long cap = (long long)num_sms * 2;
+    return (int)(total < cap ? total : cap);
+}
+
+template <int PASS>
+static int launch_slide_pass_t(const SlideArgs& a, int grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    const size_t smem = OD_REP_BYTES + 2 * L1_BINS * sizeof(unsigned);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(slide_pass_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    slide_pass_kernel<PASS><<<grid, SLIDE_NT, smem, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int launch_slide_pass(const SlideArgs& a, int pass, int grid, cudaStream_t stream) {
+    switch (pass) {
+        case 0: return launch_slide_pass_t<0>(a, grid, stream);
+        case 1: return launch_slide_pass_t<1>(a, grid, stream);
+        case 2: return launch_slide_pass_t<2>(a, grid, stream);
+        case 3: return launch_slide_pass_t<3>(a, grid, stream);
+        default: return launch_slide_pass_t<4>(a, grid, stream);
+    }
+}
+
 }  // namespace sb

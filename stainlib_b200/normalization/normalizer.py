@@ -63,11 +63,33 @@ class ExtractiveStainNormalizer(object):
         self._target = target
         return torch.cat([M.reshape(6), maxC.reshape(2)]).cpu()
 
-    def fit(self, target, src=0, group=None):
+    def fit(self, target, src=0, group=None, slide=None):
         """Fit to a target image (normalizer.py:27-36): stain matrix of the target and the 99th percentile of its
-        concentrations, one fused kernel.  Under torch.distributed only rank ``src`` needs a real target."""
+        concentrations, one fused kernel.  Under torch.distributed only rank ``src`` needs a real target.
+
+        Slide-level fit (``slide=True``, or a batch of more than one tile): ``target`` is this rank's share
+        ``uint8 [T,H,W,3]`` of the tiles of ONE target slide (``None`` / ``T = 0`` allowed on a rank); the result is what
+        the reference would compute on the concatenation of all ranks' tiles -- see normalization/slide_fit.py.  Every
+        rank of ``group`` must make the call with ``slide=True``; ``src`` is ignored."""
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized()
+        if slide is None:
+            slide = (isinstance(target, (torch.Tensor, np.ndarray)) and target.ndim == 4 and target.shape[0] != 1)
+        if slide:
+            if self._method != nv.SB_METHOD_MACENKO:
+                raise NotImplementedError("slide-level fit is implemented for method='macenko'")
+            from stainlib_b200.normalization.slide_fit import macenko_slide_fit
+            tiles = None
+            if isinstance(target, np.ndarray):
+                target = torch.from_numpy(np.ascontiguousarray(target))
+            if target is not None and target.shape[0] > 0:
+                assert target.dim() == 4 and is_uint8_image(target), "Image should be RGB uint8."
+                tiles = nv.Batch(target).dev
+            p = self._params()
+            self.stain_matrix_target, self.maxC_target = macenko_slide_fit(
+                tiles, p.luminosity_threshold, p.angular_percentile, p.lasso_lambda, p.conc_percentile, group=group)
+            self._target = None
+            return
         vec = torch.zeros(8, dtype=torch.float64)
         if not distributed or dist.get_rank(group) == src:
             vec = self._fit_local(target)
