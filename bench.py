@@ -37,7 +37,7 @@ WORKLOADS = {
     "macenko512": ("macenko", 1024, 512, 512, "config[1]: 1024 synthetic 512x512 H&E tiles, Macenko normalize"),
     "macenko256": ("macenko", 4096, 256, 256, "4096 synthetic 256x256 tiles, Macenko normalize (config[4] tile size)"),
     "macenko1024": ("macenko", 256, 1024, 1024, "256 synthetic 1024x1024 tiles, Macenko normalize"),
-    "vahadane1024": ("vahadane", 256, 1024, 1024, "config[2] tile size: 1024x1024 tiles, Vahadane sparse-NMF normalize (256 per GPU; --tiles 4096 = the full config)"),
+    "vahadane1024": ("vahadane", 1024, 1024, 1024, "config[2] tile size: 1024x1024 tiles, Vahadane sparse-NMF normalize (1024 per GPU; --tiles 4096 = the full config)"),
     "vahadane512": ("vahadane", 1024, 512, 512, "1024 synthetic 512x512 tiles, Vahadane sparse-NMF normalize"),
     # config[4]: 100k 256x256 tiles in total, split over the ranks (strong scaling)
     "stream256": ("macenko", 100000, 256, 256, "config[4]: WSI-scale stream, 100000 synthetic 256x256 tiles in total, Macenko normalize"),

@@ -80,9 +80,17 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
     a.dl_sample_iters = p->dl_sample_iters < 0 ? 0 : p->dl_sample_iters;
     a.dl_anderson = p->dl_anderson < 0 ? 0 : (p->dl_anderson > sb::AA_MAX ? sb::AA_MAX : p->dl_anderson);
     a.Mt = Mt; a.maxCt = maxCt;
+    // Vahadane re-reads the tissue mask in every dictionary pass; tiles whose per-CTA share exceeds the shared-memory
+    // cache (262,144 pixels) keep it in a stream-ordered global scratch instead of recomputing it
+    unsigned short* mask_scratch = nullptr;
+    const int groups = (a.npx + sb::GROUP_PX - 1) / sb::GROUP_PX;
+    if (p->method == SB_METHOD_VAHADANE && groups / a.cluster_size > 16384)
+        SB_CUDA(cudaMallocAsync(&mask_scratch, (size_t)B * groups * sizeof(unsigned short), stream));
+    a.mask_scratch = mask_scratch;
     if (mode != sb::PIPE_NORMALIZE) {
         a.mode = mode; a.M_out = M; a.maxC_out = maxC; a.status = status;
         cudaError_t e = (cudaError_t)sb::launch_tile_pipeline(a, h->num_sms, stream);
+        if (mask_scratch) cudaFreeAsync(mask_scratch, stream);
         if (e != cudaSuccess) return cuda_fail(e, "tile_pipeline launch");
         h->launches += 1;
         return SB_OK;
@@ -98,6 +106,7 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
     int32_t* Sw = status ? status : reinterpret_cast<int32_t*>(ws + (size_t)B * 8);
     a.mode = sb::PIPE_FIT; a.M_out = Mw; a.maxC_out = Cw; a.status = Sw;
     cudaError_t e = (cudaError_t)sb::launch_tile_pipeline(a, h->num_sms, stream);
+    if (mask_scratch) cudaFreeAsync(mask_scratch, stream);
     if (e != cudaSuccess) return cuda_fail(e, "tile_pipeline launch");
     sb::PointArgs k{};
     k.in = in; k.out = out; k.B = B; k.npx = a.npx; k.aligned = a.aligned; k.tab = h->tab; k.lasso_lambda = p->lasso_lambda;

@@ -42,6 +42,7 @@ struct PipeArgs {
     double* M_out;        // [B,2,3] or null
     double* maxC_out;     // [B,2] or null
     int32_t* status;      // [B] or null
+    unsigned short* mask_scratch;   // Vahadane, tiles too big for the shared-memory mask cache: [B][groups] or null
 };
 
 int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream);

@@ -473,7 +473,10 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
     const bool aligned = a.aligned != 0;
     const uint32_t lane_off = (threadIdx.x & 31) << 3;      // {od, gamma} pairs: 8 bytes per lane
     const YCoef yc{a.ycoef[0], a.ycoef[1], a.ycoef[2], a.ybound};
-    const bool cache_mask = (ge - gb) <= MASK_CAP_GROUPS;   // Vahadane only; else the mask is recomputed in every iteration
+    // Vahadane keeps the tissue mask of its tile for all dictionary passes: 16 bits per group in the idle histogram
+    // buffer when the CTA's share fits (262,144 pixels), else in a global scratch row (L2-resident, one 2-byte load per group)
+    const bool cache_smem = (ge - gb) <= MASK_CAP_GROUPS;
+    const bool cache_mask = cache_smem || a.mask_scratch != nullptr;
 
     fill_odg_rep(od_rep, a.tab.od, a.tab.gamma, NT);
     __syncthreads();
@@ -754,7 +757,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     const uint32_t mbits = mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
                     cnt_tissue += __popc(mbits);
                     if (is_sample_group(g, nfull)) cnt_sample += __popc(mbits);
-                    if (cache_mask) *mask_slot(sh->hist, g - gb) = (unsigned short)mbits;
+                    if (cache_mask) *(cache_smem ? mask_slot(sh->hist, g - gb) : a.mask_scratch + (size_t)tile * G + g) = (unsigned short)mbits;
                 });
                 double acc[9];
 #pragma unroll
@@ -791,7 +794,8 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
 #pragma unroll
                     for (int i = 0; i < 9; ++i) f[i] = make_float2(0.f, 0.f);
                     auto accumulate_general = [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                        const uint32_t mbits = cache_mask ? *mask_slot(sh->hist, g - gb) : mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
+                        const uint32_t mbits = cache_mask ? *(cache_smem ? mask_slot(sh->hist, g - gb) : a.mask_scratch + (size_t)tile * G + g)
+                                                          : mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
                         for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
                             float c0, c1;
                             lasso2(lk, o0, o1, o2, c0, c1);
@@ -805,7 +809,8 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     auto accumulate_unit = [&](auto unit) {
                         return [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
                             constexpr int LM = decltype(unit)::value;
-                            const uint32_t mbits = cache_mask ? *mask_slot(sh->hist, g - gb) : mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
+                            const uint32_t mbits = cache_mask ? *(cache_smem ? mask_slot(sh->hist, g - gb) : a.mask_scratch + (size_t)tile * G + g)
+                                                              : mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
                             for_each_pair_od(od_rep, lane_off, w, [&](int i, float2 o0, float2 o1, float2 o2) {
                                 float2 c0, c1;
                                 lasso2_unit_pair<LM>(lk, o0, o1, o2, c0, c1);

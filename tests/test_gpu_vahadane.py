@@ -64,7 +64,7 @@ def test_vahadane_batch_and_clusters(sb):
     assert mx <= 1 and frac >= 0.99, (mx, frac)
 
 
-@pytest.mark.parametrize("size,seed", [(256, 0), (256, 7), (512, 3), (128, 5), ((200, 333), 11)])
+@pytest.mark.parametrize("size,seed", [(256, 0), (256, 7), (512, 3), (128, 5), ((200, 333), 11), (1024, 2)])
 def test_vahadane_accelerated_vs_oracle(sb, size, seed):
     """Default schedule (sample passes, then full passes to a residual of 2e-6, Anderson memory 4) against the CPU restatement of the same
     schedule, and against the converged plain iteration (the fixed point both approximate)."""
