@@ -148,18 +148,29 @@ __global__ void __launch_bounds__(NT, 2) lab_tile_kernel(LabArgs a) {
             if (threadIdx.x < 256) sh->gam2[threadIdx.x] = sh->gamma[threadIdx.x];
             __syncthreads();
         }
-        // ---- pass 2: LAB histograms of the (standardised) tile
+        // ---- pass 2: LAB histograms of the (standardised) tile.  When a result tile will be written, its memory serves as
+        // scratch for the LAB bytes, so that pass 3 does not repeat the forward conversion (the costliest step per pixel)
+        uint8_t* __restrict__ tout = a.out ? a.out + (size_t)tile * npx * 3 : nullptr;
+        const bool keep_lab = tout != nullptr && a.mode != REINHARD_STATS;
         for (int g = threadIdx.x; g < G; g += NT) {
             uint32_t w[12]; int nvalid;
             load_group<true>(tin, npx, g, aligned, w, nvalid);
+            uint32_t lab[48];
             for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
                 int L, A, Bc;
                 lab_forward(sh, r, gg, b, L, A, Bc);
+                lab[3 * i] = L; lab[3 * i + 1] = A; lab[3 * i + 2] = Bc;
                 if (i < nvalid) {
                     atomicAdd(&sh->hist[0][L], 1u);
                     if (reinhard) { atomicAdd(&sh->hist[1][A], 1u); atomicAdd(&sh->hist[2][Bc], 1u); }
                 }
             });
+            if (keep_lab) {
+                uint32_t o[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) o[k] = lab[4 * k] | (lab[4 * k + 1] << 8) | (lab[4 * k + 2] << 16) | (lab[4 * k + 3] << 24);
+                store_group_keep(tout, npx, g, aligned, o);
+            }
         }
         __syncthreads();
         if (reinhard) {
@@ -200,18 +211,16 @@ __global__ void __launch_bounds__(NT, 2) lab_tile_kernel(LabArgs a) {
             if (threadIdx.x < 256) sh->cmap[0][threadIdx.x] = trunc_clip_u8(255.0 * (double)threadIdx.x / sh->p);
         }
         __syncthreads();
-        // ---- pass 3: map and convert back
-        uint8_t* __restrict__ tout = a.out + (size_t)tile * npx * 3;
+        // ---- pass 3: map and convert back; reads the LAB bytes this thread stored in pass 2 and overwrites them with RGB
         const bool use_mask = reinhard && a.mask_background;
         const int lmax = a.lmax;
         int seen = 0;
         for (int g = threadIdx.x; g < G; g += NT) {
             uint32_t w[12], o[12]; int nvalid;
-            load_group<false>(tin, npx, g, aligned, w, nvalid);
+            load_group_rw(tout, npx, g, aligned, w, nvalid);
             uint32_t ob[48];
-            for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
-                int L, A, Bc;
-                lab_forward(sh, r, gg, b, L, A, Bc);
+            for_each_px(w, [&](int i, uint32_t Lu, uint32_t Au, uint32_t Bu) {
+                const int L = (int)Lu, A = (int)Au, Bc = (int)Bu;
                 int L2, A2, B2;
                 if (reinhard) {
                     const bool tissue = !use_mask || L <= lmax;

@@ -90,6 +90,53 @@ __device__ __forceinline__ void store_group(uint8_t* __restrict__ tile, int npx,
     }
 }
 
+// Loads a group from memory THIS kernel has written (coherent ld.global, never the read-only .nc path).
+__device__ __forceinline__ void load_group_rw(const uint8_t* tile, int npx, int g, bool aligned, uint32_t (&w)[12], int& nvalid) {
+    const int p0 = g * GROUP_PX;
+    nvalid = min(GROUP_PX, npx - p0);
+    const uint8_t* src = tile + (size_t)p0 * 3;
+    if (aligned && nvalid == GROUP_PX) {
+        uint4 a, b, c;
+        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(src));
+        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(src + 16));
+        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(src + 32));
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+    } else {
+        const int nbytes = nvalid * 3;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = i * 4 + j;
+                uint32_t byte = 255u;
+                if (k < nbytes) asm volatile("ld.global.u8 %0, [%1];" : "=r"(byte) : "l"(src + k));
+                x |= byte << (8 * j);
+            }
+            w[i] = x;
+        }
+    }
+}
+
+// Same with default caching (the data is read back soon: keep it in L2).
+__device__ __forceinline__ void store_group_keep(uint8_t* __restrict__ tile, int npx, int g, bool aligned, const uint32_t (&w)[12]) {
+    const int p0 = g * GROUP_PX;
+    const int nvalid = min(GROUP_PX, npx - p0);
+    uint8_t* dst = tile + (size_t)p0 * 3;
+    if (aligned && nvalid == GROUP_PX) {
+        uint4* v = reinterpret_cast<uint4*>(dst);
+        v[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        v[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        v[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    } else {
+        const int nbytes = nvalid * 3;
+#pragma unroll
+        for (int k = 0; k < 48; ++k)
+            if (k < nbytes) dst[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    }
+}
+
 // Calls f(pixel_index_in_group, r, g, b) for the 16 pixels of a group.
 template <class F>
 __device__ __forceinline__ void for_each_px(const uint32_t (&w)[12], F&& f) {
