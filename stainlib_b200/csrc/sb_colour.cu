@@ -9,7 +9,8 @@
 //     evaluated ONCE per tile in fp64 into 256-entry tables (brightness standardisation, the three Reinhard affine
 //     maps, the luminosity rescale) -- the per-pixel work is table lookups and integer multiply-adds, bit-exact.
 //     Percentiles of uint8-valued data come from exact 256-bin histograms.
-//   hed_kernel        HedColorAugmenter.transform  augmenter.py:276-331  (skimage 0.17 colour deconvolution collapsed
+//   hed_kernel        HedColorAugmenter.transform  augmenter.py:276-331  (single pass: speculative transform + patch-mean gate
+//                     by the last CTA of each tile; skimage 0.17 colour deconvolution collapsed
 //                     to  rgb' = b^(log_b(rgb/255+2) . A - c) - 2  with a per-tile 3x3 A and 3-vector c)
 //   gray_kernel       GrayscaleAugmentor.pop       augmenter.py:390-401
 #include "sb_kernels.h"
@@ -258,43 +259,26 @@ struct HedArgs {
     const double* bias;    // [B,3]
     double cutoff_lo, cutoff_hi, log_base;
     int32_t* status;       // 1 = tile outside the cutoff (copied through)
-    unsigned long long* sums;   // [B] workspace: sum of all channel bytes
+    unsigned long long* sums;   // [B] workspace (zeroed): sum of all channel bytes
+    unsigned* done;             // [B] workspace (zeroed): CTAs of the tile that have finished
 };
 
-__global__ void __launch_bounds__(256) byte_sum_kernel(const uint8_t* in, int npx, int aligned, unsigned long long* sums) {
-    const int tile = blockIdx.x;
-    const uint8_t* tin = in + (size_t)tile * npx * 3;
-    const int G = (npx + GROUP_PX - 1) / GROUP_PX;
-    unsigned s = 0;
-    unsigned long long acc = 0;
-    for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < G; g += gridDim.y * blockDim.x) {
-        uint32_t w[12]; int nvalid;
-        load_group<true>(in + (size_t)tile * npx * 3, npx, g, aligned != 0, w, nvalid);
-        (void)tin;
-        if (nvalid == GROUP_PX) {
-#pragma unroll
-            for (int k = 0; k < 12; ++k) s += __vsadu4(w[k], 0u);      // sum of the four bytes
-        } else {
-            for (int k = 0; k < nvalid * 3; ++k) s += (w[k >> 2] >> (8 * (k & 3))) & 255u;
-        }
-        acc += s; s = 0;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&sums[tile], acc);
-}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) { float d; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 
-__global__ void __launch_bounds__(256, 4) hed_kernel(HedArgs a) {
-    __shared__ float l2[256];        // log2(v/255 + 2)
+__global__ void __launch_bounds__(256, 3) hed_kernel(HedArgs a) {
+    // log2(v/255 + 2), replicated per lane with 256-byte rows like the OD table of K4: one PRMT builds the offset from
+    // the packed pixel word, the lookup is bank-conflict free
+    extern __shared__ __align__(256) unsigned char l2_rep[];
+    __shared__ float l2[256];
     __shared__ float A[9], c[3];
     __shared__ int skip;
+    __shared__ unsigned long long wsum[8];
     const int tile = blockIdx.x;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) l2[i] = (float)log2((double)i / 255.0 + 2.0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x)
+        *reinterpret_cast<float*>(l2_rep + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = l2[i >> 5];
     if (threadIdx.x == 0) {
-        // patch mean in [0,1] (augmenter.py:288-293); exact integer sum instead of numpy's float32 pairwise mean
-        const double mean = (double)a.sums[tile] / (3.0 * (double)a.npx) / 255.0;
-        skip = !(a.cutoff_lo <= mean && mean <= a.cutoff_hi);
-        if (a.status) a.status[tile] = skip;
         // A = inv(M) diag(1+sigma) M, c = bias M  (M = rgb_from_hed), exponent scaled to base 2
         const double M[9] = {0.65, 0.70, 0.29, 0.07, 0.99, 0.11, 0.27, 0.57, 0.78};
         const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
@@ -321,35 +305,83 @@ __global__ void __launch_bounds__(256, 4) hed_kernel(HedArgs a) {
     const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
     const float a00 = A[0], a01 = A[1], a02 = A[2], a10 = A[3], a11 = A[4], a12 = A[5], a20 = A[6], a21 = A[7], a22 = A[8];
     const float c0 = -c[0], c1 = -c[1], c2 = -c[2];
-    const bool copy = skip != 0;
+    const uint32_t lane_off = (threadIdx.x & 31) << 2;
+    // The patch-mean gate (augmenter.py:288-293) needs the sum of ALL bytes of the tile -- a global dependency that would
+    // cost a separate read pass.  Tiles outside the cutoff are rare, so every CTA transforms its share speculatively while
+    // it sums its bytes; the last CTA of a tile to finish evaluates the gate and, if the tile is to be left unchanged,
+    // copies the input over the speculative output.
+    unsigned long long acc = 0;
     for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < G; g += gridDim.y * blockDim.x) {
         uint32_t w[12], o[12]; int nvalid;
         load_group<false>(tin, a.npx, g, a.aligned != 0, w, nvalid);
-        if (!copy) {
+        {
+            unsigned sg = 0;
+            if (nvalid == GROUP_PX) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) sg += __vsadu4(w[k], 0u);      // sum of the four bytes
+            } else {
+                for (int k = 0; k < nvalid * 3; ++k) sg += (w[k >> 2] >> (8 * (k & 3))) & 255u;
+            }
+            acc += sg;
+        }
+        {
+            // two pixels at a time on the packed f32x2 pipe; clip(b^e - 2, [0,1]) * 255 truncated (hed2rgb clip, then
+            // augmenter.py:320-325) = one saturating FMA and one round-down FMA onto 2^23 per value
+            auto px_pair = [&](float2 lr, float2 lg, float2 lb, uint32_t (&bits)[6]) {
+                const float2 e0 = __ffma2_rn(lb, dup(a20), __ffma2_rn(lg, dup(a10), __ffma2_rn(lr, dup(a00), dup(c0))));
+                const float2 e1 = __ffma2_rn(lb, dup(a21), __ffma2_rn(lg, dup(a11), __ffma2_rn(lr, dup(a01), dup(c1))));
+                const float2 e2 = __ffma2_rn(lb, dup(a22), __ffma2_rn(lg, dup(a12), __ffma2_rn(lr, dup(a02), dup(c2))));
+                bits[0] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e0.x), 1.f, -2.f), 255.f, 8388608.f));
+                bits[1] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e1.x), 1.f, -2.f), 255.f, 8388608.f));
+                bits[2] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e2.x), 1.f, -2.f), 255.f, 8388608.f));
+                bits[3] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e0.y), 1.f, -2.f), 255.f, 8388608.f));
+                bits[4] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e1.y), 1.f, -2.f), 255.f, 8388608.f));
+                bits[5] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e2.y), 1.f, -2.f), 255.f, 8388608.f));
+            };
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
-                const uint32_t rr[4] = {byte_of(wa, 0), byte_of(wa, 3), byte_of(wb, 2), byte_of(wc, 1)};
-                const uint32_t gg[4] = {byte_of(wa, 1), byte_of(wb, 0), byte_of(wb, 3), byte_of(wc, 2)};
-                const uint32_t bb[4] = {byte_of(wa, 2), byte_of(wb, 1), byte_of(wc, 0), byte_of(wc, 3)};
-                uint32_t bits[12];
-#pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const float lr = l2[rr[p]], lg = l2[gg[p]], lb = l2[bb[p]];
-                    const float e0 = fmaf(lb, a20, fmaf(lg, a10, fmaf(lr, a00, c0)));
-                    const float e1 = fmaf(lb, a21, fmaf(lg, a11, fmaf(lr, a01, c1)));
-                    const float e2 = fmaf(lb, a22, fmaf(lg, a12, fmaf(lr, a02, c2)));
-                    // clip(b^e - 2, [0,1]) * 255, truncated (hed2rgb clip to [-1,1], then augmenter.py:320-325)
-                    bits[3 * p] = clip_u8_bits(fmaxf(fmaf(ex2_approx(e0), 255.f, -510.f), 0.f));
-                    bits[3 * p + 1] = clip_u8_bits(fmaxf(fmaf(ex2_approx(e1), 255.f, -510.f), 0.f));
-                    bits[3 * p + 2] = clip_u8_bits(fmaxf(fmaf(ex2_approx(e2), 255.f, -510.f), 0.f));
-                }
-                o[3 * q] = pack4(bits[0], bits[1], bits[2], bits[3]);
-                o[3 * q + 1] = pack4(bits[4], bits[5], bits[6], bits[7]);
-                o[3 * q + 2] = pack4(bits[8], bits[9], bits[10], bits[11]);
+                // pixels: p0=(a0,a1,a2) p1=(a3,b0,b1) p2=(b2,b3,c0) p3=(c1,c2,c3)
+                uint32_t b01[6], b23[6];
+                px_pair(f2(od_lookup(l2_rep, wa, lane_off, 0), od_lookup(l2_rep, wa, lane_off, 3)),
+                        f2(od_lookup(l2_rep, wa, lane_off, 1), od_lookup(l2_rep, wb, lane_off, 0)),
+                        f2(od_lookup(l2_rep, wa, lane_off, 2), od_lookup(l2_rep, wb, lane_off, 1)), b01);
+                px_pair(f2(od_lookup(l2_rep, wb, lane_off, 2), od_lookup(l2_rep, wc, lane_off, 1)),
+                        f2(od_lookup(l2_rep, wb, lane_off, 3), od_lookup(l2_rep, wc, lane_off, 2)),
+                        f2(od_lookup(l2_rep, wc, lane_off, 0), od_lookup(l2_rep, wc, lane_off, 3)), b23);
+                o[3 * q] = pack4(b01[0], b01[1], b01[2], b01[3]);
+                o[3 * q + 1] = pack4(b01[4], b01[5], b23[0], b23[1]);
+                o[3 * q + 2] = pack4(b23[2], b23[3], b23[4], b23[5]);
             }
             store_group(tout, a.npx, g, a.aligned != 0, o);
-        } else {
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();                                   // also orders this CTA's output stores before the ticket below
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) t += wsum[wv];
+        atomicAdd(&a.sums[tile], t);
+        __threadfence();
+        const unsigned ticket = atomicAdd(&a.done[tile], 1u);
+        int sk = 0;
+        if (ticket == gridDim.y - 1) {
+            __threadfence();
+            const unsigned long long total = atomicAdd(&a.sums[tile], 0ull);
+            // patch mean in [0,1]; exact integer sum instead of numpy's float32 pairwise mean
+            const double mean = (double)total / (3.0 * (double)a.npx) / 255.0;
+            sk = !(a.cutoff_lo <= mean && mean <= a.cutoff_hi);
+            if (a.status) a.status[tile] = sk;
+        }
+        skip = sk;
+    }
+    __syncthreads();
+    if (skip) {                                        // rare: the whole tile is returned unchanged
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            uint32_t w[12]; int nvalid;
+            load_group<false>(tin, a.npx, g, a.aligned != 0, w, nvalid);
             store_group(tout, a.npx, g, a.aligned != 0, w);
         }
     }
@@ -465,20 +497,25 @@ int sb_hed_augment(sb_handle* hh, const uint8_t* rgb_in, uint8_t* rgb_out, int B
     if (bad_img(hh, rgb_in, B, H, W) || !rgb_out || !sigma || !bias) return SB_ERR_ARG;
     sb_handle* h = hh;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long* sums = nullptr;
-    if (cudaMallocAsync(&sums, (size_t)B * 8, st) != cudaSuccess) return SB_ERR_CUDA;
-    if (cudaMemsetAsync(sums, 0, (size_t)B * 8, st) != cudaSuccess) return SB_ERR_CUDA;
+    unsigned long long* sums = nullptr;                 // [B] byte sums followed by [B] finished-CTA counters
+    if (cudaMallocAsync(&sums, (size_t)B * 12, st) != cudaSuccess) return SB_ERR_CUDA;
+    if (cudaMemsetAsync(sums, 0, (size_t)B * 12, st) != cudaSuccess) return SB_ERR_CUDA;
     const int npx = H * W, al = aligned16(rgb_in, rgb_out, npx);
     const dim3 grid = tile_grid(B, npx, h->num_sms);
-    sb::byte_sum_kernel<<<grid, 256, 0, st>>>(rgb_in, npx, al, sums);
     sb::HedArgs a{};
     a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = npx; a.aligned = al; a.sigma = sigma; a.bias = bias;
     a.cutoff_lo = cutoff_lo; a.cutoff_hi = cutoff_hi; a.log_base = log_base; a.status = status; a.sums = sums;
-    sb::hed_kernel<<<grid, 256, 0, st>>>(a);
+    a.done = reinterpret_cast<unsigned*>(sums + B);
+    static bool hed_attr = false;
+    if (!hed_attr) {
+        if (cudaFuncSetAttribute(sb::hed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sb::OD_REP_BYTES) != cudaSuccess) return SB_ERR_CUDA;
+        hed_attr = true;
+    }
+    sb::hed_kernel<<<grid, 256, sb::OD_REP_BYTES, st>>>(a);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(sums, st);
     if (e != cudaSuccess) return SB_ERR_CUDA;
-    h->launches += 2;
+    h->launches += 1;
     return SB_OK;
 }
 

@@ -97,6 +97,16 @@ def test_hed_cutoff_and_batch(sb, golden):
         mx, frac = lsb_stats(out[i], ref)
         assert mx <= 1 and frac >= 0.999, (i, mx, frac)
     assert h.last_status.cpu().tolist() == [0, 0, 0, 1]
+    # large tiles split over many CTAs: the last CTA of a tile decides the gate and restores the input of a skipped tile
+    big = synth_batch(60, 3, 512, 512)
+    big[1] = 255
+    big[2] = (big[2].astype(np.float32) * 0.04).astype(np.uint8)          # mean below the 0.05 cutoff
+    sig, bia = rng.uniform(-0.1, 0.1, (3, 3)), rng.uniform(-0.1, 0.1, (3, 3))
+    out = h.transform(torch.from_numpy(big).cuda(), sigmas=sig, biases=bia).cpu().numpy()
+    assert h.last_status.cpu().tolist() == [0, 1, 1]
+    assert np.array_equal(out[1], big[1]) and np.array_equal(out[2], big[2])
+    mx, frac = lsb_stats(out[0], so.hed_augment(big[0], sig[0], bia[0]))
+    assert mx <= 1 and frac >= 0.999, (mx, frac)
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
