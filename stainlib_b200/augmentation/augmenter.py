@@ -160,10 +160,9 @@ class GrayscaleAugmentor(object):
 
     def pop(self):
         b = nv.Batch(self.image)
-        draws = np.empty((b.B, 2), dtype=np.float64)
-        for i in range(b.B):
-            draws[i, 0] = np.random.uniform(1 - 0.2, 1 + 0.2)
-            draws[i, 1] = np.random.uniform(-0.2, 0.2)
+        # per tile alpha ~ U(0.8, 1.2) then beta ~ U(-0.2, 0.2): one vectorised call consumes numpy's global stream in
+        # exactly the order of the reference's scalar calls (augmenter.py:395-396), tile after tile
+        draws = np.random.uniform(low=[1 - 0.2, -0.2], high=[1 + 0.2, 0.2], size=(b.B, 2))
         par = torch.as_tensor(np.ascontiguousarray(draws.T)).to(b.dev.device)   # [2,B]: alphas then betas
         out = b.new_like()
         import ctypes
@@ -209,18 +208,18 @@ class StainAugmentor(object):
     def pop(self, alphas=None, betas=None):
         b = self._batch
         if alphas is None:
-            alphas = np.empty((b.B, 2))
-            betas = np.empty((b.B, 2))
-            for t in range(b.B):
-                for i in range(self.n_stains):
-                    alphas[t, i] = np.random.uniform(1 - self.sigma1, 1 + self.sigma1)
-                    betas[t, i] = np.random.uniform(-self.sigma2, self.sigma2)
+            # (alpha_0, beta_0, alpha_1, beta_1) per tile, drawn in the reference's order (augmenter.py:435-437) by one
+            # vectorised call on numpy's global stream
+            d = np.random.uniform(low=[1 - self.sigma1, -self.sigma2], high=[1 + self.sigma1, self.sigma2], size=(b.B, 2, 2))
+            alphas, betas = d[:, :, 0], d[:, :, 1]
         al = np.broadcast_to(np.asarray(alphas, dtype=np.float64), (b.B, 2))
         be = np.broadcast_to(np.asarray(betas, dtype=np.float64), (b.B, 2))
         par = torch.as_tensor(np.ascontiguousarray(np.concatenate([al, be], axis=0))).to(b.dev.device)
         M = self.stain_matrix
-        Mt = torch.as_tensor(np.asarray(M.cpu()) if isinstance(M, torch.Tensor) else np.asarray(M), dtype=torch.float64)
-        Mt = Mt.reshape(-1, 2, 3).contiguous().to(b.dev.device)
+        if isinstance(M, torch.Tensor) and M.is_cuda:
+            Mt = M.to(torch.float64).reshape(-1, 2, 3).contiguous()          # batched fit: already on the device
+        else:
+            Mt = torch.as_tensor(np.asarray(M), dtype=torch.float64).reshape(-1, 2, 3).contiguous().to(b.dev.device)
         out = b.new_like()
         import ctypes
         nv.check(nv.load_library().sb_stain_augment(

@@ -444,6 +444,7 @@ int sb_stain_augment(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int 
     a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb_in, rgb_out, a.npx);
     a.tab = h->tab; a.M = M; a.scale = alpha; a.beta = beta; a.lasso_lambda = lasso_lambda;
     a.augment_background = augment_background; a.ybound = mask_ybound_f(luminosity_threshold);
+    for (int c = 0; c < 3; ++c) a.ycoef[c] = (float)SB_RGB2LAB_COEFFS[3 + c];
     cudaError_t e = (cudaError_t)sb::launch_stain_augment(a, h->num_sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "stain_augment launch");
     h->launches += 1;

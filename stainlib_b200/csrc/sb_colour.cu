@@ -14,6 +14,7 @@
 //                     to  rgb' = b^(log_b(rgb/255+2) . A - c) - 2  with a per-tile 3x3 A and 3-vector c)
 //   gray_kernel       GrayscaleAugmentor.pop       augmenter.py:390-401
 #include "sb_kernels.h"
+#include "sb_ring.cuh"
 #include "sb_tables.inc"
 
 namespace sb {
@@ -387,6 +388,106 @@ __global__ void __launch_bounds__(256, 3) hed_kernel(HedArgs a) {
     }
 }
 
+// ---- HED on the TMA ring (sb_ring.cuh): the path for 16-byte aligned tiles; hed_kernel above serves the rest.
+struct HedConsts { float A[9]; float c[3]; };
+struct HedRingParams {
+    const HedConsts* consts;       // [B]
+    unsigned long long* sums;      // [B] zeroed: sum of all channel bytes of the tile (patch-mean gate)
+};
+
+// Per-tile A = inv(M) diag(1+sigma) M and c = bias M scaled to base 2 (M = rgb_from_hed), as in hed_kernel.
+__global__ void hed_prepare_kernel(int B, const double* __restrict__ sigma, const double* __restrict__ bias, double log_base, HedConsts* out) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= B) return;
+    const double M[9] = {0.65, 0.70, 0.29, 0.07, 0.99, 0.11, 0.27, 0.57, 0.78};
+    const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+    double Mi[9];
+    Mi[0] = (M[4] * M[8] - M[5] * M[7]) / det; Mi[1] = (M[2] * M[7] - M[1] * M[8]) / det; Mi[2] = (M[1] * M[5] - M[2] * M[4]) / det;
+    Mi[3] = (M[5] * M[6] - M[3] * M[8]) / det; Mi[4] = (M[0] * M[8] - M[2] * M[6]) / det; Mi[5] = (M[2] * M[3] - M[0] * M[5]) / det;
+    Mi[6] = (M[3] * M[7] - M[4] * M[6]) / det; Mi[7] = (M[1] * M[6] - M[0] * M[7]) / det; Mi[8] = (M[0] * M[4] - M[1] * M[3]) / det;
+    const double l2b = log2(log_base);
+    HedConsts k;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double v = 0.0;
+            for (int q = 0; q < 3; ++q) v += Mi[3 * i + q] * (1.0 + sigma[(size_t)tile * 3 + q]) * M[3 * q + j];
+            k.A[3 * i + j] = (float)v;
+        }
+    for (int j = 0; j < 3; ++j) {
+        double v = 0.0;
+        for (int q = 0; q < 3; ++q) v += bias[(size_t)tile * 3 + q] * M[3 * q + j];
+        k.c[j] = (float)(-v * l2b);
+    }
+    out[tile] = k;
+}
+
+struct HedOp {
+    using Consts = HedConsts;
+    using Params = HedRingParams;
+    using Acc = unsigned;
+    static constexpr int kLaneShift = 2;
+    __device__ static void fill_table(unsigned char* tab, const Params&, int tid, int n) {
+        for (int i = tid; i < 256 * 32; i += n)
+            *reinterpret_cast<float*>(tab + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = (float)log2((double)(i >> 5) / 255.0 + 2.0);
+    }
+    __device__ static void acc_init(Acc& a) { a = 0u; }
+    __device__ static void pair(const Consts& k, float2 lr, float2 lg, float2 lb, uint32_t (&bits)[6]) {
+        const float2 e0 = __ffma2_rn(lb, dup(k.A[6]), __ffma2_rn(lg, dup(k.A[3]), __ffma2_rn(lr, dup(k.A[0]), dup(k.c[0]))));
+        const float2 e1 = __ffma2_rn(lb, dup(k.A[7]), __ffma2_rn(lg, dup(k.A[4]), __ffma2_rn(lr, dup(k.A[1]), dup(k.c[1]))));
+        const float2 e2 = __ffma2_rn(lb, dup(k.A[8]), __ffma2_rn(lg, dup(k.A[5]), __ffma2_rn(lr, dup(k.A[2]), dup(k.c[2]))));
+        bits[0] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e0.x), 1.f, -2.f), 255.f, 8388608.f));
+        bits[1] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e1.x), 1.f, -2.f), 255.f, 8388608.f));
+        bits[2] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e2.x), 1.f, -2.f), 255.f, 8388608.f));
+        bits[3] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e0.y), 1.f, -2.f), 255.f, 8388608.f));
+        bits[4] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e1.y), 1.f, -2.f), 255.f, 8388608.f));
+        bits[5] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e2.y), 1.f, -2.f), 255.f, 8388608.f));
+    }
+    __device__ static void process(const Consts& k, const Params&, const OdAbs tab, uint4* grp, Acc& acc) {
+        const uint4 va = grp[0], vb = grp[1], vc = grp[2];
+        const uint32_t w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
+        uint32_t o[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc += __vsadu4(w[i], 0u);           // the speculative transform also sums the input bytes
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
+            uint32_t b01[6], b23[6];
+            pair(k, f2(od_lookup(tab, wa, 0u, 0), od_lookup(tab, wa, 0u, 3)), f2(od_lookup(tab, wa, 0u, 1), od_lookup(tab, wb, 0u, 0)),
+                 f2(od_lookup(tab, wa, 0u, 2), od_lookup(tab, wb, 0u, 1)), b01);
+            pair(k, f2(od_lookup(tab, wb, 0u, 2), od_lookup(tab, wc, 0u, 1)), f2(od_lookup(tab, wb, 0u, 3), od_lookup(tab, wc, 0u, 2)),
+                 f2(od_lookup(tab, wc, 0u, 0), od_lookup(tab, wc, 0u, 3)), b23);
+            o[3 * q] = pack4(b01[0], b01[1], b01[2], b01[3]);
+            o[3 * q + 1] = pack4(b01[4], b01[5], b23[0], b23[1]);
+            o[3 * q + 2] = pack4(b23[2], b23[3], b23[4], b23[5]);
+        }
+        grp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        grp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        grp[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    }
+    __device__ static void finish_run(const Params& p, int tile, Acc& acc) {
+        unsigned long long t = acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if ((threadIdx.x & 31) == 0 && t) atomicAdd(&p.sums[tile], t);
+        acc = 0u;
+    }
+};
+
+// Runs behind the ring kernel: evaluates the patch-mean gate of every tile (augmenter.py:288-293) and copies the input
+// back over the (rare) tiles that are to be left unchanged.  One CTA per tile; 16-byte aligned tiles.
+__global__ void __launch_bounds__(256) hed_gate_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int npx,
+                                                        const unsigned long long* __restrict__ sums, double lo, double hi, int32_t* status) {
+    const int tile = blockIdx.x;
+    const double mean = (double)sums[tile] / (3.0 * (double)npx) / 255.0;
+    const bool skip = !(lo <= mean && mean <= hi);
+    if (threadIdx.x == 0 && status) status[tile] = skip ? 1 : 0;
+    if (!skip) return;
+    const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)tile * npx * 3);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)tile * npx * 3);
+    const size_t nvec = (size_t)npx * 3 / 16;
+    for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
+}
+
 struct GrayArgs {
     const uint8_t* in;
     uint8_t* out;
@@ -421,6 +522,45 @@ __global__ void __launch_bounds__(256, 4) gray_kernel(GrayArgs a) {
         store_group(tout, a.npx, g, a.aligned != 0, o);
     }
 }
+
+// ---- GrayscaleAugmentor.pop on the TMA ring
+struct GrayConsts { float al, be; };
+struct GrayConstsView {                      // consts[tile] builds the pair from the caller's double arrays
+    const double* alpha;
+    const double* beta;
+    __device__ GrayConsts operator[](int tile) const { return GrayConsts{(float)alpha[tile], (float)beta[tile]}; }
+};
+struct GrayRingParams { GrayConstsView consts; };
+struct GrayOp {
+    using Consts = GrayConsts;
+    using Params = GrayRingParams;
+    struct Acc {};
+    static constexpr int kLaneShift = 2;
+    __device__ static void fill_table(unsigned char*, const Params&, int, int) {}
+    __device__ static void acc_init(Acc&) {}
+    __device__ static void process(const Consts& k, const Params&, const OdAbs, uint4* grp, Acc&) {
+        const uint4 va = grp[0], vb = grp[1], vc = grp[2];
+        const uint32_t w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
+        const float kr = (float)(0.2125 / 255.0), kg = (float)(0.7154 / 255.0), kb = (float)(0.0721 / 255.0);
+        uint32_t v[16], o[12];
+        for_each_px(w, [&](int i, uint32_t r, uint32_t gg, uint32_t b) {
+            const float gray = fmaf((float)b, kb, fmaf((float)gg, kg, (float)r * kr));
+            const float x = fminf(fmaxf(fmaf(gray, k.al, k.be), 0.f), 1.f) * 255.f;
+            v[i] = clip_u8_bits(x) & 255u;
+        });
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t p0 = v[4 * q], p1 = v[4 * q + 1], p2 = v[4 * q + 2], p3 = v[4 * q + 3];
+            o[3 * q] = p0 | (p0 << 8) | (p0 << 16) | (p1 << 24);
+            o[3 * q + 1] = p1 | (p1 << 8) | (p2 << 16) | (p2 << 24);
+            o[3 * q + 2] = p2 | (p3 << 8) | (p3 << 16) | (p3 << 24);
+        }
+        grp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        grp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        grp[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    }
+    __device__ static void finish_run(const Params&, int, Acc&) {}
+};
 
 }  // namespace sb
 
@@ -497,10 +637,31 @@ int sb_hed_augment(sb_handle* hh, const uint8_t* rgb_in, uint8_t* rgb_out, int B
     if (bad_img(hh, rgb_in, B, H, W) || !rgb_out || !sigma || !bias) return SB_ERR_ARG;
     sb_handle* h = hh;
     cudaStream_t st = (cudaStream_t)stream;
+    const int npx = H * W, al = aligned16(rgb_in, rgb_out, npx);
+    if (al) {
+        // TMA ring: per-tile constants -> ring kernel (speculative transform + byte sums) -> gate kernel
+        unsigned char* ws = nullptr;
+        const size_t c_bytes = ((size_t)B * sizeof(sb::HedConsts) + 15) & ~(size_t)15;
+        if (cudaMallocAsync(&ws, c_bytes + (size_t)B * 8, st) != cudaSuccess) return SB_ERR_CUDA;
+        sb::HedConsts* consts = reinterpret_cast<sb::HedConsts*>(ws);
+        unsigned long long* sums = reinterpret_cast<unsigned long long*>(ws + c_bytes);
+        cudaMemsetAsync(sums, 0, (size_t)B * 8, st);
+        sb::hed_prepare_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, sigma, bias, log_base, consts);
+        sb::RingGeom g{rgb_in, rgb_out, B, npx};
+        sb::HedRingParams p{consts, sums};
+        int rc = sb::launch_ring<sb::HedOp>(g, p, h->num_sms, st);
+        if (rc == 0) {
+            sb::hed_gate_kernel<<<B, 256, 0, st>>>(rgb_in, rgb_out, npx, sums, cutoff_lo, cutoff_hi, status);
+            rc = (int)cudaGetLastError();
+        }
+        cudaFreeAsync(ws, st);
+        if (rc != 0) return SB_ERR_CUDA;
+        h->launches += 3;
+        return SB_OK;
+    }
     unsigned long long* sums = nullptr;                 // [B] byte sums followed by [B] finished-CTA counters
     if (cudaMallocAsync(&sums, (size_t)B * 12, st) != cudaSuccess) return SB_ERR_CUDA;
     if (cudaMemsetAsync(sums, 0, (size_t)B * 12, st) != cudaSuccess) return SB_ERR_CUDA;
-    const int npx = H * W, al = aligned16(rgb_in, rgb_out, npx);
     const dim3 grid = tile_grid(B, npx, h->num_sms);
     sb::HedArgs a{};
     a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = npx; a.aligned = al; a.sigma = sigma; a.bias = bias;
@@ -525,6 +686,13 @@ int sb_grayscale_augment(sb_handle* hh, const uint8_t* rgb_in, uint8_t* rgb_out,
     sb_handle* h = hh;
     sb::GrayArgs a{};
     a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = aligned16(rgb_in, rgb_out, a.npx); a.alpha = alpha; a.beta = beta;
+    if (a.aligned) {
+        // TMA ring; the per-tile constants are the caller's alpha / beta arrays themselves
+        sb::GrayRingParams p{sb::GrayConstsView{alpha, beta}};
+        if (sb::launch_ring<sb::GrayOp>(sb::RingGeom{rgb_in, rgb_out, B, a.npx}, p, h->num_sms, (cudaStream_t)stream) != 0) return SB_ERR_CUDA;
+        h->launches += 1;
+        return SB_OK;
+    }
     sb::gray_kernel<<<tile_grid(B, a.npx, h->num_sms), 256, 0, (cudaStream_t)stream>>>(a);
     if (cudaGetLastError() != cudaSuccess) return SB_ERR_CUDA;
     h->launches += 1;

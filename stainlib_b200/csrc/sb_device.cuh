@@ -271,6 +271,13 @@ __device__ __forceinline__ float od_lookup(const OdAbs& t, uint32_t w, uint32_t 
     return r;
 }
 __device__ __forceinline__ float od_lookup(const OdAbs* t, uint32_t w, uint32_t lane_off, int k) { return od_lookup(*t, w, lane_off, k); }
+// {od, gamma} pair table (8 bytes per lane, lane_base = lane << 3 | T >> 16 << 8): one LDS.64.
+__device__ __forceinline__ float2 odg_lookup_abs(const OdAbs& t, uint32_t w, int k) {
+    const uint32_t addr = __byte_perm(w, t.lane_base, 0x6504u | (k << 4));
+    float2 r;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    return r;
+}
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }

@@ -69,6 +69,7 @@ struct PointArgs {
     int B, npx, aligned;
     Tables tab;
     float ybound;
+    float ycoef[3];        // Y row of cv2's RGB->XYZ matrix (stain_augment's ring path computes the mask from gamma values)
     const double* M;       // [B,2,3] per-tile source matrices
     const double* scale;   // [B,2]   (recombine)  /  alpha (augment)
     const double* beta;    // [B,2]   (augment)

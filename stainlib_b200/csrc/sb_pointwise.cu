@@ -8,6 +8,7 @@
 // Work unit = one 16-pixel group (48 B, three 16-byte vectors); a tile is a whole number of CTA-sized spans so the
 // per-tile constants are block-uniform.  grid = (spans_per_tile, B).
 #include "sb_kernels.h"
+#include "sb_ring.cuh"
 
 namespace sb {
 
@@ -162,7 +163,88 @@ int launch_mask(const PointArgs& a, int num_sms, cudaStream_t stream) {
     mask_kernel<<<point_grid(a, num_sms, 8), PT, 0, stream>>>(a);
     return (int)cudaGetLastError();
 }
+// ---- StainAugmentor.pop on the TMA ring (sb_ring.cuh): the path for 16-byte aligned tiles
+struct AugConsts {
+    LassoK lk;
+    float A[6];              // -M_jk log2(e): recombination with the tile's own stain matrix
+    float alpha[2], beta[2];
+};
+struct AugRingParams {
+    const AugConsts* consts;
+    const float* od;
+    const unsigned short* gamma;
+    float ycoef[3], ybound;
+    int all_px;
+};
+__global__ void aug_prepare_kernel(PointArgs a, AugConsts* out) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= a.B) return;
+    double M[6];
+    for (int k = 0; k < 6; ++k) M[k] = a.M[(size_t)tile * 6 + k];
+    AugConsts c;
+    make_lasso_consts(M, a.lasso_lambda, c.lk);
+    const double LOG2E = 1.4426950408889634;
+    for (int k = 0; k < 6; ++k) c.A[k] = (float)(-M[k] * LOG2E);
+    for (int j = 0; j < 2; ++j) { c.alpha[j] = (float)a.scale[(size_t)tile * 2 + j]; c.beta[j] = (float)a.beta[(size_t)tile * 2 + j]; }
+    out[tile] = c;
+}
+struct AugOp {
+    using Consts = AugConsts;
+    using Params = AugRingParams;
+    struct Acc {};
+    static constexpr int kLaneShift = 3;      // {od, gamma} pairs
+    __device__ static void fill_table(unsigned char* tab, const Params& p, int tid, int n) {
+        for (int i = tid; i < 256 * 32; i += n)
+            *reinterpret_cast<float2*>(tab + (i >> 5) * OD_ROW_BYTES + (i & 31) * 8) = make_float2(p.od[i >> 5], (float)p.gamma[i >> 5]);
+    }
+    __device__ static void acc_init(Acc&) {}
+    __device__ static void pixel(const Consts& k, const Params& p, float2 r, float2 g, float2 b, uint32_t* bits) {
+        float c0, c1;
+        lasso2(k.lk, r.x, g.x, b.x, c0, c1);
+        const bool m = p.all_px | (fmaf(p.ycoef[2], b.y, fmaf(p.ycoef[1], g.y, p.ycoef[0] * r.y)) < p.ybound);
+        c0 = m ? fmaf(c0, k.alpha[0], k.beta[0]) : c0;
+        c1 = m ? fmaf(c1, k.alpha[1], k.beta[1]) : c1;
+        bits[0] = clip_u8_bits(ex2_approx(fmaf(c1, k.A[3], fmaf(c0, k.A[0], LOG2_255_UP))));
+        bits[1] = clip_u8_bits(ex2_approx(fmaf(c1, k.A[4], fmaf(c0, k.A[1], LOG2_255_UP))));
+        bits[2] = clip_u8_bits(ex2_approx(fmaf(c1, k.A[5], fmaf(c0, k.A[2], LOG2_255_UP))));
+    }
+    __device__ static void process(const Consts& k, const Params& p, const OdAbs tab, uint4* grp, Acc&) {
+        const uint4 va = grp[0], vb = grp[1], vc = grp[2];
+        const uint32_t w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
+        uint32_t o[12];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
+            uint32_t bits[12];
+            pixel(k, p, odg_lookup_abs(tab, wa, 0), odg_lookup_abs(tab, wa, 1), odg_lookup_abs(tab, wa, 2), bits);
+            pixel(k, p, odg_lookup_abs(tab, wa, 3), odg_lookup_abs(tab, wb, 0), odg_lookup_abs(tab, wb, 1), bits + 3);
+            pixel(k, p, odg_lookup_abs(tab, wb, 2), odg_lookup_abs(tab, wb, 3), odg_lookup_abs(tab, wc, 0), bits + 6);
+            pixel(k, p, odg_lookup_abs(tab, wc, 1), odg_lookup_abs(tab, wc, 2), odg_lookup_abs(tab, wc, 3), bits + 9);
+            o[3 * q] = pack4(bits[0], bits[1], bits[2], bits[3]);
+            o[3 * q + 1] = pack4(bits[4], bits[5], bits[6], bits[7]);
+            o[3 * q + 2] = pack4(bits[8], bits[9], bits[10], bits[11]);
+        }
+        grp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        grp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        grp[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    }
+    __device__ static void finish_run(const Params&, int, Acc&) {}
+};
+
 int launch_stain_augment(const PointArgs& a, int num_sms, cudaStream_t stream) {
+    if (a.aligned) {
+        AugConsts* consts = nullptr;
+        cudaError_t e = cudaMallocAsync(&consts, (size_t)a.B * sizeof(AugConsts), stream);
+        if (e != cudaSuccess) return (int)e;
+        aug_prepare_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a, consts);
+        AugRingParams p{};
+        p.consts = consts; p.od = a.tab.od; p.gamma = a.tab.gamma;
+        p.ycoef[0] = a.ycoef[0]; p.ycoef[1] = a.ycoef[1]; p.ycoef[2] = a.ycoef[2]; p.ybound = a.ybound;
+        p.all_px = a.augment_background != 0;
+        const int rc = launch_ring<AugOp>(RingGeom{a.in, a.out, a.B, a.npx}, p, num_sms, stream);
+        cudaFreeAsync(consts, stream);
+        return rc;
+    }
     stain_augment_kernel<<<point_grid(a, num_sms, 4), PT, 0, stream>>>(a);
     return (int)cudaGetLastError();
 }

@@ -12,6 +12,7 @@
 //   * in the TMA kernel the table sits at a 64 KB-aligned shared address, so the PRMT output IS the LDS address.
 #include <cstdlib>
 #include "sb_kernels.h"
+#include "sb_ring.cuh"   // mbarrier / cp.async.bulk helpers shared with the generic ring kernel
 
 namespace sb {
 
@@ -71,34 +72,6 @@ __global__ void __launch_bounds__(RT, 3) recombine_v2_kernel(PointArgs a, const 
 // PLACE in shared memory, and the chunk leaves with one bulk store.  Loads run NSTAGE-1 chunks ahead of the math, both
 // directions are fully coalesced by the copy engine, and no thread ever waits on a global load.
 // Template parameters: TT compute threads (+ one producer warp), NSTAGE ring slots of TT*48 bytes.
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
 
 // Per-tile constants for sb_recombine: source matrices + scales given by the caller.
 __global__ void k4_prepare_kernel(PointArgs a, K4Consts* out) {

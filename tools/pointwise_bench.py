@@ -1,0 +1,65 @@
+"""Device-resident timing of every single-operator entry point on 1024 x 512^2 tiles (CUDA events, 3 warm-ups, mean of
+10): ms per launch sequence, Gpx/s, and the fraction of the measured HBM copy peak at the operator's algorithmic bytes.
+python tools/pointwise_bench.py > gpurun_out/pointwise.txt"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import stainlib_b200 as sb
+from stainlib_b200.augmentation.augmenter import GrayscaleAugmentor, HedLightColorAugmenter, StainAugmentor
+from stainlib_b200.synth import synth_batch, synth_tile
+from stainlib_b200.utils.stain_utils import LuminosityStandardizer, LuminosityThresholdTissueLocator
+
+B, H, W = 1024, 512, 512
+peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+    os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+pool = torch.from_numpy(synth_batch(5000, 64, H, W))
+x = pool.repeat(B // 64, 1, 1, 1).contiguous().cuda()
+npx = B * H * W
+
+
+def timed(fn, n=10):
+    for _ in range(3):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+rng = np.random.default_rng(0)
+hed = HedLightColorAugmenter()
+sig, bia = rng.uniform(-0.1, 0.1, (B, 3)), rng.uniform(-0.1, 0.1, (B, 3))
+rein = sb.ReinhardStainNormalizer()
+rein.fit(synth_tile(1, H, W, kind="target"))
+mac = sb.ExtractiveStainNormalizer("macenko")
+mac.fit(synth_tile(1, H, W, kind="target"))
+aug = StainAugmentor("macenko")
+aug.fit(x)
+gray = GrayscaleAugmentor()
+gray.fit(x)
+rows = [
+    ("HedLightColorAugmenter.transform (hed ring)", 6.0, lambda: hed.transform(x, sigmas=sig, biases=bia)),
+    ("StainAugmentor.pop (stain-augment ring)", 6.0, lambda: aug.pop()),
+    ("GrayscaleAugmentor.pop (gray ring)", 6.0, lambda: gray.pop()),
+    ("ReinhardStainNormalizer.transform (lab_tile_kernel)", 6.0, lambda: rein.transform(x)),
+    ("LuminosityStandardizer.standardize (lab_tile_kernel)", 6.0, lambda: LuminosityStandardizer.standardize(x)),
+    ("get_tissue_mask (mask_kernel)", 4.0, lambda: LuminosityThresholdTissueLocator.get_tissue_mask(x)),
+    ("MacenkoStainExtractor.get_stain_matrix (tile_pipeline_kernel, extract)", 3.0, lambda: sb.MacenkoStainExtractor.get_stain_matrix(x)),
+    ("ExtractiveStainNormalizer('macenko').transform", 6.0, lambda: mac.transform(x)),
+]
+print(f"# {B} x {H}x{W} tiles, device-resident, ms per call; peak = {peak:.0f} GB/s (measured copy rate)")
+for name, bpp, fn in rows:
+    try:
+        ms = timed(fn)
+        print(f"{name:75s} {ms:8.3f} ms  {npx / ms / 1e6:8.1f} Gpx/s  {npx * bpp / ms / 1e6 / peak:6.3f} of peak @ {bpp:.0f} B/px")
+    except Exception as e:                                     # keep going: this is a survey
+        print(f"{name:75s} failed: {type(e).__name__}: {e}")
