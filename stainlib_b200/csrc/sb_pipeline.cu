@@ -42,8 +42,9 @@ struct __align__(16) PipeShared {
     int n_distinct;
     unsigned okey[4];                // the four selected 23-bit keys (either selection path writes them)
     // sampled-bracket selection
-    unsigned lhist[256];
-    unsigned l_len[2], l_below[2], l_bin, l_rem, s_cnt;
+    unsigned lhist[2][256];
+    unsigned l_len[2], l_below[2], l_bin[2], l_rem[2], l_cnt[2], l_min[2], s_cnt;
+    double ang[4], cs[4];            // the four selected angles; cos/sin of the two interpolated ones
     unsigned brk_a[2], brk_b[2];
     float fast_lo[2], fast_hi[2];    // conservative float thresholds that let most pixels skip the exact key
     unsigned wq[NWARP][WQ_CAP];      // per-warp compaction queues of the rare pixels that need the exact key
@@ -317,39 +318,75 @@ __device__ inline void plan_bracket(unsigned n, unsigned n_s, unsigned lo, unsig
     rb = b > (double)(n_s - 1) ? n_s - 1 : (unsigned)b;
 }
 
-// rank-th smallest (0-based) key of list[0..len): 8-bit radix levels (two for offsets, three for full keys) with a
-// 256-bin histogram; whole block calls.
-__device__ __forceinline__ unsigned list_select(PipeShared* sh, const KeyList& list, unsigned len, unsigned rank) {
-    unsigned prefix = 0, mask = 0;
-    const unsigned origin = list.wide ? 0u : list.start;
-    for (int shift = list.wide ? 16 : 8; shift >= 0; shift -= 8) {
-        if (threadIdx.x < 256) sh->lhist[threadIdx.x] = 0;
+// The order statistics r_lo[j] and r_hi[j] (= r_lo[j] or r_lo[j] + 1: numpy's two interpolation neighbours) of BOTH
+// lists in one sweep: 8-bit radix levels over the two lists side by side (two for offsets, three when a list holds full
+// keys; warp j scans list j's 256-bin histogram), then -- only if a rank's upper neighbour is not another copy of the
+// same key -- one pass for the smallest key above it.  A dozen block barriers instead of four selections' three dozen.
+// key[2j] / key[2j+1] receive the keys of r_lo[j] / r_hi[j].  Whole block calls.
+__device__ __forceinline__ void list_select_pairs(PipeShared* sh, const KeyList& l0, const KeyList& l1, const unsigned (&r_lo)[2],
+                                                  const unsigned (&r_hi)[2], unsigned* key) {
+    const unsigned len[2] = {sh->l_len[0], sh->l_len[1]};
+    const unsigned origin[2] = {l0.wide ? 0u : l0.start, l1.wide ? 0u : l1.start};
+    unsigned prefix[2] = {0u, 0u}, rank[2] = {r_lo[0], r_lo[1]};
+    unsigned mask = 0;
+    for (int shift = (l0.wide || l1.wide) ? 16 : 8; shift >= 0; shift -= 8) {
+        (&sh->lhist[0][0])[threadIdx.x] = 0;                     // NT == 512 == 2 x 256
         __syncthreads();
-        for (unsigned i = threadIdx.x; i < len; i += NT) {
-            const unsigned k = list.get(i) - origin;
-            if ((k & mask) == prefix) atomicAdd(&sh->lhist[(k >> shift) & 255u], 1u);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const KeyList& l = j ? l1 : l0;
+            for (unsigned i = threadIdx.x; i < len[j]; i += NT) {
+                const unsigned k = l.get(i) - origin[j];
+                if ((k & mask) == prefix[j]) atomicAdd(&sh->lhist[j][(k >> shift) & 255u], 1u);
+            }
         }
         __syncthreads();
-        if (threadIdx.x < 32) {
+        if (threadIdx.x < 64) {
+            const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
             unsigned v[8], sum = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { v[i] = sh->lhist[threadIdx.x * 8 + i]; sum += v[i]; }
+            for (int i = 0; i < 8; ++i) { v[i] = sh->lhist[j][lane * 8 + i]; sum += v[i]; }
             const unsigned incl = warp_incl_scan(sum);
             unsigned c = incl - sum;
-            if (rank >= c && rank < incl) {
+            if (rank[j] >= c && rank[j] < incl) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if (rank >= c && rank < c + v[i]) { sh->l_bin = threadIdx.x * 8 + i; sh->l_rem = rank - c; }
+                    if (rank[j] >= c && rank[j] < c + v[i]) { sh->l_bin[j] = lane * 8 + i; sh->l_rem[j] = rank[j] - c; sh->l_cnt[j] = v[i]; }
                     c += v[i];
                 }
             }
         }
         __syncthreads();
-        prefix |= sh->l_bin << shift;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { prefix[j] |= sh->l_bin[j] << shift; rank[j] = sh->l_rem[j]; }
         mask |= 255u << shift;
-        rank = sh->l_rem;
     }
-    return origin + prefix;
+    // rank[j] = position of r_lo[j] among the l_cnt[j] copies of its key
+    bool next[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) next[j] = r_hi[j] > r_lo[j] && rank[j] + 1u >= sh->l_cnt[j];
+    if (next[0] || next[1]) {
+        if (threadIdx.x < 2) sh->l_min[threadIdx.x] = 0xFFFFFFFFu;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (!next[j]) continue;
+            const KeyList& l = j ? l1 : l0;
+            unsigned m = 0xFFFFFFFFu;
+            for (unsigned i = threadIdx.x; i < len[j]; i += NT) {
+                const unsigned k = l.get(i) - origin[j];
+                if (k > prefix[j] && k < m) m = k;
+            }
+            if (m != 0xFFFFFFFFu) atomicMin(&sh->l_min[j], m);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        key[2 * j] = origin[j] + prefix[j];
+        key[2 * j + 1] = next[j] ? origin[j] + sh->l_min[j] : origin[j] + prefix[j];
+    }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------- rare-pixel compaction queues
@@ -650,11 +687,12 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                         }
                         __syncthreads();
                         if (sh->s_ok) {
-                            for (int q = 0; q < 4; ++q) {
-                                const int j = q >> 1;
-                                const unsigned r = ((q & 1) ? p_hi[j] : p_lo[j]) - sh->l_below[j];
-                                const unsigned key = list_select(sh, j ? list1 : list0, sh->l_len[j], r);
-                                if (threadIdx.x == 0) sh->okey[q] = key;
+                            {
+                                const unsigned r_lo[2] = {p_lo[0] - sh->l_below[0], p_lo[1] - sh->l_below[1]};
+                                const unsigned r_hi[2] = {p_hi[0] - sh->l_below[0], p_hi[1] - sh->l_below[1]};
+                                unsigned keys[4];
+                                list_select_pairs(sh, list0, list1, r_lo, r_hi, keys);
+                                if (threadIdx.x < 4) sh->okey[threadIdx.x] = keys[threadIdx.x];
                             }
                             __syncthreads();
                             sampled = true;
@@ -714,14 +752,19 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     if (threadIdx.x < 4) sh->okey[threadIdx.x] = (sh->q_bin[threadIdx.x] << L2_BITS) | sh->q_key[threadIdx.x];
                     __syncthreads();
                 }
+                // the fp64 transcendentals of this step are latency-bound on one thread: four threads take one atan2 each,
+                // two threads one sincos each
+                if (threadIdx.x < 4) sh->ang[threadIdx.x] = angle_from_key(sh->okey[threadIdx.x]);
+                __syncthreads();
+                if (threadIdx.x < 2) {
+                    unsigned lo, hi; double fr;
+                    percentile_index(n_tissue, threadIdx.x == 0 ? 100.0 - a.ang_pct : a.ang_pct, lo, hi, fr);
+                    const double phi = lerp_np(sh->ang[2 * threadIdx.x], sh->ang[2 * threadIdx.x + 1], fr);
+                    sh->cs[2 * threadIdx.x] = cos(phi); sh->cs[2 * threadIdx.x + 1] = sin(phi);
+                }
+                __syncthreads();
                 if (threadIdx.x == 0) {
-                    double ang[4];
-                    for (int q = 0; q < 4; ++q) ang[q] = angle_from_key(sh->okey[q]);
-                    unsigned lo, hi; double fr_lo, fr_hi;
-                    percentile_index(n_tissue, 100.0 - a.ang_pct, lo, hi, fr_lo);
-                    percentile_index(n_tissue, a.ang_pct, lo, hi, fr_hi);
-                    const double min_phi = lerp_np(ang[0], ang[1], fr_lo), max_phi = lerp_np(ang[2], ang[3], fr_hi);
-                    const double c1 = cos(min_phi), s1 = sin(min_phi), c2 = cos(max_phi), s2 = sin(max_phi);
+                    const double c1 = sh->cs[0], s1 = sh->cs[1], c2 = sh->cs[2], s2 = sh->cs[3];
                     double v1[3], v2[3];
                     for (int k = 0; k < 3; ++k) {
                         v1[k] = sh->D[k] * c1 + sh->D[3 + k] * s1;
@@ -1005,11 +1048,12 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     }
                     __syncthreads();
                     if (sh->s_ok) {
-                        for (int q = 0; q < 4; ++q) {
-                            const int j = q >> 1;
-                            const unsigned r = ((q & 1) ? c_hi : c_lo) - sh->l_below[j];
-                            const unsigned key = list_select(sh, j ? list1 : list0, sh->l_len[j], r);
-                            if (threadIdx.x == 0) sh->okey[q] = key;
+                        {
+                            const unsigned r_lo[2] = {c_lo - sh->l_below[0], c_lo - sh->l_below[1]};
+                            const unsigned r_hi[2] = {c_hi - sh->l_below[0], c_hi - sh->l_below[1]};
+                            unsigned keys[4];
+                            list_select_pairs(sh, list0, list1, r_lo, r_hi, keys);
+                            if (threadIdx.x < 4) sh->okey[threadIdx.x] = keys[threadIdx.x];
                         }
                         __syncthreads();
                         sampled = true;
