@@ -266,11 +266,18 @@ def run_hed_reinhard(args, B, H, W, desc, rank, world, local, cpu):
 
     e2e = None
     if not args.no_e2e:
+        from stainlib_b200.io import stream_host_batches
         host_out = torch.empty_like(host_in).pin_memory()
+        chunk = 128                                     # 100 MB per slot: the Python-level operator calls are amortised
 
-        def e2e_step():                                 # pinned host -> device, both operators on the device, -> pinned host
-            x = host_in.cuda(non_blocking=True)
-            host_out.copy_(step(x), non_blocking=True)
+        def e2e_step():                                 # pinned host -> device -> both operators -> pinned host, overlapped chunks
+            pos = {"t0": 0}
+
+            def op(x):
+                t0 = pos["t0"]
+                pos["t0"] += x.shape[0]
+                return rein.transform(hed.transform(x, sigmas=sig[t0:t0 + x.shape[0]], biases=bias[t0:t0 + x.shape[0]]))
+            stream_host_batches(op, host_in, host_out, chunk_tiles=chunk)
             torch.cuda.synchronize()
         for _ in range(2):
             e2e_step()

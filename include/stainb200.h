@@ -148,6 +148,13 @@ int sb_reinhard_transform(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out,
                           const double* target_means, const double* target_stds, int mask_background,
                           double luminosity_threshold, int32_t* status, void* stream);
 
+/* Host feeding (replaces the PIL loading of the reference's callers,
+ * stainlib_normalization.ipynb:61-74): batched nvJPEG decode of B baseline JPEGs, all H x W, from HOST memory into the
+ * DEVICE batch rgb_out uint8 [B,H,W,3] (interleaved RGB), stream-ordered on `stream`.  jpeg[i] / nbytes[i]: the i-th
+ * compressed tile.  SB_ERR_ARG for a corrupt / unsupported stream or a tile that is not H x W. */
+int sb_decode_jpeg(sb_handle* h, const uint8_t* const* jpeg, const size_t* nbytes, int B, int H, int W, uint8_t* rgb_out,
+                   void* stream);
+
 /* LuminosityStandardizer.standardize -- stain_utils.py:53-67. */
 int sb_luminosity_standardize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W,
                               double percentile, void* stream);

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstainb200.so")
-SOURCES = ["sb_api.cu", "sb_pipeline.cu", "sb_pointwise.cu", "sb_colour.cu", "sb_recombine.cu"]
+SOURCES = ["sb_api.cu", "sb_pipeline.cu", "sb_pointwise.cu", "sb_colour.cu", "sb_recombine.cu", "sb_io.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lnvjpeg"]
     subprocess.check_call(cmd)
     return LIB
 

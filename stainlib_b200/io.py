@@ -1,0 +1,68 @@
+"""Host feeding helpers.
+
+* ``decode_jpeg_batch``: compressed tiles -> ``torch.uint8 [B,H,W,3]`` on the GPU through nvJPEG (``sb_decode_jpeg``);
+  the B200-native replacement of the PIL loading step of the reference's callers (stainlib_normalization.ipynb:61-74).
+* ``stream_host_batches``: runs ANY device-batch operator of this package (a normaliser's ``transform``, an augmenter,
+  a composition) over a pinned host batch in overlapped chunks -- H2D, compute and D2H on three streams with three
+  slots, the Python counterpart of ``sb_normalize_host`` for the operators that have no fused host entry point.
+"""
+import ctypes
+
+import torch
+
+from stainlib_b200 import _native as nv
+
+
+def decode_jpeg_batch(jpegs, H, W, device=None, out=None):
+    """jpegs: sequence of ``bytes`` / ``bytearray`` / 1-D uint8 tensors holding baseline JPEG streams, every one H x W.
+    Returns (or fills ``out``) a uint8 [B,H,W,3] RGB CUDA tensor, stream-ordered on the current stream."""
+    h, idx = nv.get_handle(device)
+    B = len(jpegs)
+    bufs = [bytes(j) if not isinstance(j, torch.Tensor) else bytes(j.cpu().numpy().tobytes()) for j in jpegs]
+    ptrs = (ctypes.c_void_p * B)(*[ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p) for b in bufs])
+    sizes = (ctypes.c_size_t * B)(*[len(b) for b in bufs])
+    if out is None:
+        out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=f"cuda:{idx}")
+    assert out.is_cuda and out.dtype == torch.uint8 and tuple(out.shape) == (B, H, W, 3) and out.is_contiguous()
+    nv.check(nv.load_library().sb_decode_jpeg(h, ptrs, sizes, B, int(H), int(W), nv.ptr(out), nv.stream_ptr(idx)))
+    torch.cuda.current_stream(idx).synchronize()          # nvJPEG reads the host buffers asynchronously: keep them alive
+    return out
+
+
+def stream_host_batches(op, host_in, host_out=None, chunk_tiles=16, device=None):
+    """``host_out[i] = op(host_in[i])`` tile batch by tile batch with copies and compute overlapped.
+
+    op: callable taking and returning a uint8 [b,H,W,3] CUDA tensor (e.g. ``lambda x: rein.transform(hed.transform(x))``).
+    host_in / host_out: uint8 [B,H,W,3] CPU tensors, pinned for full speed.  Returns host_out."""
+    _, idx = nv.get_handle(device)
+    dev = torch.device("cuda", idx)
+    if host_out is None:
+        host_out = torch.empty_like(host_in, pin_memory=host_in.is_pinned())
+    B = host_in.shape[0]
+    s_in, s_comp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    n_slot = 3
+    d_in = [torch.empty((chunk_tiles,) + tuple(host_in.shape[1:]), dtype=torch.uint8, device=dev) for _ in range(n_slot)]
+    d_out = [None] * n_slot
+    ev_in = [torch.cuda.Event() for _ in range(n_slot)]
+    ev_comp = [torch.cuda.Event() for _ in range(n_slot)]
+    ev_out = [torch.cuda.Event() for _ in range(n_slot)]
+    for c, t0 in enumerate(range(0, B, chunk_tiles)):
+        slot, nt = c % n_slot, min(chunk_tiles, B - t0)
+        if c >= n_slot:
+            s_in.wait_event(ev_comp[slot])              # the slot's previous input has been consumed
+            s_comp.wait_event(ev_out[slot])             # ... and its previous output copied out
+        with torch.cuda.stream(s_in):
+            d_in[slot][:nt].copy_(host_in[t0:t0 + nt], non_blocking=True)
+            ev_in[slot].record(s_in)
+        with torch.cuda.stream(s_comp):
+            s_comp.wait_event(ev_in[slot])
+            d_out[slot] = op(d_in[slot][:nt])
+            ev_comp[slot].record(s_comp)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_comp[slot])
+            host_out[t0:t0 + nt].copy_(d_out[slot], non_blocking=True)
+            d_out[slot].record_stream(s_out)
+            ev_out[slot].record(s_out)
+    s_out.synchronize()
+    s_comp.synchronize()
+    return host_out

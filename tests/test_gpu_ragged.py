@@ -1,4 +1,4 @@
-"""Tiles whose byte size is NOT a multiple of 16 (61x53 and 127x33 pixels): every operator must take its bytewise /
+"""Tiles whose byte size is NOT a multiple of 16 (61x53 and 127x333 pixels): every operator must take its bytewise /
 register-staged path (no TMA ring, no 16-byte vectors, a ragged last 16-pixel group) and still meet the parity bar of
 the aligned path -- bit-exact for the integer pipelines, <= 1 LSB for the floating-point ones."""
 import numpy as np
@@ -10,7 +10,7 @@ from sb_testutil import lsb_stats
 from stainlib_b200.synth import synth_tile
 
 pytestmark = pytest.mark.gpu
-SHAPES = [(61, 53), (127, 33)]
+SHAPES = [(61, 53), (127, 333)]
 
 
 @pytest.fixture(scope="module")
