@@ -821,6 +821,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                 const int n_it = phase == 0 ? a.dl_sample_iters : a.dl_iters + ((a.dl_sample_iters > 0 && !use_sample) ? 4 : 0);
                 // The full passes inherit the difference history of the sample passes: the sample map has (nearly) the same
                 // Jacobian, so the first full steps are already quasi-Newton steps; only the residual bookkeeping restarts.
+                __syncthreads();     // every thread has read the previous phase's dl_stop before it is cleared
                 if (threadIdx.x == 0) { if (phase == 0 || !use_sample) aa_reset(sh->aa); else aa_carry(sh->aa); sh->dl_stop = 0; }
                 for (int it = 0; it < n_it; ++it) {
                     const LassoK lk = sh->lk;
