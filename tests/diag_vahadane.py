@@ -1,4 +1,4 @@
-"""Diagnostic: |GPU - oracle| and |. - fixed point| of the Vahadane stain matrix for a few synthetic tiles and pass counts."""
+"""Diagnostic (run by hand on the GPU box: python tests/diag_vahadane.py): |GPU - oracle| and |. - fixed point| of the Vahadane stain matrix for a few synthetic tiles and pass counts."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
