@@ -12,7 +12,7 @@ arithmetic; this module restates that published algorithm (tables generated from
 kernels have an exact integer specification to follow.  The restatement is pinned exhaustively against ``cv2`` on all
 2**24 colours in ``tests/test_oracle_lab.py`` (both directions, all three channels).
 
-The generated tables are also what ``tools/gen_tables.py`` writes into ``stainlib_b200/csrc/sb_tables.inc``.
+The generated tables are also what ``oracle/gen_tables.py`` writes into ``stainlib_b200/csrc/sb_tables.inc``.
 """
 import numpy as np
 

@@ -30,7 +30,7 @@ def test_mask_collapses_to_y_index(cube):
 
 
 def test_generated_tables_are_current():
-    """stainlib_b200/csrc/sb_tables.inc must be what tools/gen_tables.py produces from these formulas."""
+    """stainlib_b200/csrc/sb_tables.inc must be what oracle/gen_tables.py produces from these formulas."""
     import os
     import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
