@@ -29,23 +29,41 @@ def decode_jpeg_batch(jpegs, H, W, device=None, out=None):
     return out
 
 
-def stream_host_batches(op, host_in, host_out=None, chunk_tiles=16, device=None):
+_STREAMS = {}      # device index -> (s_in, s_comp, s_out): kept across calls (stream-ordered allocations stay on one stream)
+_SLOTS = {}        # (device index, chunk shape) -> three device input slots
+
+
+def stream_host_batches(op, host_in, host_out=None, chunk_tiles=0, device=None):
     """``host_out[i] = op(host_in[i])`` tile batch by tile batch with copies and compute overlapped.
 
     op: callable taking and returning a uint8 [b,H,W,3] CUDA tensor (e.g. ``lambda x: rein.transform(hed.transform(x))``).
-    host_in / host_out: uint8 [B,H,W,3] CPU tensors, pinned for full speed.  Returns host_out."""
+    host_in / host_out: uint8 [B,H,W,3] CPU tensors, pinned for full speed.  chunk_tiles = 0 picks ~96 MB chunks: the
+    per-chunk cost of the Python-level operator calls (~0.2 ms) wants chunks of at least tens of MB.  Returns host_out."""
     _, idx = nv.get_handle(device)
     dev = torch.device("cuda", idx)
     if host_out is None:
         host_out = torch.empty_like(host_in, pin_memory=host_in.is_pinned())
     B = host_in.shape[0]
-    s_in, s_comp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    tile_bytes = int(host_in[0].numel())
+    if chunk_tiles <= 0:
+        chunk_tiles = max(1, (96 << 20) // tile_bytes)
+    chunk_tiles = min(chunk_tiles, B)
+    if idx not in _STREAMS:
+        _STREAMS[idx] = tuple(torch.cuda.Stream(dev) for _ in range(3))
+    s_in, s_comp, s_out = _STREAMS[idx]
     n_slot = 3
-    d_in = [torch.empty((chunk_tiles,) + tuple(host_in.shape[1:]), dtype=torch.uint8, device=dev) for _ in range(n_slot)]
+    key = (idx, (chunk_tiles,) + tuple(host_in.shape[1:]))
+    if key not in _SLOTS:
+        _SLOTS.clear()                                  # one geometry at a time: do not hoard device memory
+        _SLOTS[key] = [torch.empty(key[1], dtype=torch.uint8, device=dev) for _ in range(n_slot)]
+    d_in = _SLOTS[key]
     d_out = [None] * n_slot
     ev_in = [torch.cuda.Event() for _ in range(n_slot)]
     ev_comp = [torch.cuda.Event() for _ in range(n_slot)]
     ev_out = [torch.cuda.Event() for _ in range(n_slot)]
+    cur = torch.cuda.current_stream(dev)
+    for s in (s_in, s_comp, s_out):
+        s.wait_stream(cur)                              # order behind whatever the caller queued (and earlier calls)
     for c, t0 in enumerate(range(0, B, chunk_tiles)):
         slot, nt = c % n_slot, min(chunk_tiles, B - t0)
         if c >= n_slot:
@@ -65,4 +83,5 @@ def stream_host_batches(op, host_in, host_out=None, chunk_tiles=16, device=None)
             ev_out[slot].record(s_out)
     s_out.synchronize()
     s_comp.synchronize()
+    s_in.synchronize()
     return host_out
