@@ -231,15 +231,9 @@ int sb_tissue_mask(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double
     sb::PointArgs a{};
     a.in = rgb; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb, mask, a.npx) && (a.npx % 16 == 0);
     a.tab = h->tab; a.ybound = mask_ybound_f(luminosity_threshold); a.mask_out = mask; a.status = status;
-    if (status) {
-        // preset every tile to EMPTY_MASK (int32 value 1); the kernel clears the bit when it sees tissue
-        std::vector<int32_t> ones((size_t)B, SB_STATUS_EMPTY_MASK);
-        SB_CUDA(cudaMemcpyAsync(status, ones.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
-        SB_CUDA(cudaStreamSynchronize(st));   // `ones` is pageable host memory
-    }
-    cudaError_t e = (cudaError_t)sb::launch_mask(a, h->num_sms, st);
+    cudaError_t e = (cudaError_t)sb::launch_mask(a, h->num_sms, st);     // presets status to EMPTY_MASK on the stream first
     if (e != cudaSuccess) return cuda_fail(e, "mask launch");
-    h->launches += 1;
+    h->launches += status ? 2 : 1;
     return SB_OK;
 }
 

@@ -271,6 +271,13 @@ __device__ __forceinline__ float od_lookup(const OdAbs& t, uint32_t w, uint32_t 
     return r;
 }
 __device__ __forceinline__ float od_lookup(const OdAbs* t, uint32_t w, uint32_t lane_off, int k) { return od_lookup(*t, w, lane_off, k); }
+// The two halves of a pair-table entry as separate 4-byte loads (same PRMT address, immediate offset): lets the od
+// values and the gamma values of two pixels land in adjacent registers for the packed f32x2 pipe.
+__device__ __forceinline__ void odg_lookup_split(const OdAbs& t, uint32_t w, int k, float& od, float& gam) {
+    const uint32_t addr = __byte_perm(w, t.lane_base, 0x6504u | (k << 4));
+    asm("ld.shared.f32 %0, [%1];" : "=f"(od) : "r"(addr));
+    asm("ld.shared.f32 %0, [%1+4];" : "=f"(gam) : "r"(addr));
+}
 // {od, gamma} pair table (8 bytes per lane, lane_base = lane << 3 | T >> 16 << 8): one LDS.64.
 __device__ __forceinline__ float2 odg_lookup_abs(const OdAbs& t, uint32_t w, int k) {
     const uint32_t addr = __byte_perm(w, t.lane_base, 0x6504u | (k << 4));

@@ -159,7 +159,14 @@ static dim3 point_grid(const PointArgs& a, int num_sms, int ctas_per_sm) {
     return dim3(a.B, spans);
 }
 
+__global__ void fill_i32_kernel(int32_t* p, int n, int32_t v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 int launch_mask(const PointArgs& a, int num_sms, cudaStream_t stream) {
+    // preset every tile to EMPTY_MASK; a CTA that sees tissue clears the bit (stream-ordered: no host synchronisation)
+    if (a.status) fill_i32_kernel<<<(a.B + 255) / 256, 256, 0, stream>>>(a.status, a.B, SB_STATUS_EMPTY_MASK);
     mask_kernel<<<point_grid(a, num_sms, 8), PT, 0, stream>>>(a);
     return (int)cudaGetLastError();
 }
@@ -208,22 +215,58 @@ struct AugOp {
         bits[1] = clip_u8_bits(ex2_approx(fmaf(c1, k.A[4], fmaf(c0, k.A[1], LOG2_255_UP))));
         bits[2] = clip_u8_bits(ex2_approx(fmaf(c1, k.A[5], fmaf(c0, k.A[2], LOG2_255_UP))));
     }
-    __device__ static void process(const Consts& k, const Params& p, const OdAbs tab, uint4* grp, Acc&) {
-        const uint4 va = grp[0], vb = grp[1], vc = grp[2];
-        const uint32_t w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
-        uint32_t o[12];
+    // Two pixels at a time on the packed f32x2 pipe, for unit-norm stain vectors (the compare-free LASSO of K4).
+    // px = {{od, gamma} of r, g, b} of pixel a (index 0..2) and pixel b (3..5), already split into od[] / gm[].
+    template <int LM>
+    __device__ static void pair(const Consts& k, const Params& p, const float (&od)[6], const float (&gm)[6], uint32_t* bits) {
+        float2 c0, c1;
+        lasso2_unit_pair<LM>(k.lk, f2(od[0], od[3]), f2(od[1], od[4]), f2(od[2], od[5]), c0, c1);
+        const float2 y = __ffma2_rn(dup(p.ycoef[2]), f2(gm[2], gm[5]), __ffma2_rn(dup(p.ycoef[1]), f2(gm[1], gm[4]), __fmul2_rn(dup(p.ycoef[0]), f2(gm[0], gm[3]))));
+        const bool ma = p.all_px | (y.x < p.ybound), mb = p.all_px | (y.y < p.ybound);
+        const float2 t0 = __ffma2_rn(c0, dup(k.alpha[0]), dup(k.beta[0])), t1 = __ffma2_rn(c1, dup(k.alpha[1]), dup(k.beta[1]));
+        c0 = f2(ma ? t0.x : c0.x, mb ? t0.y : c0.y);
+        c1 = f2(ma ? t1.x : c1.x, mb ? t1.y : c1.y);
+        const float2 L = dup(LOG2_255_UP);
+        const float2 e0 = __ffma2_rn(c1, dup(k.A[3]), __ffma2_rn(c0, dup(k.A[0]), L));
+        const float2 e1 = __ffma2_rn(c1, dup(k.A[4]), __ffma2_rn(c0, dup(k.A[1]), L));
+        const float2 e2 = __ffma2_rn(c1, dup(k.A[5]), __ffma2_rn(c0, dup(k.A[2]), L));
+        bits[0] = clip_u8_bits(ex2_approx(e0.x)); bits[1] = clip_u8_bits(ex2_approx(e1.x)); bits[2] = clip_u8_bits(ex2_approx(e2.x));
+        bits[3] = clip_u8_bits(ex2_approx(e0.y)); bits[4] = clip_u8_bits(ex2_approx(e1.y)); bits[5] = clip_u8_bits(ex2_approx(e2.y));
+    }
+    template <int LM>
+    __device__ static void group(const Consts& k, const Params& p, const OdAbs tab, const uint32_t (&w)[12], uint32_t (&o)[12]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
             uint32_t bits[12];
-            pixel(k, p, odg_lookup_abs(tab, wa, 0), odg_lookup_abs(tab, wa, 1), odg_lookup_abs(tab, wa, 2), bits);
-            pixel(k, p, odg_lookup_abs(tab, wa, 3), odg_lookup_abs(tab, wb, 0), odg_lookup_abs(tab, wb, 1), bits + 3);
-            pixel(k, p, odg_lookup_abs(tab, wb, 2), odg_lookup_abs(tab, wb, 3), odg_lookup_abs(tab, wc, 0), bits + 6);
-            pixel(k, p, odg_lookup_abs(tab, wc, 1), odg_lookup_abs(tab, wc, 2), odg_lookup_abs(tab, wc, 3), bits + 9);
+            if (LM == LASSO_GENERAL) {
+                pixel(k, p, odg_lookup_abs(tab, wa, 0), odg_lookup_abs(tab, wa, 1), odg_lookup_abs(tab, wa, 2), bits);
+                pixel(k, p, odg_lookup_abs(tab, wa, 3), odg_lookup_abs(tab, wb, 0), odg_lookup_abs(tab, wb, 1), bits + 3);
+                pixel(k, p, odg_lookup_abs(tab, wb, 2), odg_lookup_abs(tab, wb, 3), odg_lookup_abs(tab, wc, 0), bits + 6);
+                pixel(k, p, odg_lookup_abs(tab, wc, 1), odg_lookup_abs(tab, wc, 2), odg_lookup_abs(tab, wc, 3), bits + 9);
+            } else {
+                // pixels: p0=(a0,a1,a2) p1=(a3,b0,b1) p2=(b2,b3,c0) p3=(c1,c2,c3)
+                float od[6], gm[6];
+                odg_lookup_split(tab, wa, 0, od[0], gm[0]); odg_lookup_split(tab, wa, 1, od[1], gm[1]); odg_lookup_split(tab, wa, 2, od[2], gm[2]);
+                odg_lookup_split(tab, wa, 3, od[3], gm[3]); odg_lookup_split(tab, wb, 0, od[4], gm[4]); odg_lookup_split(tab, wb, 1, od[5], gm[5]);
+                pair<LM>(k, p, od, gm, bits);
+                odg_lookup_split(tab, wb, 2, od[0], gm[0]); odg_lookup_split(tab, wb, 3, od[1], gm[1]); odg_lookup_split(tab, wc, 0, od[2], gm[2]);
+                odg_lookup_split(tab, wc, 1, od[3], gm[3]); odg_lookup_split(tab, wc, 2, od[4], gm[4]); odg_lookup_split(tab, wc, 3, od[5], gm[5]);
+                pair<LM>(k, p, od, gm, bits + 6);
+            }
             o[3 * q] = pack4(bits[0], bits[1], bits[2], bits[3]);
             o[3 * q + 1] = pack4(bits[4], bits[5], bits[6], bits[7]);
             o[3 * q + 2] = pack4(bits[8], bits[9], bits[10], bits[11]);
         }
+    }
+    __device__ static void process(const Consts& k, const Params& p, const OdAbs tab, uint4* grp, Acc&) {
+        const uint4 va = grp[0], vb = grp[1], vc = grp[2];
+        const uint32_t w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
+        uint32_t o[12];
+        const int lm = lasso_mode_of(k.lk.rg00, k.lk.rg11, k.lk.g01);       // per tile: warp-uniform
+        if (lm == LASSO_UNIT_POS) group<LASSO_UNIT_POS>(k, p, tab, w, o);
+        else if (lm == LASSO_UNIT_NEG) group<LASSO_UNIT_NEG>(k, p, tab, w, o);
+        else group<LASSO_GENERAL>(k, p, tab, w, o);
         grp[0] = make_uint4(o[0], o[1], o[2], o[3]);
         grp[1] = make_uint4(o[4], o[5], o[6], o[7]);
         grp[2] = make_uint4(o[8], o[9], o[10], o[11]);
