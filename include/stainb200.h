@@ -114,6 +114,11 @@ int sb_slide_moments(sb_handle* h, const uint8_t* rgb, int B, int H, int W, doub
                      double* partials, void* stream);
 int sb_slide_angle_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold,
                         const double* V, int level, const unsigned* bins, unsigned long long* hist, void* stream);
+/*   sb_slide_dl_sums     one Vahadane dictionary pass: sparse codes of the tissue pixels (sample != 0: of the 1-in-16 sample
+ *                        groups of every tile) under the dictionary D (HOST double[6], rows = atoms); partials double
+ *                        [sb_slide_grid()][10] = (sum a a^T (00,01,11), sum x a_0 [3], sum x a_1 [3], pixel count). */
+int sb_slide_dl_sums(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold, const double* D,
+                     double dl_lambda, int sample, double* partials, void* stream);
 int sb_slide_conc_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, const double* M, double lasso_lambda,
                        int level, const unsigned* bins, unsigned long long* hist, void* stream);
 

@@ -25,7 +25,7 @@ EXPORTS = [
     "sb_launch_count", "sb_tissue_mask", "sb_extract", "sb_fit", "sb_normalize", "sb_normalize_host",
     "sb_concentrations", "sb_recombine", "sb_stain_augment", "sb_reinhard_stats", "sb_reinhard_transform",
     "sb_luminosity_standardize", "sb_hed_augment", "sb_grayscale_augment",
-    "sb_slide_grid", "sb_slide_moments", "sb_slide_angle_hist", "sb_slide_conc_hist", "sb_decode_jpeg",
+    "sb_slide_grid", "sb_slide_moments", "sb_slide_angle_hist", "sb_slide_conc_hist", "sb_slide_dl_sums", "sb_decode_jpeg",
 ]
 
 
@@ -94,6 +94,7 @@ def load_library():
         lib.sb_slide_moments.argtypes = [vp, vp, ci, ci, ci, cd, vp, vp]
         lib.sb_slide_angle_hist.argtypes = [vp, vp, ci, ci, ci, cd, vp, ci, vp, vp, vp]
         lib.sb_slide_conc_hist.argtypes = [vp, vp, ci, ci, ci, vp, cd, ci, vp, vp, vp]
+        lib.sb_slide_dl_sums.argtypes = [vp, vp, ci, ci, ci, cd, vp, cd, ci, vp, vp]
         for name in EXPORTS:
             if name not in ("sb_default_params", "sb_error_string", "sb_last_cuda_error", "sb_launch_count"):
                 getattr(lib, name).restype = ci

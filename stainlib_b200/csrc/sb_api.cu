@@ -308,6 +308,20 @@ int sb_slide_angle_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, d
     return SB_OK;
 }
 
+int sb_slide_dl_sums(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold, const double* D,
+                     double dl_lambda, int sample, double* partials, void* stream) {
+    sb::SlideArgs a;
+    int rc = slide_args(h, rgb, B, H, W, luminosity_threshold, a);
+    if (rc) return rc;
+    if (!D || !partials) return SB_ERR_ARG;
+    sb::make_lasso_consts(D, dl_lambda, a.lk);
+    a.sums = partials;
+    cudaError_t e = (cudaError_t)sb::launch_slide_pass(a, sample ? 6 : 5, sb::slide_grid(a, h->num_sms), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "slide dictionary pass launch");
+    h->launches += 1;
+    return SB_OK;
+}
+
 int sb_slide_conc_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, const double* M, double lasso_lambda,
                        int level, const unsigned* bins, unsigned long long* hist, void* stream) {
     sb::SlideArgs a;

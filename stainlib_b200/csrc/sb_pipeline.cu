@@ -1222,6 +1222,27 @@ __global__ void __launch_bounds__(SLIDE_NT, 2) slide_pass_kernel(SlideArgs a) {
                 cnt += c;
 #pragma unroll
                 for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
+            } else if (PASS == 5 || PASS == 6) {
+                // Vahadane dictionary pass: sparse codes of the tissue pixels (PASS 6: of the 1-in-16 sample groups of
+                // every tile) under the dictionary in lk; sums of a a^T (3) and x a^T (6), and the pixel count
+                if (PASS == 6 && !is_sample_group(g, npx / GROUP_PX)) continue;
+                float f[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) f[i] = 0.f;
+                unsigned c = 0;
+                for_each_px_odg(od_rep, lane_off, w, [&](int i, float2 r, float2 gg, float2 b) {
+                    float c0, c1;
+                    lasso2(lk, r.x, gg.x, b.x, c0, c1);
+                    const bool m = (i < nvalid) & (tissue_y(yc, r.y, gg.y, b.y) < yc.bound);
+                    c0 = m ? c0 : 0.f; c1 = m ? c1 : 0.f;
+                    c += m ? 1u : 0u;
+                    f[0] = fmaf(c0, c0, f[0]); f[1] = fmaf(c0, c1, f[1]); f[2] = fmaf(c1, c1, f[2]);
+                    f[3] = fmaf(r.x, c0, f[3]); f[4] = fmaf(gg.x, c0, f[4]); f[5] = fmaf(b.x, c0, f[5]);
+                    f[6] = fmaf(r.x, c1, f[6]); f[7] = fmaf(gg.x, c1, f[7]); f[8] = fmaf(b.x, c1, f[8]);
+                });
+                cnt += c;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
             } else if (PASS == 1 || PASS == 2) {
                 for_each_px_odg(od_rep, lane_off, w, [&](int i, float2 r, float2 gg, float2 b) {
                     const float px = fmaf(b.x, v02, fmaf(gg.x, v01, r.x * v00));
@@ -1255,7 +1276,7 @@ __global__ void __launch_bounds__(SLIDE_NT, 2) slide_pass_kernel(SlideArgs a) {
                 });
             }
         }
-        if (PASS != 0) {
+        if (PASS >= 1 && PASS <= 4) {
             // shared counters are 32-bit: a CTA flushes after every work item (65,536 pixels)
             __syncthreads();
             for (int i = threadIdx.x; i < 2 * L1_BINS; i += SLIDE_NT) {
@@ -1265,7 +1286,7 @@ __global__ void __launch_bounds__(SLIDE_NT, 2) slide_pass_kernel(SlideArgs a) {
             __syncthreads();
         }
     }
-    if (PASS == 0) {
+    if (PASS == 0 || PASS >= 5) {
         // per-CTA partial sums, added on the host in CTA order (fixed order for a fixed grid)
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -1311,7 +1332,9 @@ int launch_slide_pass(const SlideArgs& a, int pass, int grid, cudaStream_t strea
         case 1: return launch_slide_pass_t<1>(a, grid, stream);
         case 2: return launch_slide_pass_t<2>(a, grid, stream);
         case 3: return launch_slide_pass_t<3>(a, grid, stream);
-        default: return launch_slide_pass_t<4>(a, grid, stream);
+        case 4: return launch_slide_pass_t<4>(a, grid, stream);
+        case 5: return launch_slide_pass_t<5>(a, grid, stream);
+        default: return launch_slide_pass_t<6>(a, grid, stream);
     }
 }
 

@@ -76,9 +76,7 @@ class ExtractiveStainNormalizer(object):
         if slide is None:
             slide = (isinstance(target, (torch.Tensor, np.ndarray)) and target.ndim == 4 and target.shape[0] != 1)
         if slide:
-            if self._method != nv.SB_METHOD_MACENKO:
-                raise NotImplementedError("slide-level fit is implemented for method='macenko'")
-            from stainlib_b200.normalization.slide_fit import macenko_slide_fit
+            from stainlib_b200.normalization.slide_fit import macenko_slide_fit, vahadane_slide_fit
             tiles = None
             if isinstance(target, np.ndarray):
                 target = torch.from_numpy(np.ascontiguousarray(target))
@@ -86,8 +84,13 @@ class ExtractiveStainNormalizer(object):
                 assert target.dim() == 4 and is_uint8_image(target), "Image should be RGB uint8."
                 tiles = nv.Batch(target).dev
             p = self._params()
-            self.stain_matrix_target, self.maxC_target = macenko_slide_fit(
-                tiles, p.luminosity_threshold, p.angular_percentile, p.lasso_lambda, p.conc_percentile, group=group)
+            if self._method == nv.SB_METHOD_MACENKO:
+                self.stain_matrix_target, self.maxC_target = macenko_slide_fit(
+                    tiles, p.luminosity_threshold, p.angular_percentile, p.lasso_lambda, p.conc_percentile, group=group)
+            else:
+                self.stain_matrix_target, self.maxC_target = vahadane_slide_fit(
+                    tiles, p.luminosity_threshold, p.dl_lambda, p.dl_iters, p.dl_sample_iters, p.dl_anderson, p.lasso_lambda,
+                    p.conc_percentile, group=group)
             self._target = None
             return
         vec = torch.zeros(8, dtype=torch.float64)

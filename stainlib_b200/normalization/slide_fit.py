@@ -1,4 +1,4 @@
-"""Slide-level (multi-tile) Macenko fit -- SURVEY section 8-f rank 2.
+"""Slide-level (multi-tile) Macenko and Vahadane fit -- SURVEY section 8-f rank 2.
 
 ``ExtractiveStainNormalizer.fit`` (normalizer.py:27-36) fits ONE target image.  Whole-slide pipelines fit one stain
 matrix per slide from many tiles; this module computes exactly what the reference would return for the tiles
@@ -104,6 +104,19 @@ class SlidePasses(object):
             out = part.sum(dim=0)
         return out
 
+    def dl_sums(self, D, lam, sample):
+        """One dictionary pass under D (2x3, rows = atoms): float64 [10] = (A00, A01, A11, B[:,0] (3), B[:,1] (3), count)."""
+        out = torch.zeros(10, dtype=torch.float64, device=self.dev)
+        if self.tiles is not None:
+            T, H, W = self._shape()
+            grid = self.lib.sb_slide_grid(self.h, T, H, W)
+            part = torch.zeros(grid, 10, dtype=torch.float64, device=self.dev)
+            Dc = (ctypes.c_double * 6)(*[float(x) for x in np.asarray(D).reshape(6)])
+            nv.check(self.lib.sb_slide_dl_sums(self.h, nv.ptr(self.tiles), T, H, W, self.thr, Dc, float(lam), int(bool(sample)),
+                                               nv.ptr(part), nv.stream_ptr(self.idx)))
+            out = part.sum(dim=0)
+        return out
+
     def _hist(self, fn, *args):
         hist = torch.zeros(8192, dtype=torch.int64, device=self.dev)
         if self.tiles is not None:
@@ -165,7 +178,11 @@ def macenko_slide_fit(tiles, luminosity_threshold=0.8, angular_percentile=99.0, 
     v2 = vec @ np.array([math.cos(max_phi), math.sin(max_phi)])
     HE = np.array([v1, v2]) if v1[0] > v2[0] else np.array([v2, v1])
     M = HE / np.linalg.norm(HE, axis=1)[:, None]
-    # ---- passes 3 + 4: exact 99th percentile of each concentration over ALL pixels
+    return M, _conc_percentiles(sp, M, n_all, conc_percentile, group)
+
+
+def _conc_percentiles(sp, M, n_all, conc_percentile, group):
+    """Passes 3 + 4: exact ``conc_percentile`` of each concentration over ALL pixels of the slide -> maxC (1x2)."""
     lo, hi, fr = percentile_index(n_all, conc_percentile)
     c1 = _all_reduce(sp.conc_hist(M, 1), group).cpu().numpy().reshape(2, 1 << L1_BITS)
     loc = [_locate(c1[0], lo), _locate(c1[0], hi), _locate(c1[1], lo), _locate(c1[1], hi)]
@@ -174,5 +191,103 @@ def macenko_slide_fit(tiles, luminosity_threshold=0.8, angular_percentile=99.0, 
     for q, (b, rem) in enumerate(loc):
         low, _ = _locate(c2[q], rem)
         cv.append(conc_from_key((b << L2_BITS) | low))
-    maxC = np.array([[lerp_np(cv[0], cv[1], fr), lerp_np(cv[2], cv[3], fr)]])
-    return M, maxC
+    return np.array([[lerp_np(cv[0], cv[1], fr), lerp_np(cv[2], cv[3], fr)]])
+
+
+# ------------------------------------------------------------------------------------------------- Vahadane, slide level
+RUIFROK_HE = np.array([[0.65, 0.70, 0.29], [0.07, 0.99, 0.11]], dtype=np.float64)
+DL_SAMPLE_TOL, DL_FULL_TOL = 1e-4, 2e-6          # csrc/sb_pipeline.cu
+
+
+def _dict_update(D, t):
+    """One block-coordinate sweep of Mairal et al. 2010, Alg. 2 with non-negativity and the unit ball (thread 0 of the
+    tile kernel).  D: 2x3 (rows = atoms); t = the ten sums of a dictionary pass."""
+    A = np.array([[t[0], t[1]], [t[1], t[2]]])
+    Bm = np.array([t[3:6], t[6:9]])                      # rows = atoms
+    D = D.copy()
+    for j in range(2):
+        if A[j, j] > 1e-12:
+            u = (Bm[j] - A[0, j] * D[0] - A[1, j] * D[1]) / A[j, j] + D[j]
+            u = np.maximum(u, 0.0)
+            D[j] = u / max(np.linalg.norm(u), 1.0)
+    return D
+
+
+class _Anderson(object):
+    """Type-II Anderson acceleration of the 6-component map, as csrc/sb_device.cuh: aa_step."""
+
+    def __init__(self, m):
+        self.m, self.dx, self.dr, self.px, self.pr, self.last = m, [], [], None, None, -1.0
+
+    def carry(self):
+        self.px, self.pr, self.last = None, None, -1.0
+
+    def step(self, D, FD):
+        x, r = D.reshape(-1).copy(), (FD - D).reshape(-1)
+        rn = float(np.sqrt((r * r).sum()))
+        if self.m <= 0:
+            return FD.copy()
+        if self.last >= 0.0 and rn > self.last:
+            self.dx, self.dr, self.px, self.pr = [], [], None, None
+        self.last = rn
+        if self.px is not None:
+            self.dx.append(x - self.px)
+            self.dr.append(r - self.pr)
+            if len(self.dx) > self.m:
+                self.dx.pop(0)
+                self.dr.pop(0)
+        self.px, self.pr = x, r.copy()
+        h = len(self.dx)
+        if h < 1:
+            return FD.copy()
+        G = np.array([[float((self.dr[i] * self.dr[j]).sum()) for j in range(h)] for i in range(h)])
+        tr = float(np.trace(G))
+        if not (tr > 0.0 and np.isfinite(tr)):
+            return FD.copy()
+        try:
+            gam = np.linalg.solve(G + 1e-10 * tr * np.eye(h), np.array([float((self.dr[i] * r).sum()) for i in range(h)]))
+        except np.linalg.LinAlgError:
+            return FD.copy()
+        xn = x + r - sum(gam[i] * (self.dx[i] + self.dr[i]) for i in range(h))
+        if not np.all(np.isfinite(xn)):
+            return FD.copy()
+        Dn = np.maximum(xn, 0.0).reshape(D.shape)
+        return Dn / np.maximum(np.sqrt((Dn * Dn).sum(axis=1)), 1.0)[:, None]
+
+
+def vahadane_slide_fit(tiles, luminosity_threshold=0.8, dl_lambda=0.1, dl_iters=10, dl_sample_iters=12, dl_anderson=4,
+                       lasso_lambda=0.01, conc_percentile=99.0, group=None, device=None, passes=None):
+    """Vahadane stain matrix (2x3) and maxC (1x2) of the union of ``tiles`` over all ranks of ``group``: the dictionary
+    iteration of the tile kernel (sample warm start, Anderson acceleration, residual stopping rules) with each pass's
+    ten sums all-reduced, the sample being the union of the tiles' own 1-in-16 samples."""
+    sp = passes if passes is not None else SlidePasses(tiles, luminosity_threshold, lasso_lambda, device)
+    n_px = torch.tensor([sp.n_pixels()], dtype=torch.float64, device=sp.dev)
+    n_all = int(round(float(_all_reduce(n_px, group).item())))
+    D = RUIFROK_HE / np.linalg.norm(RUIFROK_HE, axis=1)[:, None]
+    aa = _Anderson(dl_anderson)
+    n_tissue = None
+    phases = ([(True, dl_sample_iters)] if dl_sample_iters > 0 else []) + [(False, dl_iters)]
+    k = 0
+    while k < len(phases):
+        sample, n_it = phases[k]
+        k += 1
+        aa.carry()
+        for it in range(n_it):
+            t = _all_reduce(sp.dl_sums(D, dl_lambda, sample), group).cpu().numpy()
+            if sample and it == 0 and t[9] < 1024.0:              # sample too small: four more full passes instead
+                phases[k] = (False, dl_iters + 4)
+                aa = _Anderson(dl_anderson)
+                break
+            if not sample:
+                n_tissue = t[9]
+                if n_tissue < 1.0:
+                    raise TissueMaskException("Empty tissue mask computed")
+            FD = _dict_update(D, t)
+            stop = dl_anderson > 0 and float(np.sqrt(((FD - D) ** 2).sum())) < (DL_SAMPLE_TOL if sample else DL_FULL_TOL)
+            D = aa.step(D, FD)
+            if stop:
+                break
+    if D[0, 0] < D[1, 0]:                                          # vahadane_stain_extractor.py:38-43
+        D = D[[1, 0]]
+    M = D / np.linalg.norm(D, axis=1)[:, None]
+    return M, _conc_percentiles(sp, M, n_all, conc_percentile, group)

@@ -51,9 +51,21 @@ def test_slide_fit_numpy_batch_and_errors(sb):
     n = sb.ExtractiveStainNormalizer("macenko")
     with pytest.raises(TissueMaskException):
         n.fit(np.full((3, 64, 64, 3), 255, np.uint8))
-    with pytest.raises(NotImplementedError):
-        sb.ExtractiveStainNormalizer("vahadane").fit(np.stack([synth_tile(i, 64) for i in range(2)]))
     tiles = np.stack([synth_tile(90 + i, 64) for i in range(3)])
     n.fit(tiles)                                              # numpy [T,H,W,3] works as well
     o = _oracle_fit(tiles)
     np.testing.assert_allclose(n.stain_matrix_target, o.stain_matrix_target, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape,T", [((256, 256), 6), ((160, 176), 4), ((61, 53), 5)])
+def test_vahadane_slide_fit_vs_oracle(sb, shape, T):
+    from test_slide_fit_cpu import oracle_vahadane_slide
+    tiles = np.stack([synth_tile(120 + i, *shape) for i in range(T)])
+    tiles[-1] = 255
+    n = sb.ExtractiveStainNormalizer("vahadane")
+    n.fit(torch.from_numpy(tiles).cuda())
+    M_ref, C_ref = oracle_vahadane_slide(list(tiles))
+    np.testing.assert_allclose(n.stain_matrix_target, M_ref, rtol=0, atol=1e-4)
+    np.testing.assert_allclose(n.maxC_target, C_ref, rtol=1e-3)
+    src = synth_tile(3, 128)
+    assert n.transform(src).shape == src.shape

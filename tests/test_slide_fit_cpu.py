@@ -74,6 +74,24 @@ class NumpyPasses(object):
         px, py = x @ V[:3], x @ V[3:]
         return self._hists([self._angle_key(px.astype(np.float32), py.astype(np.float32))], level, bins)
 
+    def dl_sums(self, D, lam, sample):
+        so = self.so
+        od = self.od.astype(np.float64)
+        sel = self.mask.copy()
+        if sample:
+            keep = np.zeros(len(od), bool)
+            off = 0
+            for t in self.tiles if self.tiles is not None else []:
+                n = t.shape[0] * t.shape[1]
+                keep[off + so.dl_sample_indices(n)] = True
+                off += n
+            sel &= keep
+        X = od[sel].T
+        Al = so.lasso_pos2(X, np.asarray(D, np.float64).reshape(2, 3).T, lam) if X.shape[1] else np.zeros((2, 0))
+        A, Bm = Al @ Al.T, X @ Al.T
+        return torch.tensor([A[0, 0], A[0, 1], A[1, 1], Bm[0, 0], Bm[1, 0], Bm[2, 0], Bm[0, 1], Bm[1, 1], Bm[2, 1], float(X.shape[1])],
+                            dtype=torch.float64)
+
     def conc_hist(self, M, level, bins=None):
         C = self.so.lasso_pos2(self.od.astype(np.float64).T, np.asarray(M, np.float64).reshape(2, 3).T, self.lam) if len(self.od) else np.zeros((2, 0))
         return self._hists([self._conc_key(C[0]), self._conc_key(C[1])], level, bins)
@@ -159,3 +177,34 @@ def test_key_inverses_roundtrip():
     c = np.array([0.0, 1e-3, 0.5, 1.5, 4.0, 9.0])
     back = np.array([conc_from_key(int(k)) for k in NumpyPasses._conc_key(c)])
     assert np.abs(back - c).max() < 2e-5
+
+
+def oracle_vahadane_slide(tiles):
+    """What the reference-style learner returns for the union of the tiles: the oracle's accelerated schedule on all
+    tissue pixels, warm-started on the union of the tiles' own samples; then maxC on the concatenated image."""
+    from oracle import stain_oracle as so
+    Xs, X = [], []
+    for t in tiles:
+        od = so.convert_RGB_to_OD(t).reshape(-1, 3)
+        m = so_has_tissue(so, t, 0.8) and so.get_tissue_mask(t).reshape(-1)
+        if m is False:
+            continue
+        X.append(od[m])
+        si = so.dl_sample_indices(len(od))
+        Xs.append(od[si[m[si]]])
+    D = so.train_dl_accel(np.concatenate(X).T, np.concatenate(Xs).T)
+    M = so.vahadane_finish(D.T)
+    big = np.concatenate(list(tiles), axis=0)
+    C = so.get_concentrations(big, M)
+    return M, np.percentile(C, 99, axis=0).reshape(1, 2)
+
+
+def test_vahadane_slide_fit_host_logic():
+    sys.path.insert(0, ROOT)
+    from stainlib_b200.synth import synth_tile
+    from stainlib_b200.normalization.slide_fit import vahadane_slide_fit
+    tiles = [synth_tile(40 + i, 160, 176) for i in range(3)] + [np.full((160, 176, 3), 255, np.uint8)]
+    M, maxC = vahadane_slide_fit(None, passes=NumpyPasses(tiles))
+    M_ref, C_ref = oracle_vahadane_slide(tiles)
+    np.testing.assert_allclose(M, M_ref, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(maxC, C_ref, rtol=1e-4)
