@@ -477,7 +477,7 @@ def main():
             "dtype": "f32 per-pixel arithmetic on u8 pixels, f64 per-tile reductions", "data": "synthetic",
             "config": {"workload": desc, "tiles_per_gpu": B, "tile": [H, W], "method": method,
                        "l2_policy": f"input {host_in.numel() / 1e6:.0f} MB + output per GPU, larger than the 126 MB L2; no flush needed",
-                       "flagged_tiles": status_bad, "kernels_per_step": "tile_pipeline_kernel + k4_prepare_normalize_kernel + recombine_tma_kernel"},
+                       "flagged_tiles": status_bad, "kernels_per_step": "tile_pipeline_kernel + k4_prepare_normalize_kernel + ring_pointwise_kernel<K4Op>"},
             "clocks": clocks.summary(),
             "e2e": e2e,
             "gpu_launches": int(launches),
@@ -486,10 +486,10 @@ def main():
                          "achieved": round(stats_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(stats_gbs / peak, 4),
                          "peak_source": peak_src, "algorithmic_bytes_per_px": 3.0, "launch_ms": round(stats_ms, 4),
                          "share_of_step": round(stats_ms / med_step_ms, 3), "traffic": ncu_traffic(args.workload, "tile_pipeline_kernel")},
-            "roofline_k4": {"bound": "hbm", "kernel": "recombine_tma_kernel (fused OD+recombine, TMA ring)",
+            "roofline_k4": {"bound": "hbm", "kernel": "ring_pointwise_kernel<K4Op> (fused OD+recombine on the TMA ring)",
                             "achieved": round(k4_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(k4_gbs / peak, 4),
                             "algorithmic_bytes_per_px": BYTES_PER_PX, "launch_ms": round(k4_ms, 4), "share_of_step": round(k4_ms / med_step_ms, 3),
-                            "bytes_equal_transform_path": k4_match, "traffic": ncu_traffic(args.workload, "recombine_tma_kernel")},
+                            "bytes_equal_transform_path": k4_match, "traffic": ncu_traffic(args.workload, "ring_pointwise_kernel<K4Op>")},
             "roofline_step": {"bound": "hbm", "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(step_gbs / peak, 4),
                               "algorithmic_bytes_per_px": BYTES_PER_PX, "step_ms_median": round(med_step_ms, 4)},
             "hbm_probe_gbs": round(hbm_probe, 1),

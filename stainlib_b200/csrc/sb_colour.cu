@@ -442,7 +442,9 @@ struct HedOp {
         bits[4] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e1.y), 1.f, -2.f), 255.f, 8388608.f));
         bits[5] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e2.y), 1.f, -2.f), 255.f, 8388608.f));
     }
-    __device__ static void process(const Consts& k, const Params&, const OdAbs tab, uint4* grp, Acc& acc) {
+    struct Run {};
+    __device__ static Run begin_run(const Consts&, const Params&) { return Run{}; }
+    __device__ static void process(const Consts& k, const Params&, const Run&, const OdAbs tab, uint4* grp, Acc& acc) {
         const uint4 va = grp[0], vb = grp[1], vc = grp[2];
         const uint32_t w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
         uint32_t o[12];
@@ -538,7 +540,9 @@ struct GrayOp {
     static constexpr int kLaneShift = 2;
     __device__ static void fill_table(unsigned char*, const Params&, int, int) {}
     __device__ static void acc_init(Acc&) {}
-    __device__ static void process(const Consts& k, const Params&, const OdAbs, uint4* grp, Acc&) {
+    struct Run {};
+    __device__ static Run begin_run(const Consts&, const Params&) { return Run{}; }
+    __device__ static void process(const Consts& k, const Params&, const Run&, const OdAbs, uint4* grp, Acc&) {
         const uint4 va = grp[0], vb = grp[1], vc = grp[2];
         const uint32_t w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
         const float kr = (float)(0.2125 / 255.0), kg = (float)(0.7154 / 255.0), kb = (float)(0.0721 / 255.0);

@@ -259,11 +259,12 @@ struct AugOp {
             o[3 * q + 2] = pack4(bits[8], bits[9], bits[10], bits[11]);
         }
     }
-    __device__ static void process(const Consts& k, const Params& p, const OdAbs tab, uint4* grp, Acc&) {
+    using Run = int;                                                         // the tile's LASSO mode
+    __device__ static Run begin_run(const Consts& k, const Params&) { return lasso_mode_of(k.lk.rg00, k.lk.rg11, k.lk.g01); }
+    __device__ static void process(const Consts& k, const Params& p, const Run& lm, const OdAbs tab, uint4* grp, Acc&) {
         const uint4 va = grp[0], vb = grp[1], vc = grp[2];
         const uint32_t w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
         uint32_t o[12];
-        const int lm = lasso_mode_of(k.lk.rg00, k.lk.rg11, k.lk.g01);       // per tile: warp-uniform
         if (lm == LASSO_UNIT_POS) group<LASSO_UNIT_POS>(k, p, tab, w, o);
         else if (lm == LASSO_UNIT_NEG) group<LASSO_UNIT_NEG>(k, p, tab, w, o);
         else group<LASSO_GENERAL>(k, p, tab, w, o);

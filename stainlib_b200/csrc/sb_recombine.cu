@@ -66,12 +66,10 @@ __global__ void __launch_bounds__(RT, 3) recombine_v2_kernel(PointArgs a, const 
     }
 }
 
-// ------------------------------------------------------------------------------------------- K4 v3: TMA-staged ring
-// Persistent CTAs (one per SM).  A tile is cut into chunks of TT*48 bytes; thread 0 streams chunks HBM -> shared memory
-// with cp.async.bulk (TMA, 1-D) completing on an mbarrier per stage, every thread recombines its own 48-byte group IN
-// PLACE in shared memory, and the chunk leaves with one bulk store.  Loads run NSTAGE-1 chunks ahead of the math, both
-// directions are fully coalesced by the copy engine, and no thread ever waits on a global load.
-// Template parameters: TT compute threads (+ one producer warp), NSTAGE ring slots of TT*48 bytes.
+// ------------------------------------------------------------------------------------------- K4 on the TMA-staged ring
+// The transport (persistent CTAs, cp.async.bulk loads into a 6-slot shared-memory ring, in-place transform, bulk store,
+// 64 KB-aligned lookup table) lives in sb_ring.cuh; K4 is its K4Op.  Measured alternatives with more resident warps
+// (2 x 480, 3 x 320, 3 x 256 consumer threads): 0.36-0.42 ms against 0.33 ms -- the kernel is issue-bound, not latency-bound.
 
 // Per-tile constants for sb_recombine: source matrices + scales given by the caller.
 __global__ void k4_prepare_kernel(PointArgs a, K4Consts* out) {
@@ -121,156 +119,42 @@ __device__ __forceinline__ void recombine_group_smem(const K4Consts& k, const Od
     grp[2] = make_uint4(o[8], o[9], o[10], o[11]);
 }
 
-// Shared-memory plan of the TMA kernel.  The CTA asks for the whole 227 KB; the 64 KB lane-replicated OD table is put
-// at the 64 KB-aligned address inside the window (so lookups need no address add), the mbarriers at the window start,
-// and the ring slots fill the space in front of and behind the table.
-constexpr int K4_SMEM_BYTES = 227 * 1024;
-constexpr int K4_BAR_BYTES = 256;
-
-// Template parameters: NG consumer groups of GT threads (+ one producer warp), NSTAGE ring slots of GT*48 bytes.  Group
-// g recombines the CTA's chunks g, g+NG, ...: two groups of 15 warps keep 30 warps resident (the 16-pixel body needs
-// 56 registers when the compiler is held to that occupancy) and work on different slots at different phases.
-template <int GT, int NG, int NSTAGE>
-__global__ void __launch_bounds__(GT * NG + 32, 1) recombine_tma_kernel(PointArgs a, const K4Consts* __restrict__ consts, int chunks_per_tile, long long total_chunks) {
-    constexpr int TT = GT * NG;
-    constexpr int TT_ALL = TT + 32;
-    constexpr int CHUNK_BYTES = GT * 48;
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const uint32_t base = smem_u32(smem);
-    const uint32_t tab_addr = (base + 0xFFFFu) & ~0xFFFFu;
-    unsigned char* od_rep = smem + (tab_addr - base);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                            // TMA load landed
-    uint64_t* done = full + NSTAGE;                                                // all compute warps wrote the stage back
-    const int n_front = tab_addr - base >= (uint32_t)K4_BAR_BYTES ? (int)((tab_addr - base - K4_BAR_BYTES) / CHUNK_BYTES) : 0;
-    const int n_back = ((int)K4_SMEM_BYTES - (int)(tab_addr - base) - OD_REP_BYTES) / CHUNK_BYTES;
-    if (n_front + n_back < NSTAGE || tab_addr - base < (uint32_t)K4_BAR_BYTES) __trap();   // launch_tma_variant sized the window for this
-    auto stage_ptr = [&](int s) -> unsigned char* {
-        return s < n_front ? smem + K4_BAR_BYTES + (size_t)s * CHUNK_BYTES : od_rep + OD_REP_BYTES + (size_t)(s - n_front) * CHUNK_BYTES;
-    };
-    const size_t tile_bytes = (size_t)a.npx * 3;
-    const long long c_begin = total_chunks * blockIdx.x / gridDim.x, c_end = total_chunks * (blockIdx.x + 1) / gridDim.x;
-    const int n_local = (int)(c_end - c_begin);
-
-    auto chunk_geom = [&](long long c, int& tile, size_t& off, uint32_t& bytes) {
-        tile = (int)(c / chunks_per_tile);
-        off = (size_t)(c % chunks_per_tile) * CHUNK_BYTES;
-        const size_t rem = tile_bytes - off;
-        bytes = (uint32_t)(rem < (size_t)CHUNK_BYTES ? rem : (size_t)CHUNK_BYTES);
-    };
-
-    if (threadIdx.x == TT) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], GT / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+// K4 as an Op of the generic ring (sb_ring.cuh).
+struct K4RingParams { const K4Consts* consts; const float* od; int copy_only; };
+struct K4Op {
+    using Consts = K4Consts;
+    using Params = K4RingParams;
+    struct Acc {};
+    static constexpr int kLaneShift = 2;
+    __device__ static void fill_table(unsigned char* tab, const Params& p, int tid, int n) {
+        for (int i = tid; i < 256 * 32; i += n)
+            *reinterpret_cast<float*>(tab + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = p.od[i >> 5];
     }
-    for (int i = threadIdx.x; i < 256 * 32; i += TT_ALL)
-        *reinterpret_cast<float*>(od_rep + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = a.tab.od[i >> 5];
-    __syncthreads();
-
-    if (threadIdx.x >= TT) {
-        // ------------------------------------------------------------------ producer warp (one elected lane)
-        if (threadIdx.x == TT) {
-            for (int i = 0; i < NSTAGE && i < n_local; ++i) {
-                int tile; size_t off; uint32_t bytes;
-                chunk_geom(c_begin + i, tile, off, bytes);
-                mbar_expect_tx(&full[i], bytes);
-                bulk_load(stage_ptr(i), a.in + (size_t)tile * tile_bytes + off, bytes, &full[i]);
-            }
-            for (int i = 0; i < n_local; ++i) {
-                const int s = i % NSTAGE;
-                int tile; size_t off; uint32_t bytes;
-                chunk_geom(c_begin + i, tile, off, bytes);
-                mbar_wait(&done[s], (uint32_t)((i / NSTAGE) & 1));          // stage s holds the finished output of chunk i
-                bulk_store(a.out + (size_t)tile * tile_bytes + off, stage_ptr(s), bytes);
-                // refill the stage of chunk i-1 once its store has finished reading shared memory
-                if (i >= 1 && i - 1 + NSTAGE < n_local) {
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    const int ps = (i - 1) % NSTAGE;
-                    int t2; size_t o2; uint32_t b2;
-                    chunk_geom(c_begin + i - 1 + NSTAGE, t2, o2, b2);
-                    mbar_expect_tx(&full[ps], b2);
-                    bulk_load(stage_ptr(ps), a.in + (size_t)t2 * tile_bytes + o2, b2, &full[ps]);
-                }
-            }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __device__ static void acc_init(Acc&) {}
+    using Run = int;                 // code variant of the tile: wrap check x LASSO mode, zero fill, copy through
+    __device__ static Run begin_run(const Consts& k, const Params& p) {
+        return (p.copy_only || k.mode == 2) ? 7 : (k.mode == 1 ? 6 : (k.need_check ? 3 : 0) + k.lasso_mode);
+    }
+    __device__ static void process(const Consts& k, const Params&, const Run& variant, const OdAbs tab, uint4* grp, Acc&) {
+        switch (variant) {
+            case 0: recombine_group_smem<false, LASSO_GENERAL>(k, tab, grp); break;
+            case 1: recombine_group_smem<false, LASSO_UNIT_POS>(k, tab, grp); break;
+            case 2: recombine_group_smem<false, LASSO_UNIT_NEG>(k, tab, grp); break;
+            case 3: recombine_group_smem<true, LASSO_GENERAL>(k, tab, grp); break;
+            case 4: recombine_group_smem<true, LASSO_UNIT_POS>(k, tab, grp); break;
+            case 5: recombine_group_smem<true, LASSO_UNIT_NEG>(k, tab, grp); break;
+            case 6: grp[0] = grp[1] = grp[2] = make_uint4(0, 0, 0, 0); break;
+            default: break;
         }
-        return;
     }
-    // ---------------------------------------------------------------------- compute warps
-    const OdAbs tab{((threadIdx.x & 31u) << 2) | ((tab_addr >> 16) << 8)};
-    const bool copy_only = a.debug_copy != 0;
-    const int gidx = threadIdx.x / GT, tig = threadIdx.x - gidx * GT;
-    int i = gidx;
-    while (i < n_local) {
-      // run of this group's chunks that belong to one tile: constants are loaded once per run
-      const int i0 = i;
-      const int tile = (int)((c_begin + i0) / chunks_per_tile);
-      const int first_in_tile = (int)((c_begin + i0) - (long long)tile * chunks_per_tile);
-      int i_last = i0 + (chunks_per_tile - 1 - first_in_tile);
-      if (i_last > n_local - 1) i_last = n_local - 1;
-      const K4Consts k = consts[tile];
-      const int variant = (copy_only || k.mode == 2) ? 7 : (k.mode == 1 ? 6 : (k.need_check ? 3 : 0) + k.lasso_mode);
-      for (; i <= i_last; i += NG) {
-        const size_t off = (size_t)(first_in_tile + (i - i0)) * CHUNK_BYTES;
-        const int s = i % NSTAGE;
-        const uint32_t parity = (uint32_t)((i / NSTAGE) & 1);
-        const size_t rem = tile_bytes - off;
-        const uint32_t bytes = (uint32_t)(rem < (size_t)CHUNK_BYTES ? rem : (size_t)CHUNK_BYTES);
-        unsigned char* buf = stage_ptr(s);
-        mbar_wait(&full[s], parity);
-        if (tig * 48u < bytes) {
-            uint4* grp = reinterpret_cast<uint4*>(buf + tig * 48u);
-            switch (variant) {
-                case 0: recombine_group_smem<false, LASSO_GENERAL>(k, tab, grp); break;
-                case 1: recombine_group_smem<false, LASSO_UNIT_POS>(k, tab, grp); break;
-                case 2: recombine_group_smem<false, LASSO_UNIT_NEG>(k, tab, grp); break;
-                case 3: recombine_group_smem<true, LASSO_GENERAL>(k, tab, grp); break;
-                case 4: recombine_group_smem<true, LASSO_UNIT_POS>(k, tab, grp); break;
-                case 5: recombine_group_smem<true, LASSO_UNIT_NEG>(k, tab, grp); break;
-                case 6: grp[0] = grp[1] = grp[2] = make_uint4(0, 0, 0, 0); break;
-                default: break;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk store
-        }
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(&done[s]);
-      }
-    }
-}
-
-template <int GT, int NG, int NSTAGE>
-static int launch_tma_variant(const PointArgs& a, int num_sms, cudaStream_t stream, const K4Consts* consts) {
-    constexpr int CHUNK_BYTES = GT * 48;
-    static_assert(GT % 32 == 0 && GT * NG + 32 <= 1024, "block size");
-    // the table must sit on a 64 KB boundary of the shared window wherever the window starts: take the whole 227 KB
-    static_assert(OD_REP_BYTES + NSTAGE * CHUNK_BYTES + 1024 + K4_BAR_BYTES <= K4_SMEM_BYTES, "ring does not fit");
-    static_assert(2 * NSTAGE * 8 <= K4_BAR_BYTES, "barrier area");
-    const int smem_bytes = K4_SMEM_BYTES;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(recombine_tma_kernel<GT, NG, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        if (e != cudaSuccess) return (int)e;
-        attr = true;
-    }
-    const size_t tile_bytes = (size_t)a.npx * 3;
-    const int cpt = (int)((tile_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES);
-    const long long total = (long long)cpt * a.B;
-    int grid = num_sms;
-    if ((long long)grid > total) grid = (int)total;
-    recombine_tma_kernel<GT, NG, NSTAGE><<<grid, GT * NG + 32, smem_bytes, stream>>>(a, consts, cpt, total);
-    return (int)cudaGetLastError();
-}
+    __device__ static void finish_run(const Params&, int, Acc&) {}
+};
 
 // Runs K4 over the batch with the given per-tile constants: TMA ring when every tile is a whole number of 16-byte
 // vectors at a 16-byte aligned address, register-staged kernel otherwise.
 static int launch_k4(const PointArgs& a, int num_sms, cudaStream_t stream, const K4Consts* consts, bool use_tma) {
-    if (use_tma) {
-        // ring geometry: 512 compute threads x 6 slots of 24 KB (chunks divide 256^2 and 512^2 tiles evenly); two slots sit
-        // in front of the 64 KB-aligned table, four behind it
-        // (measured alternatives, 1024 x 512^2 tiles: 2 groups x 480 threads 0.420 ms, 3 x 320 0.358 ms, 3 x 256 0.404 ms,
-        //  1 x 512 0.357 ms -- more resident warps do not help, the kernel is issue-bound, not latency-bound)
-        return launch_tma_variant<512, 1, 6>(a, num_sms, stream, consts);
-    }
+    if (use_tma)   // 512 compute threads x 6 slots of 24 KB (chunks divide 256^2 and 512^2 tiles evenly) on the generic ring
+        return launch_ring<K4Op>(RingGeom{a.in, a.out, a.B, a.npx}, K4RingParams{consts, a.tab.od, a.debug_copy}, num_sms, stream);
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(recombine_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OD_REP_BYTES);

@@ -14,7 +14,8 @@
 //   Acc                     per-thread accumulator carried over a run (e.g. a byte sum)
 //   kLaneShift              log2 of the table entry size per lane (2: float, 3: float2)
 //   fill_table(tab, p, tid, n)   all n threads fill the 64 KB table
-//   process(k, p, tab, grp, acc) transform the 48-byte group at grp (3 x uint4 in shared memory) in place
+//   Run / begin_run(k, p)        per-run state derived once from the tile's constants (e.g. which code variant to run)
+//   process(k, p, run, tab, grp, acc)  transform the 48-byte group at grp (3 x uint4 in shared memory) in place
 //   finish_run(p, tile, acc)     called by every compute thread when the CTA leaves a tile (warp collectives allowed)
 #pragma once
 #include "sb_kernels.h"
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(GT + 32, 1) ring_pointwise_kernel(RingGeom g, 
         int run = chunks_per_tile - first_in_tile;
         if (run > n_local - i) run = n_local - i;
         const typename Op::Consts k = p.consts[tile];
+        const typename Op::Run rs = Op::begin_run(k, p);
         for (int j = 0; j < run; ++j, ++i) {
             const int s = i % NSTAGE;
             const uint32_t parity = (uint32_t)((i / NSTAGE) & 1);
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(GT + 32, 1) ring_pointwise_kernel(RingGeom g, 
             unsigned char* buf = stage_ptr(s);
             mbar_wait(&full[s], parity);
             if (threadIdx.x * 48u < bytes) {
-                Op::process(k, p, tab, reinterpret_cast<uint4*>(buf + threadIdx.x * 48u), acc);
+                Op::process(k, p, rs, tab, reinterpret_cast<uint4*>(buf + threadIdx.x * 48u), acc);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk store
             }
             __syncwarp();

@@ -3,6 +3,7 @@ instruction mix per pixel, and profiles/traffic.json (dram bytes per launch, rea
 
 usage: python tools/ncu_summary.py <round-tag> <workload> <pixels-per-launch> <report.ncu-rep> [<report2> ...]"""
 import csv
+import re
 import io
 import json
 import os
@@ -33,8 +34,12 @@ def main():
     for rep in sys.argv[4:]:
         hdr, units, launches = raw(rep)
         vals = launches[0]
-        kname = vals[hdr.index("Kernel Name")].split("(")[0].split("<")[0].replace("void ", "").strip()
-        base = os.path.join(ROOT, "profiles", f"{tag}_{kname}")
+        full = vals[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").strip()
+        kname = full.split("<")[0]
+        m = re.search(r"ring_pointwise_kernel<(?:sb::)?(\w+)", full)
+        if m:                                           # the ring template: keep the Op in the name
+            kname = f"ring_pointwise_kernel<{m.group(1)}>"
+        base = os.path.join(ROOT, "profiles", f"{tag}_{kname}".replace("<", "_").replace(">", ""))
         with open(base + "_ncu.csv", "w") as f:
             f.write(f"# ncu --set full --clock-control none, {workload}, first profiled launch; from {os.path.basename(rep)}\n")
             f.write(f"Kernel Name,,{vals[hdr.index('Kernel Name')]}\n")
