@@ -5,24 +5,30 @@
 // on it without leaving the kernel; clusters are persistent and stride over the batch:
 //
 //   Macenko (macenko_stain_extractor.py:7-44)
-//     A   tissue mask + masked OD moments (n, sum od, sum od x od)      -> 3x3 covariance, fp64 Jacobi eigenvectors
-//     B1  angle keys of tissue pixels -> 4096-bin histogram              -> bins holding the two angular percentiles
-//     B2  11-bit refinement inside those bins                             -> exact order statistics -> stain matrix
-//   Vahadane (vahadane_stain_extractor.py:19-43; spams.trainDL restated as deterministic full-batch learning)
-//     V x T  sparse-code tissue pixels with the current dictionary, accumulate A = sum aa^T, B = sum xa^T, update D
+//     A    tissue mask + masked OD moments (n, sum od, sum od x od)     -> 3x3 covariance, fp64 Jacobi eigenvectors
+//     B0   angle keys of a 1-in-16 sample -> 4096-bin histogram          -> a key bracket around each angular percentile
+//     B1'  one full pass: count the keys below each bracket, list the keys inside -> exact order statistics -> stain matrix
+//          (on a miss, and for clusters: B1 full 4096-bin histogram + B2 11-bit refinement -- same keys, same result)
+//   Vahadane (vahadane_stain_extractor.py:19-43; spams.trainDL restated as a deterministic dictionary iteration)
+//     V0   tissue mask (kept as one bit per pixel)
+//     V    sparse-code the tissue pixels, accumulate A = sum aa^T, B = sum xa^T, update D: sample passes to a residual of
+//          1e-4, then full passes to 2e-6, the fixed-point map Anderson-accelerated (memory 4)
 //   common (stain_utils.py:69-78, normalizer.py:46-50)
-//     C1  closed-form non-negative LASSO concentrations of ALL pixels -> two 4096-bin histograms
-//     C2  11-bit refinement                                              -> exact 99th percentiles (maxC)
-//     D   recombine with the target matrix: the TMA-ring K4 kernel of sb_recombine.cu, launched right behind this
-//         kernel on the same stream with the per-tile statistics computed here (sb_normalize = this kernel + K4)
+//     C0 + C1'  the same sampled-bracket selection for the 99th percentile of each closed-form non-negative LASSO
+//          concentration over ALL pixels (fallback C1 + C2: two-level histograms)
+//     D    recombine with the target matrix: K4 (sb_recombine.cu on the ring of sb_ring.cuh), launched right behind this
+//          kernel on the same stream with the per-tile statistics computed here (sb_normalize = this kernel + K4)
 //
 // Every pass re-reads the tile with 16-byte vector loads.  Instruction issue, not HBM, bounds this kernel, so the
-// passes are built to minimise instructions: the OD table is replicated per lane with 256-byte rows (one PRMT makes
-// the lookup offset, no bank conflicts), the tissue mask is computed once (pass A) and kept as one bit per pixel in
-// the unused half of those rows, the ragged last group is peeled off so the main loops carry no validity checks, and
-// the final pass is the packed f32x2 recombine of sb_recombine.cu.  Cross-CTA reductions
-// (moments, histograms) go through distributed shared memory; every CTA of a cluster redundantly evaluates the small
-// serial steps (eigenvectors, selections) so no broadcast is needed and results are bit-identical.
+// passes are built to minimise instructions: the lookup table holds one {od, gamma} pair per lane in 256-byte rows (one
+// PRMT makes the offset, one conflict-free LDS.64 returns density and linearised value; the Macenko passes recompute
+// the tissue mask from the gammas instead of storing it), the moments are predicated adds, the concentration pass runs
+// the compare-free LASSO on the packed f32x2 pipe, the rare pixels that need an exact key go through per-warp
+// compaction queues, and the ragged last group is peeled off so the main loops carry no validity checks.  Cross-CTA
+// reductions (moments, histograms) go through distributed shared memory; every CTA of a cluster redundantly evaluates
+// the small serial steps (eigenvectors, selections) so no broadcast is needed and results are bit-identical.
+// The slide-level (multi-tile, multi-rank) fit passes at the end of the file produce the same statistics as sums that
+// add across tiles, launches and ranks.
 #include "sb_kernels.h"
 
 namespace sb {

@@ -5,11 +5,12 @@
 //   * OD table replicated per lane with a 256-byte row stride: ONE PRMT builds the shared-memory offset
 //     (value << 8 | lane << 2) straight from the packed pixel word, and the lookup is bank-conflict free;
 //   * all multiply-adds run two pixels at a time on the packed f32x2 pipe (FFMA2 / FADD2.RD, sm_100 only);
-//   * the "value >= 2^23" / NaN guard of the unclipped uint8 wrap is hoisted to a block-uniform template flag: it is
-//     only compiled in when the target matrix has a negative entry (otherwise 255*exp(.) <= 255 always);
+//   * the "value >= 2^23" / NaN guard of the unclipped uint8 wrap is hoisted to a per-tile code variant: it only runs
+//     when the per-tile constants cannot PROVE 255*2^e < 2^23 for every uint8 pixel (make_k4_consts);
 //   * with row-normalised stain matrices (unit Gram diagonal) the whole LASSO case analysis collapses to
 //     c_j = max(0, min(a_j, u_j)) (or one 3-input max when the stain vectors have a negative dot product): no compares;
-//   * in the TMA kernel the table sits at a 64 KB-aligned shared address, so the PRMT output IS the LDS address.
+//   * on the TMA ring (sb_ring.cuh, the path for 16-byte aligned tiles) the table sits at a 64 KB-aligned shared
+//     address, so the PRMT output IS the LDS address; unaligned tiles take the register-staged recombine_v2_kernel.
 #include <cstdlib>
 #include "sb_kernels.h"
 #include "sb_ring.cuh"   // mbarrier / cp.async.bulk helpers shared with the generic ring kernel
