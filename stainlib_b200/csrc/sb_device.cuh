@@ -482,9 +482,11 @@ __device__ inline void jacobi_eig3(const double a_in[6], double w[3], double v[3
             for (int q = p + 1; q < 3; ++q) {
                 const double apq = a[p][q];
                 if (apq == 0.0) continue;
-                const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) with theta = d / (2 apq), written with one square root, one
+                // division and one reciprocal square root (this runs on ONE thread per tile: fp64 latency is what it costs)
+                const double d = a[q][q] - a[p][p];
+                const double t = (d >= 0 ? 2.0 : -2.0) * apq / (fabs(d) + sqrt(d * d + 4.0 * apq * apq));
+                const double c = rsqrt(t * t + 1.0), s = t * c;
                 const int r = 3 - p - q;
                 const double app = a[p][p], aqq = a[q][q], arp = a[r][p], arq = a[r][q];
                 a[p][p] = app - t * apq;
