@@ -87,6 +87,15 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
     if (p->method == SB_METHOD_VAHADANE && groups / a.cluster_size > 16384)
         SB_CUDA(cudaMallocAsync(&mask_scratch, (size_t)B * groups * sizeof(unsigned short), stream));
     a.mask_scratch = mask_scratch;
+    {
+        // bracket half-width: the rule in plan_bracket (sb_pipeline.cu) unless a sweep overrides it through the environment
+        static float sig = -2.f, pad = 0.f;
+        if (sig < -1.5f) {
+            const char* e1 = getenv("SB_BRACKET_SIGMAS"); const char* e2 = getenv("SB_BRACKET_PAD");
+            sig = e1 ? (float)atof(e1) : -1.f; pad = e2 ? (float)atof(e2) : 0.f;
+        }
+        a.bracket_sigmas = sig; a.bracket_pad = pad;
+    }
     if (mode != sb::PIPE_NORMALIZE) {
         a.mode = mode; a.M_out = M; a.maxC_out = maxC; a.status = status;
         cudaError_t e = (cudaError_t)sb::launch_tile_pipeline(a, h->num_sms, stream);

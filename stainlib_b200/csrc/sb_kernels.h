@@ -43,6 +43,7 @@ struct PipeArgs {
     double* maxC_out;     // [B,2] or null
     int32_t* status;      // [B] or null
     unsigned short* mask_scratch;   // Vahadane, tiles too big for the shared-memory mask cache: [B][groups] or null
+    float bracket_sigmas, bracket_pad;   // half-width of the sampled rank brackets: sigmas * binomial sigma + pad (sample ranks)
 };
 
 int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream);

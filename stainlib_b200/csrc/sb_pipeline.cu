@@ -315,10 +315,20 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned x) {
     return x;
 }
 
-__device__ inline void plan_bracket(unsigned n, unsigned n_s, unsigned lo, unsigned& ra, unsigned& rb) {
+// Half-width m (in sample ranks) of the bracket around sample rank pos.  The sample consists of 16-pixel groups, i.e. of
+// spatially correlated pixels, so its rank error exceeds the binomial sigma.  Measured on eight pools of 512^2 tiles
+// (profiles/r01_bracket_sweep.txt): with 3 sigma + 8 about 2 % of the tiles miss a bracket and pay the two-level fallback
+// (1.31-1.70 ms per 1024 tiles depending on the pool), 5 sigma + 16 has no miss on any pool (1.38 ms everywhere), 8 sigma
+// overflows the lists.  Small samples (256^2 tiles) do not miss at 3 sigma + 8 and only pay for wider brackets (+6 %),
+// and beyond ~80 ranks the brackets of big tiles approach the list capacity: hence the two regimes and the cap.
+// sigmas >= 0 (SB_BRACKET_SIGMAS / SB_BRACKET_PAD, sweeps only) overrides the rule with sigmas * sigma + pad.
+__device__ inline void plan_bracket(unsigned n, unsigned n_s, unsigned lo, unsigned& ra, unsigned& rb, float sigmas, float pad) {
     const double q = (double)lo / (double)n;
     const double pos = q * (double)n_s;
-    const double m = 3.0 * sqrt((double)n_s * q * (1.0 - q)) + 8.0;
+    const double sd = sqrt((double)n_s * q * (1.0 - q));
+    const double m_narrow = 3.0 * sd + 8.0, m_wide = 5.0 * sd + 16.0;
+    double m = n_s < 6000u ? m_narrow : fmin(m_wide, fmax(m_narrow, 80.0));
+    if (sigmas >= 0.f) m = (double)sigmas * sd + (double)pad;
     const double a = floor(pos - m), b = ceil(pos + m) + 1.0;
     ra = a < 0.0 ? 0u : (unsigned)a;
     rb = b > (double)(n_s - 1) ? n_s - 1 : (unsigned)b;
@@ -608,8 +618,8 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     if (threadIdx.x == 0) {
                         const unsigned n_s = sh->s_cnt;
                         if (n_s >= 1024u) {
-                            plan_bracket(n_tissue, n_s, p_lo[0], sh->q_rank[0], sh->q_rank[1]);
-                            plan_bracket(n_tissue, n_s, p_lo[1], sh->q_rank[2], sh->q_rank[3]);
+                            plan_bracket(n_tissue, n_s, p_lo[0], sh->q_rank[0], sh->q_rank[1], a.bracket_sigmas, a.bracket_pad);
+                            plan_bracket(n_tissue, n_s, p_lo[1], sh->q_rank[2], sh->q_rank[3], a.bracket_sigmas, a.bracket_pad);
                             for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
                             sh->s_ok = 1;
                         }
@@ -968,7 +978,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                 if (threadIdx.x == 0) {
                     const unsigned n_s = sh->s_cnt;
                     if (n_s >= 1024u) {
-                        plan_bracket((unsigned)npx, n_s, c_lo, sh->q_rank[0], sh->q_rank[1]);
+                        plan_bracket((unsigned)npx, n_s, c_lo, sh->q_rank[0], sh->q_rank[1], a.bracket_sigmas, a.bracket_pad);
                         sh->q_rank[2] = sh->q_rank[0]; sh->q_rank[3] = sh->q_rank[1];
                         for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
                         sh->s_ok = 1;
