@@ -153,6 +153,25 @@ class ClockSampler:
         return {"sm_mhz": m[len(m) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(m)}
 
 
+def pin_to_gpu_numa_node(index):
+    """Binds this process to the CPUs NVML reports as local to GPU `index` BEFORE the pinned host buffers are allocated:
+    pinned memory lands on the NUMA node of the allocating thread, and a buffer on the far socket halves the
+    host<->device rate of the e2e leg (observed spread between boxes: 5.5 - 15.6 Gpx/s).  Best effort."""
+    try:
+        import pynvml as nv
+        import torch
+        nv.nvmlInit()
+        try:                                            # CUDA_VISIBLE_DEVICES may renumber: go through the PCI address
+            pr = torch.cuda.get_device_properties(index)
+            h = nv.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByIndex(index)
+        nv.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -356,6 +375,7 @@ def main():
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
+    pin_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
