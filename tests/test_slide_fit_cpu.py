@@ -110,6 +110,11 @@ def _tiles():
     return [synth_tile(40 + i, 96, 112) for i in range(3)] + [np.full((96, 112, 3), 255, np.uint8)]
 
 
+def _big_tiles():
+    from stainlib_b200.synth import synth_tile
+    return [synth_tile(60 + i, 160, 176) for i in range(4)]
+
+
 def _expected(tiles):
     from oracle import stain_oracle as so
     big = np.concatenate(tiles, axis=0)
@@ -142,11 +147,13 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from stainlib_b200.normalization.slide_fit import macenko_slide_fit
+    from stainlib_b200.normalization.slide_fit import macenko_slide_fit, vahadane_slide_fit
     tiles = _tiles()
     mine = tiles[:3] if rank == 0 else tiles[3:]          # rank 1 holds only the all-white tile: no tissue of its own
     M, maxC = macenko_slide_fit(None, passes=NumpyPasses(mine))
-    q.put((rank, M.tolist(), maxC.tolist()))
+    big = _big_tiles()
+    Mv, Cv = vahadane_slide_fit(None, passes=NumpyPasses(big[rank::world]))        # interleaved shards
+    q.put((rank, M.tolist(), maxC.tolist(), Mv.tolist(), Cv.tolist()))
     dist.destroy_process_group()
 
 
@@ -166,6 +173,12 @@ def test_slide_fit_sharded_world2_equals_unsharded():
     M1, C1 = macenko_slide_fit(None, passes=NumpyPasses(_tiles()))
     np.testing.assert_allclose(np.array(res[0][1]), M1, rtol=0, atol=1e-12)   # sharded == unsharded (integer histograms add exactly)
     np.testing.assert_allclose(np.array(res[0][2]), C1, rtol=1e-12)
+    # Vahadane: every dictionary pass all-reduces ten sums; the ranks agree and match the unsharded run (summation order only)
+    assert res[0][3] == res[1][3] and res[0][4] == res[1][4]
+    from stainlib_b200.normalization.slide_fit import vahadane_slide_fit
+    Mv1, Cv1 = vahadane_slide_fit(None, passes=NumpyPasses(_big_tiles()))
+    np.testing.assert_allclose(np.array(res[0][3]), Mv1, rtol=0, atol=1e-8)
+    np.testing.assert_allclose(np.array(res[0][4]), Cv1, rtol=1e-7)
 
 
 def test_key_inverses_roundtrip():
