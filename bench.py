@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- Mpixels/s of stain normalisation on B200 (BASELINE.json metric), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload macenko512|...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|macenko512|...]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -9,17 +9,24 @@ A "step" is one pass of the hot path (ExtractiveStainNormalizer.transform, norma
 synthetic tiles per GPU (weak scaling: every rank owns a full batch; tiles shard with no data-path collective, the
 only collective is the one all-reduce of the fitted target statistics in fit()).
 
+The headline of the line is BASELINE.json's config[1] (1024 x 512^2 tiles, Macenko):
   value     device-resident throughput: inputs already in HBM, CUDA events on the launching stream, max over ranks.
-  e2e       same metric through the public API with pinned HOST tensors: H2D + kernels + D2H inside the timed region.
+  e2e       same metric through the public API with pinned HOST tensors: H2D + kernels + D2H inside the timed region,
+            beside the host-link ceiling measured in the same run (simultaneous H2D + D2H copies on all ranks).
   roofline  dominant kernel of the step (tile_pipeline_kernel, read-only, 3 algorithmic B/px), timed alone with CUDA
             events; roofline_k4 = the fused OD+recombine kernel (6 B/px); roofline_step = the whole step at 6 B/px;
             all against MEASURED_PEAKS.json.
-  cpu_baseline  the numpy/OpenCV oracle port of the reference path on the host cores, bounded sample (rank 0, N=1).
+  cpu_baseline  the reference's own Python (baseline/_ref, spams.lasso shimmed) or, without it, the numpy/OpenCV oracle
+            port, on the host cores with ONE BLAS/OpenMP thread per worker process; bounded sample (rank 0, N=1).
+With the default `--workload all` the same line carries `workloads`: one sub-record (value, ms_per_step, e2e, clocks,
+dominant-kernel roofline) for each other configuration of the north-star matrix -- Vahadane 512^2, Macenko 1024^2,
+Vahadane 1024^2 (config[2], 4096 tiles), HED-light + Reinhard and StainAugmentor fit+pop (config[3]), and the
+100 000-tile 256^2 stream (config[4], the one strong-scaling line).  `--workload NAME` runs one of them as the headline.
 
---impl reference times that same CPU port (oracle/stain_oracle.py -- the reference is pure Python and cannot travel
-to the GPU box; the port is pinned bit-for-bit to the real reference by tests/golden) with every host core.
+--impl reference times the reference CPU arm alone, with every host core, on the headline's config.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -33,63 +40,131 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (method, tiles per GPU, H, W, description)
-    "macenko512": ("macenko", 1024, 512, 512, "config[1]: 1024 synthetic 512x512 H&E tiles, Macenko normalize"),
-    "macenko256": ("macenko", 4096, 256, 256, "4096 synthetic 256x256 tiles, Macenko normalize (config[4] tile size)"),
-    "macenko1024": ("macenko", 256, 1024, 1024, "256 synthetic 1024x1024 tiles, Macenko normalize"),
-    "vahadane1024": ("vahadane", 1024, 1024, 1024, "config[2] tile size: 1024x1024 tiles, Vahadane sparse-NMF normalize (1024 per GPU; --tiles 4096 = the full config)"),
-    "vahadane512": ("vahadane", 1024, 512, 512, "1024 synthetic 512x512 tiles, Vahadane sparse-NMF normalize"),
+    # kind, method, tiles per GPU (device leg), tiles per GPU of the end-to-end leg, H, W, description
+    "macenko512": dict(kind="extractive", method="macenko", tiles=1024, e2e_tiles=1024, H=512, W=512,
+                       desc="config[1]: 1024 synthetic 512x512 H&E tiles, Macenko normalize"),
+    "macenko256": dict(kind="extractive", method="macenko", tiles=4096, e2e_tiles=4096, H=256, W=256,
+                       desc="4096 synthetic 256x256 tiles, Macenko normalize (config[4] tile size)"),
+    "macenko1024": dict(kind="extractive", method="macenko", tiles=256, e2e_tiles=256, H=1024, W=1024,
+                        desc="256 synthetic 1024x1024 tiles, Macenko normalize"),
+    "vahadane512": dict(kind="extractive", method="vahadane", tiles=1024, e2e_tiles=1024, H=512, W=512,
+                        desc="1024 synthetic 512x512 tiles, Vahadane sparse-NMF normalize"),
+    "vahadane1024": dict(kind="extractive", method="vahadane", tiles=4096, e2e_tiles=256, H=1024, W=1024,
+                         desc="config[2]: 4096 synthetic 1024x1024 tiles, Vahadane sparse-NMF normalize (12.9 GB in + 12.9 GB out per GPU)"),
     # config[4]: 100k 256x256 tiles in total, split over the ranks (strong scaling)
-    "stream256": ("macenko", 100000, 256, 256, "config[4]: WSI-scale stream, 100000 synthetic 256x256 tiles in total, Macenko normalize"),
+    "stream256": dict(kind="extractive", method="macenko", tiles=100000, e2e_tiles=8192, H=256, W=256, strong=True,
+                      desc="config[4]: WSI-scale stream, 100000 synthetic 256x256 tiles in total, Macenko normalize"),
     # config[3]: HedLightColorAugmenter (per-tile sigma/bias) then ReinhardStainNormalizer, 1024 tiles of 512x512 per GPU
-    "hed_reinhard512": ("hed_reinhard", 1024, 512, 512, "config[3]: HedLightColorAugmenter + Reinhard normalize, 1024 synthetic 512x512 tiles per GPU"),
+    "hed_reinhard512": dict(kind="hed_reinhard", method="hed_reinhard", tiles=1024, e2e_tiles=1024, H=512, W=512,
+                            desc="config[3]: HedLightColorAugmenter + Reinhard normalize, 1024 synthetic 512x512 tiles per GPU"),
+    "stain_augment512": dict(kind="stain_augment", method="stain_augment", tiles=1024, e2e_tiles=1024, H=512, W=512,
+                             desc="config[3], second line: StainAugmentor('macenko').fit + pop, 1024 synthetic 512x512 tiles per GPU"),
 }
-STRONG = {"stream256"}
+MATRIX = ["vahadane512", "macenko1024", "vahadane1024", "hed_reinhard512", "stain_augment512", "stream256"]
 BYTES_PER_PX = 6.0   # 3 B read + 3 B written
 
 
-# ----------------------------------------------------------------------------------------------- CPU baseline (oracle)
+# ----------------------------------------------------------------------------------------------- CPU baseline
+# One worker process per host core, each limited to ONE BLAS / OpenMP / OpenCV thread (the environment is set before
+# the workers start, i.e. before their numpy loads its BLAS): without the limit every worker spawns a thread per core
+# and the oversubscription costs 5-8x.  Spawned, not forked: CUDA may already be initialised in the parent.
 _CPU = {}
+_THREAD_ENV = ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS", "VECLIB_MAXIMUM_THREADS")
 
 
-def _cpu_init(method, tgt):
+def _reference_root():
+    """The reference's own package: /root/reference in the build container, the pip --target copy baseline/_ref on the
+    GPU box (git-ignored, shipped by gpurun).  None when neither exists."""
+    for root in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(root, "stainlib")):
+            return root
+    return None
+
+
+def _cpu_init(method, tgt, want_reference):
     import cv2
     cv2.setNumThreads(1)
+    try:
+        from threadpoolctl import threadpool_limits
+        _CPU["limit"] = threadpool_limits(1)
+    except Exception:
+        pass
     from oracle import stain_oracle as so
+    _CPU["method"], _CPU["kind"] = method, "port"
     if method == "hed_reinhard":
         n = so.ReinhardStainNormalizer()
+    elif method == "stain_augment":
+        n = None
+    elif method == "macenko" and want_reference and _reference_root():
+        # the reference's own normalizer.py:16-50 / macenko_stain_extractor.py:7-44 / stain_utils.py, unmodified; only
+        # spams.lasso (absent from this image) is shimmed by the closed-form 2-atom solution
+        from oracle import ref_loader
+        ref = ref_loader.load_reference(root=_reference_root())
+        n = ref.ExtractiveStainNormalizer("macenko")
+        _CPU["kind"] = "reference"
     else:
         n = so.ExtractiveStainNormalizer(method)      # vahadane: the same accelerated schedule the CUDA path runs
-    n.fit(tgt)
+    if n is not None:
+        n.fit(tgt)
     _CPU["n"] = n
-    _CPU["method"] = method
 
 
 def _cpu_one(tile):
-    if _CPU["method"] == "hed_reinhard":
-        from oracle import stain_oracle as so
+    from oracle import stain_oracle as so
+    m = _CPU["method"]
+    if m == "hed_reinhard":
         rs = np.random.RandomState(int(tile[0, 0, 0]) + 1)
         aug = so.hed_augment(tile, rs.uniform(-0.1, 0.1, 3), rs.uniform(-0.1, 0.1, 3))   # HedLight ranges (augmenter.py:366-368)
-        return int(_CPU["n"].transform(aug)[0, 0, 0])
-    return int(_CPU["n"].transform(tile)[0, 0, 0])
+        return int(_CPU["n"].transform(aug)[0, 0, 0]), _CPU["kind"]
+    if m == "stain_augment":
+        a = so.StainAugmentor("macenko")
+        a.fit(tile)
+        return int(a.pop()[0, 0, 0]), _CPU["kind"]
+    return int(_CPU["n"].transform(tile)[0, 0, 0]), _CPU["kind"]
 
 
-def cpu_throughput(method, H, W, n_tiles, tiles=None):
-    """Mpx/s of the oracle port over n_tiles tiles with one process per host core.  Returns (mpx_s, cores, seconds)."""
-    import multiprocessing as mp
-    from stainlib_b200.synth import synth_tile
-    cores = os.cpu_count() or 1
-    tgt = synth_tile(1, H, W, kind="target")
-    if tiles is None:
-        tiles = [synth_tile(1000 + i, H, W) for i in range(min(n_tiles, 16))]
-    work = [tiles[i % len(tiles)] for i in range(n_tiles)]
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(method, tgt)) as pool:
-        pool.map(_cpu_one, work[:cores])          # warm-up: imports, page-in
+class CpuPool(object):
+    """Pool of single-threaded workers running the reference path tile by tile."""
+
+    def __init__(self, method, H, W, want_reference=True):
+        import multiprocessing as mp
+        from stainlib_b200.synth import synth_tile
+        self.cores = os.cpu_count() or 1
+        self.H, self.W = H, W
+        tgt = synth_tile(1, H, W, kind="target")
+        self.tiles = [synth_tile(1000 + i, H, W) for i in range(16)]
+        saved = {k: os.environ.get(k) for k in _THREAD_ENV}
+        for k in _THREAD_ENV:
+            os.environ[k] = "1"
+        try:
+            self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(method, tgt, want_reference))
+            res = self.pool.map(_cpu_one, [self.tiles[i % 16] for i in range(2 * self.cores)], chunksize=1)   # warm-up: imports, page-in
+            self.kind = res[0][1]
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+    def run(self, n_tiles):
+        """Mpx/s over n_tiles tiles, and the wall seconds."""
+        work = [self.tiles[i % len(self.tiles)] for i in range(n_tiles)]
         t0 = time.perf_counter()
-        pool.map(_cpu_one, work, chunksize=1)
+        self.pool.map(_cpu_one, work, chunksize=1)
         dt = time.perf_counter() - t0
-    return n_tiles * H * W / dt / 1e6, cores, dt
+        return n_tiles * self.H * self.W / dt / 1e6, dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def describe(self, n_tiles, dt=None):
+        what = {"reference": "the reference's own normalizer.py:39-50 + macenko_stain_extractor.py:7-44 + stain_utils.py (unmodified, baseline/_ref; "
+                             "spams.lasso shimmed by the closed-form 2-atom LASSO)",
+                "port": "numpy/OpenCV oracle port of the reference path (closed-form LASSO in place of spams.lasso)"}[self.kind]
+        wall = f" ({dt:.1f} s wall)" if dt is not None else ""
+        return f"{n_tiles} tiles of {self.H}x{self.W}{wall}, {self.cores} worker processes, threads_per_worker=1 (OMP/OpenBLAS/MKL/OpenCV); {what}"
 
 
 # ----------------------------------------------------------------------------------------------- clock sampling
@@ -179,95 +254,128 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def lib_sha16():
+    p = os.path.join(ROOT, "stainlib_b200", "libstainb200.so")
+    try:
+        return hashlib.sha256(open(p, "rb").read()).hexdigest()[:16]
+    except OSError:
+        return None
+
+
 def ncu_traffic(workload, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-    (profiles/traffic.json, written by tools/ncu_summary.py), or None."""
+    (profiles/traffic.json, written by tools/ncu_summary.py).  A capture only describes the binary it was taken from:
+    the entry carries the sha256 of that libstainb200.so and is reported only while the library on disk is that binary
+    (a CUDA process cannot count its own DRAM bytes without a profiler attached); otherwise null."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get(workload, {}).get(kernel)
-    return None
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p))
+    e = t.get(workload, {}).get(kernel)
+    if isinstance(e, dict):
+        return e.get("dram_bytes") if e.get("so_sha16") == lib_sha16() else None
+    return None                                         # legacy entry without a binary stamp: evidence about an older build
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
-def run_reference(args, method, B, H, W, desc):
+def run_reference(args, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = max(os.cpu_count() or 1, 16) * 2       # bounded sample of the workload per step
-    vals = []
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_throughput(method, H, W, per_step)
-    secs = 0.0
+    wl = WORKLOADS[name]
+    method, H, W = wl["method"], wl["H"], wl["W"]
+    pool = CpuPool(method, H, W)
+    per_step = max(pool.cores, 16) * 2                 # bounded sample of the workload per step
+    for _ in range(min(args.warmup, 1)):
+        pool.run(per_step)
+    vals, secs = [], 0.0
     for _ in range(args.steps):
-        v, cores, dt = cpu_throughput(method, H, W, per_step)
+        v, dt = pool.run(per_step)
         vals.append(v)
         secs += dt
-    value = float(np.mean(vals)) if vals else 0.0
+    pool.close()
+    value = float(per_step * H * W * args.steps / secs / 1e6) if secs > 0 else 0.0
     line = {
-        "impl": "reference", "metric": "Mpixels/sec HED-light augment + Reinhard normalize" if method == "hed_reinhard" else f"Mpixels/sec stain-normalize ({method})",
+        "impl": "reference", "metric": metric_name(method),
         "value": round(value, 3), "unit": "Mpx/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * secs / max(args.steps, 1), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "tiles_per_step": per_step, "tile": [H, W]},
-        "cpu_baseline": {"value": round(value, 3), "unit": "Mpx/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{per_step} tiles of {H}x{W} per step, one process per core, numpy/OpenCV oracle port of "
-                                   "normalizer.py:39-50 (closed-form LASSO instead of spams.lasso)"},
+        "config": {"workload": wl["desc"], "tiles_per_step": per_step, "tile": [H, W]},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Mpx/s", "cores": pool.cores, "kind": pool.kind,
+                         "threads_per_worker": 1, "per_core": round(value / pool.cores, 3),
+                         "sample": pool.describe(per_step) + " per step"},
         "e2e": {"value": round(value, 3), "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-# ----------------------------------------------------------------------------------------------- config[3]: HED + Reinhard
-def run_hed_reinhard(args, B, H, W, desc, rank, world, local, cpu):
-    """One step = HedLightColorAugmenter.transform (per-tile sigma / bias drawn on the host as augmenter.py:333-344 does)
-    followed by ReinhardStainNormalizer.transform (normalizer.py:70-94) over this rank's tiles."""
-    import torch
-    import torch.distributed as dist
-    import stainlib_b200 as sb
-    from stainlib_b200 import _native as nv
-    from stainlib_b200.augmentation.augmenter import HedLightColorAugmenter
-    from stainlib_b200.synth import synth_tile, synth_batch
+def metric_name(method):
+    return {"hed_reinhard": "Mpixels/sec HED-light augment + Reinhard normalize",
+            "stain_augment": "Mpixels/sec StainAugmentor fit + pop (macenko)"}.get(method, f"Mpixels/sec stain-normalize ({method})")
 
-    hed = HedLightColorAugmenter()
-    rein = sb.ReinhardStainNormalizer()
-    rein.fit(synth_tile(1, H, W, kind="target") if rank == 0 else None)
-    np.random.seed(rank)
-    sig = np.random.uniform(-0.1, 0.1, size=(B, 3))
-    bias = np.random.uniform(-0.1, 0.1, size=(B, 3))
-    pool = torch.from_numpy(synth_batch(5000 + 64 * rank, min(B, 64), H, W))
-    host_in = pool.repeat(-(-B // pool.shape[0]), 1, 1, 1)[:B].contiguous().pin_memory()
-    dev_in = host_in.cuda(non_blocking=True)
-    torch.cuda.synchronize()
-    npx_rank = B * H * W
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+# ----------------------------------------------------------------------------------------------- our arm
+class Ctx(object):
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch, self.dist = torch, dist
+        self._pools = {}
 
-    def step(x):
-        return rein.transform(hed.transform(x, sigmas=sig, biases=bias))
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        out = step(dev_in)
-    barrier()
-    l0 = nv.launch_count(local)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local) as clocks:
-        ev[0].record()
-        for i in range(args.steps):
-            out = step(dev_in)
-            ev[i + 1].record()
-        barrier()
-    launches = nv.launch_count(local) - l0
-    t = torch.tensor([ev[0].elapsed_time(ev[-1])], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * npx_rank * args.steps / (ms_total * 1e-3) / 1e6
+    def allreduce(self, x, op="max"):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
 
-    def timed(fn, n):
+    def tile_pool(self, H, W):
+        """Pool of distinct synthetic tiles of this rank (64; 32 for tiles of a megapixel), as a CPU tensor."""
+        key = (H, W)
+        if key not in self._pools:
+            from stainlib_b200.synth import synth_batch
+            n = 64 if H * W <= 512 * 512 else 32
+            self._pools[key] = self.torch.from_numpy(synth_batch(5000 + 64 * self.rank, n, H, W))
+        return self._pools[key]
+
+    def host_batch(self, H, W, B):
+        pool = self.tile_pool(H, W)
+        return pool.repeat(-(-B // pool.shape[0]), 1, 1, 1)[:B].contiguous().pin_memory()
+
+    def device_batch(self, H, W, B):
+        pool = self.tile_pool(H, W).cuda()
+        if B <= pool.shape[0]:
+            return pool[:B].contiguous()
+        return pool.repeat(-(-B // pool.shape[0]), 1, 1, 1)[:B].contiguous()
+
+    def timed_device(self, fn, steps, warmup):
+        """W warm-up steps, then K steps between CUDA events on the current stream; total ms as the max over ranks, the
+        per-step list of this rank, the clocks sampled during the timed region."""
+        torch = self.torch
+        for _ in range(warmup):
+            out = fn()
+        self.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        with ClockSampler(self.local) as clocks:
+            ev[0].record()
+            for i in range(steps):
+                out = fn()
+                ev[i + 1].record()
+            self.barrier()
+        ms_total = self.allreduce(ev[0].elapsed_time(ev[-1]), "max")
+        return out, ms_total, [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)], clocks.summary()
+
+    def timed_alone(self, fn, n):
+        torch = self.torch
         for _ in range(3):
             fn()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,15 +387,203 @@ def run_hed_reinhard(args, B, H, W, desc, rank, world, local, cpu):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / n
 
-    hed_ms = timed(lambda: hed.transform(dev_in, sigmas=sig, biases=bias), args.steps)
-    mid = hed.transform(dev_in, sigmas=sig, biases=bias)
-    rein_ms = timed(lambda: rein.transform(mid), args.steps)
+    def timed_host(self, fn, steps, warmup):
+        """Wall-clock seconds of K synchronous end-to-end steps (max over ranks)."""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.torch.cuda.synchronize()
+        return self.allreduce(time.perf_counter() - t0, "max")
+
+    def link_ceiling(self):
+        """Host-link ceiling of this box with ALL ranks copying at once: every rank moves 256 MB pinned host -> device and
+        256 MB device -> pinned host simultaneously on two streams (what the e2e leg does); aggregate GB/s each way."""
+        torch = self.torch
+        if hasattr(self, "_link"):
+            return self._link
+        n = 256 << 20
+        h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+        d_in, d_out = torch.empty(n, dtype=torch.uint8, device="cuda"), torch.empty(n, dtype=torch.uint8, device="cuda")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def once():
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+            s1.synchronize()
+            s2.synchronize()
+        reps = 4
+        dt = self.timed_host(once, reps, 2)
+        each_way = self.allreduce(n * reps / dt / 1e9, "sum")          # all ranks ran between the same barriers
+        self._link = round(each_way, 2)
+        return self._link
+
+    def e2e_record(self, npx_all, steps, dt, h2d, d2h, same):
+        gbs_each_way = npx_all * 3.0 * steps / dt / 1e9
+        link = self.link_ceiling()
+        return {"value": round(npx_all * steps / dt / 1e6, 1), "unit": "Mpx/s", "steps": steps,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "matches_device_path": same,
+                "link_gbs_each_way": round(gbs_each_way, 2), "link_ceiling_gbs_each_way": link,
+                "frac_of_link_ceiling": round(gbs_each_way / link, 3) if link else None}
+
+
+def run_extractive(ctx, name, steps, warmup, headline):
+    """ExtractiveStainNormalizer(method).transform over this rank's tiles.  Returns the record (rank 0) of the workload."""
+    import ctypes
+    import stainlib_b200 as sb
+    from stainlib_b200 import _native as nv
+    from stainlib_b200.synth import synth_tile
+    torch, args = ctx.torch, ctx.args
+    wl = WORKLOADS[name]
+    method, H, W = wl["method"], wl["H"], wl["W"]
+    strong = bool(wl.get("strong")) and not args.tiles
+    B = args.tiles if (args.tiles and headline) else wl["tiles"]
+    if strong:                                         # fixed total, contiguous shard per rank
+        B = (B * (ctx.rank + 1)) // ctx.world - (B * ctx.rank) // ctx.world
+    kw = {"cluster_size": args.cluster} if args.cluster else {}
+    norm = sb.ExtractiveStainNormalizer(method, **kw)
+    norm.fit(synth_tile(1, H, W, kind="target") if ctx.rank == 0 else None)     # one all-reduce shares the statistics
+    dev_in = ctx.device_batch(H, W, B)
+    npx_rank = B * H * W
+    npx_all = ctx.allreduce(npx_rank, "sum")            # pixels per step over all ranks (weak: world x shard; strong: the fixed total)
+
+    for _ in range(warmup):
+        norm.transform(dev_in)
+    l0 = nv.launch_count(ctx.local)
+    out, ms_total, per_step_ms, clocks = ctx.timed_device(lambda: norm.transform(dev_in), steps, 0)
+    launches = nv.launch_count(ctx.local) - l0
+    value = npx_all * steps / (ms_total * 1e-3) / 1e6
+    status_bad = int((norm.last_status != 0).sum().item())
+
+    # ---- the two kernels of a step, each timed alone with CUDA events on the launching stream
+    M_src = torch.empty(B, 2, 3, dtype=torch.float64, device="cuda")
+    maxC = torch.empty(B, 2, dtype=torch.float64, device="cuda")
+    p = norm._params()
+    h, _ = nv.get_handle(ctx.local)
+    lib = nv.load_library()
+    n_alone = max(2, min(steps, 10))
+    stats_ms = ctx.timed_alone(lambda: nv.check(lib.sb_fit(h, nv.ptr(dev_in), B, H, W, ctypes.byref(p), nv.ptr(M_src), nv.ptr(maxC), None,
+                                                           nv.stream_ptr(ctx.local))), n_alone)
+    scale = (torch.as_tensor(norm.maxC_target, device="cuda") / maxC).contiguous()
+    Mt = torch.as_tensor(norm.stain_matrix_target, device="cuda").contiguous()
+    out2 = torch.empty_like(dev_in)
+    k4_ms = ctx.timed_alone(lambda: nv.check(lib.sb_recombine(h, nv.ptr(dev_in), nv.ptr(out2), B, H, W, nv.ptr(M_src), nv.ptr(scale), nv.ptr(Mt), 0.01,
+                                                              nv.stream_ptr(ctx.local))), n_alone)
+    k4_match = bool(torch.equal(out2, out)) if status_bad == 0 else None
+    del out2
+
+    # ---- end to end from pinned host memory through the public API
+    e2e = None
+    if not args.no_e2e:
+        Be = min(B, wl["e2e_tiles"])
+        host_in = ctx.host_batch(H, W, Be)
+        host_out = torch.empty_like(host_in).pin_memory()     # result buffer reused across steps (as a streaming caller would)
+        e2e_steps = max(2, min(steps, 5)) if not headline else steps
+        dt = ctx.timed_host(lambda: norm.transform(host_in, out=host_out), e2e_steps, 2)   # synchronous: returns when the last byte is back
+        same = bool(torch.equal(host_out, out[:Be].cpu()))
+        npx_e = ctx.allreduce(Be * H * W, "sum")
+        e2e = ctx.e2e_record(npx_e, e2e_steps, dt, npx_e * 3, npx_e * 3 + ctx.world * 4 * Be, same)
+        if Be != B:
+            e2e["sample"] = f"first {Be} of the {B} tiles per GPU (pinned host buffers bounded)"
+        if headline:
+            # the training-consumer case: results stay on the device, only the inputs cross the link
+            from stainlib_b200.io import stream_host_batches
+            dt2 = ctx.timed_host(lambda: stream_host_batches(norm.transform, host_in, keep_on_device=True), max(2, min(steps, 5)), 2)
+            e2e["h2d_only"] = {"value": round(npx_e * max(2, min(steps, 5)) / dt2 / 1e6, 1), "unit": "Mpx/s",
+                               "note": "pinned host -> device -> transform, output left in HBM (no D2H)"}
+        del host_in, host_out
+    del dev_in, out
+    torch.cuda.empty_cache()
+    if ctx.rank != 0:
+        return None
+    peak, peak_src = measured_peak()
+    med_step_ms = float(np.median(per_step_ms))
+    gbs = lambda ms, bpp: npx_rank * bpp / (ms * 1e-3) / 1e9
+    rec = {
+        "metric": metric_name(method), "value": round(value, 1), "unit": "Mpx/s", "n_gpus": ctx.world,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms_total / steps, 4),
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f32 per-pixel arithmetic on u8 pixels, fixed-point (int64) per-tile sums, f64 per-tile algebra", "data": "synthetic",
+        "config": {"workload": wl["desc"], "tiles_per_gpu": B, "tile": [H, W], "method": method,
+                   "l2_policy": f"input {npx_rank * 3 / 1e6:.0f} MB + output per GPU, larger than the 126 MB L2; no flush needed",
+                   "flagged_tiles": status_bad, "kernels_per_step": "tile_pipeline_kernel + k4_prepare_normalize_kernel + ring_pointwise_kernel<K4Op>"},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        # dominant kernel of the step: the fused per-tile statistics kernel (read-only: 3 algorithmic bytes per pixel)
+        "roofline": {"bound": "hbm", "kernel": "tile_pipeline_kernel (mask+moments / dictionary passes, exact angular and concentration percentiles)",
+                     "achieved": round(gbs(stats_ms, 3.0), 1), "peak": peak, "unit": "GB/s", "frac": round(gbs(stats_ms, 3.0) / peak, 4),
+                     "peak_source": peak_src, "algorithmic_bytes_per_px": 3.0, "launch_ms": round(stats_ms, 4),
+                     "share_of_step": round(stats_ms / med_step_ms, 3), "traffic": ncu_traffic(name, "tile_pipeline_kernel")},
+        "roofline_k4": {"bound": "hbm", "kernel": "ring_pointwise_kernel<K4Op> (fused OD+recombine on the TMA ring)",
+                        "achieved": round(gbs(k4_ms, BYTES_PER_PX), 1), "peak": peak, "unit": "GB/s", "frac": round(gbs(k4_ms, BYTES_PER_PX) / peak, 4),
+                        "algorithmic_bytes_per_px": BYTES_PER_PX, "launch_ms": round(k4_ms, 4), "share_of_step": round(k4_ms / med_step_ms, 3),
+                        "bytes_equal_transform_path": k4_match, "traffic": ncu_traffic(name, "ring_pointwise_kernel<K4Op>")},
+        "roofline_step": {"bound": "hbm", "achieved": round(gbs(med_step_ms, BYTES_PER_PX), 1), "peak": peak, "unit": "GB/s",
+                          "frac": round(gbs(med_step_ms, BYTES_PER_PX) / peak, 4),
+                          "algorithmic_bytes_per_px": BYTES_PER_PX, "step_ms_median": round(med_step_ms, 4)},
+    }
+    return rec
+
+
+def run_operator(ctx, name, steps, warmup):
+    """config[3]: (a) HedLightColorAugmenter.transform (per-tile sigma / bias drawn on the host as augmenter.py:333-344
+    does) followed by ReinhardStainNormalizer.transform (normalizer.py:70-94); (b) StainAugmentor('macenko').fit + pop
+    (augmenter.py:416-449) over this rank's tiles."""
+    import stainlib_b200 as sb
+    from stainlib_b200 import _native as nv
+    from stainlib_b200.augmentation.augmenter import HedLightColorAugmenter, StainAugmentor
+    from stainlib_b200.io import stream_host_batches
+    from stainlib_b200.synth import synth_tile
+    torch, args = ctx.torch, ctx.args
+    wl = WORKLOADS[name]
+    H, W, B = wl["H"], wl["W"], wl["tiles"]
+    dev_in = ctx.device_batch(H, W, B)
+    npx_rank = B * H * W
+    npx_all = ctx.allreduce(npx_rank, "sum")
+    np.random.seed(ctx.rank)
+    if wl["kind"] == "hed_reinhard":
+        hed = HedLightColorAugmenter()
+        rein = sb.ReinhardStainNormalizer()
+        rein.fit(synth_tile(1, H, W, kind="target") if ctx.rank == 0 else None)
+        sig = np.random.uniform(-0.1, 0.1, size=(B, 3))
+        bias = np.random.uniform(-0.1, 0.1, size=(B, 3))
+
+        def op_chunk(x, t0):
+            return rein.transform(hed.transform(x, sigmas=sig[t0:t0 + x.shape[0]], biases=bias[t0:t0 + x.shape[0]]))
+        parts = [("lab_tile_kernel (Reinhard transform)", lambda: rein.transform(mid)),
+                 ("ring_pointwise_kernel<HedOp> (HED augment, speculative patch-mean gate)", lambda: hed.transform(dev_in, sigmas=sig, biases=bias))]
+        mid = hed.transform(dev_in, sigmas=sig, biases=bias)
+        dtype = "integer LAB (exact), f32/f64 per-tile tables"
+    else:
+        aug = StainAugmentor("macenko")
+        al = np.random.uniform(0.8, 1.2, size=(B, 2))
+        be = np.random.uniform(-0.2, 0.2, size=(B, 2))
+
+        def op_chunk(x, t0):
+            aug.fit(x)
+            return aug.pop(alphas=al[t0:t0 + x.shape[0]], betas=be[t0:t0 + x.shape[0]])
+        aug.fit(dev_in)
+        parts = [("tile_pipeline_kernel (Macenko extract: mask+moments, exact angular percentiles; 3 B/px)", lambda: aug.fit(dev_in)),
+                 ("ring_pointwise_kernel<AugOp> (StainAugmentor.pop)", lambda: aug.pop(alphas=al, betas=be))]
+        dtype = "f32 per-pixel arithmetic on u8 pixels, fixed-point per-tile sums"
+    step = lambda: op_chunk(dev_in, 0)
+    for _ in range(warmup):
+        step()
+    l0 = nv.launch_count(ctx.local)
+    out, ms_total, per_step_ms, clocks = ctx.timed_device(step, steps, 0)
+    launches = nv.launch_count(ctx.local) - l0
+    value = npx_all * steps / (ms_total * 1e-3) / 1e6
+    part_ms = [ctx.timed_alone(fn, max(2, min(steps, 10))) for _, fn in parts]
 
     e2e = None
     if not args.no_e2e:
-        from stainlib_b200.io import stream_host_batches
+        host_in = ctx.host_batch(H, W, B)
         host_out = torch.empty_like(host_in).pin_memory()
-        chunk = 0                                       # the helper's default: ~96 MB per slot
 
         def e2e_step():                                 # pinned host -> device -> both operators -> pinned host, overlapped chunks
             pos = {"t0": 0}
@@ -295,228 +591,108 @@ def run_hed_reinhard(args, B, H, W, desc, rank, world, local, cpu):
             def op(x):
                 t0 = pos["t0"]
                 pos["t0"] += x.shape[0]
-                return rein.transform(hed.transform(x, sigmas=sig[t0:t0 + x.shape[0]], biases=bias[t0:t0 + x.shape[0]]))
-            stream_host_batches(op, host_in, host_out, chunk_tiles=chunk)
+                return op_chunk(x, t0)
+            stream_host_batches(op, host_in, host_out)
             torch.cuda.synchronize()
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(world * npx_rank * args.steps / float(tt.item()) / 1e6, 1), "unit": "Mpx/s",
-               "h2d_bytes_per_step": int(world * host_in.numel()), "d2h_bytes_per_step": int(world * host_out.numel()),
-               "matches_device_path": bool(torch.equal(host_out, out.cpu()))}
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        step_ms = ms_total / args.steps
-        gbs = lambda ms, bpp: npx_rank * bpp / (ms * 1e-3) / 1e9
-        line = {
-            "metric": "Mpixels/sec HED-light augment + Reinhard normalize", "value": round(value, 1), "unit": "Mpx/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "integer LAB (exact), f32/f64 per-tile tables", "data": "synthetic",
-            "config": {"workload": desc, "tiles_per_gpu": B, "tile": [H, W], "l2_policy": "805 MB input per GPU, larger than the 126 MB L2"},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            # dominant kernel: lab_tile_kernel (Reinhard transform: percentile + LAB statistics + recolour, 6 algorithmic B/px)
-            "roofline": {"bound": "hbm", "kernel": "lab_tile_kernel (Reinhard transform)", "achieved": round(gbs(rein_ms, 6.0), 1), "peak": peak,
-                         "unit": "GB/s", "frac": round(gbs(rein_ms, 6.0) / peak, 4), "peak_source": peak_src, "algorithmic_bytes_per_px": 6.0,
-                         "launch_ms": round(rein_ms, 4), "share_of_step": round(rein_ms / step_ms, 3), "traffic": None},
-            "roofline_hed": {"bound": "hbm", "kernel": "hed_kernel (HED augment, single pass with speculative patch-mean gate)", "achieved": round(gbs(hed_ms, 6.0), 1), "peak": peak,
-                             "unit": "GB/s", "frac": round(gbs(hed_ms, 6.0) / peak, 4), "algorithmic_bytes_per_px": 6.0, "launch_ms": round(hed_ms, 4),
-                             "share_of_step": round(hed_ms / step_ms, 3), "traffic": None},
-            "cpu_baseline": cpu,
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        e2e_steps = max(2, min(steps, 5))
+        dt = ctx.timed_host(e2e_step, e2e_steps, 2)
+        e2e = ctx.e2e_record(npx_all, e2e_steps, dt, npx_all * 3, npx_all * 3, bool(torch.equal(host_out, out.cpu())))
+        del host_in, host_out
+    del dev_in, out
+    torch.cuda.empty_cache()
+    if ctx.rank != 0:
+        return None
+    peak, peak_src = measured_peak()
+    step_ms = float(np.median(per_step_ms))
+    gbs = lambda ms, bpp: npx_rank * bpp / (ms * 1e-3) / 1e9
+    bpp = [6.0, 6.0] if wl["kind"] == "hed_reinhard" else [3.0, 6.0]
+    rec = {
+        "metric": metric_name(wl["method"]), "value": round(value, 1), "unit": "Mpx/s", "n_gpus": ctx.world,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms_total / steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": wl["desc"], "tiles_per_gpu": B, "tile": [H, W], "l2_policy": f"{npx_rank * 3 / 1e6:.0f} MB input per GPU, larger than the 126 MB L2"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+    }
+    for i, key in enumerate(["roofline", "roofline_2"]):
+        rec[key] = {"bound": "hbm", "kernel": parts[i][0], "achieved": round(gbs(part_ms[i], bpp[i]), 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(gbs(part_ms[i], bpp[i]) / peak, 4), "peak_source": peak_src, "algorithmic_bytes_per_px": bpp[i],
+                    "launch_ms": round(part_ms[i], 4), "share_of_step": round(part_ms[i] / step_ms, 3), "traffic": None}
+    if part_ms[1] > part_ms[0]:                        # "roofline" is the dominant kernel of the step
+        rec["roofline"], rec["roofline_2"] = rec["roofline_2"], rec["roofline"]
+    return rec
 
 
-# ----------------------------------------------------------------------------------------------- our arm
+def run_workload(ctx, name, steps, warmup, headline=False):
+    if WORKLOADS[name]["kind"] == "extractive":
+        return run_extractive(ctx, name, steps, warmup, headline)
+    return run_operator(ctx, name, steps, warmup)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="macenko512", choices=sorted(WORKLOADS))
-    ap.add_argument("--tiles", type=int, default=0, help="override tiles per GPU")
+    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS),
+                    help="all = config[1] headline + one sub-record per other workload of the north-star matrix")
+    ap.add_argument("--tiles", type=int, default=0, help="override tiles per GPU of the headline workload")
     ap.add_argument("--cluster", type=int, default=0, help="CTAs per tile (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    method, B, H, W, desc = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    strong = args.workload in STRONG and not args.tiles
-    if args.tiles:
-        B = args.tiles
-    elif strong:                                       # fixed total, contiguous shard per rank
-        B = (B * (rank + 1)) // world - (B * rank) // world
+    head = "macenko512" if args.workload == "all" else args.workload
     if args.impl == "reference":
-        return run_reference(args, method, B, H, W, desc)
+        return run_reference(args, head)
     if args.warmup < 3:
         args.warmup = 3                                # timing rule: at least 3 warm-up steps
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    # CPU baseline first (rank 0, N=1): fork-based pool must run before CUDA is initialised in this process
+    # CPU baseline (rank 0, N=1): spawned single-threaded workers, a bounded sample sized for ~10-20 s of CPU work
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_sample = 12 * (os.cpu_count() or 1) if H * W <= 512 * 512 else 3 * (os.cpu_count() or 1)
-        v, cores, dt = cpu_throughput(method, H, W, n_sample)
-        cpu = {"value": round(v, 3), "unit": "Mpx/s", "cores": cores, "kind": "port",
-               "sample": f"{n_sample} tiles of {H}x{W} ({dt:.1f} s wall), one process per core; numpy/OpenCV oracle port of "
-                         + ("augmenter.py:276-331 (skimage 0.17 rgb2hed/hed2rgb restated) + normalizer.py:70-94" if method == "hed_reinhard" else
-                            "normalizer.py:39-50 with closed-form LASSO in place of spams.lasso")}
+        wl = WORKLOADS[head]
+        pool = CpuPool(wl["method"], wl["H"], wl["W"])
+        probe, dt0 = pool.run(2 * pool.cores)
+        n_sample = int(min(max(2 * pool.cores, 12.0 / max(dt0, 1e-3) * 2 * pool.cores), 4096))
+        v, dt = pool.run(n_sample)
+        pool.close()
+        cpu = {"value": round(v, 3), "unit": "Mpx/s", "cores": pool.cores, "kind": pool.kind, "threads_per_worker": 1,
+               "per_core": round(v / pool.cores, 3), "sample": pool.describe(n_sample, dt)}
 
     import torch
     import torch.distributed as dist
-    torch.cuda.set_device(local)
-    pin_to_gpu_numa_node(local)
+    ctx = Ctx(args)
+    torch.cuda.set_device(ctx.local)
+    pin_to_gpu_numa_node(ctx.local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import stainlib_b200 as sb
-    from stainlib_b200 import _native as nv
-    from stainlib_b200.synth import synth_tile, synth_batch
+        dist.init_process_group("nccl", device_id=torch.device("cuda", ctx.local))
 
-    if method == "hed_reinhard":
-        return run_hed_reinhard(args, B, H, W, desc, rank, world, local, cpu)
-
-    kw = {"cluster_size": args.cluster} if args.cluster else {}
-    norm = sb.ExtractiveStainNormalizer(method, **kw)
-    norm.fit(synth_tile(1, H, W, kind="target") if rank == 0 else None)     # one all-reduce shares the statistics
-    pool = torch.from_numpy(synth_batch(5000 + 64 * rank, min(B, 64), H, W))
-    reps = -(-B // pool.shape[0])
-    host_in = pool.repeat(reps, 1, 1, 1)[:B].contiguous().pin_memory()
-    dev_in = host_in.cuda(non_blocking=True)
-    torch.cuda.synchronize()
-    npx_rank = B * H * W
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing
-    for _ in range(args.warmup):
-        out = norm.transform(dev_in)
-    barrier()
-    l0 = nv.launch_count(local)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local) as clocks:
-        ev[0].record()
-        for i in range(args.steps):
-            out = norm.transform(dev_in)
-            ev[i + 1].record()
-        barrier()
-    launches = nv.launch_count(local) - l0
-    ms_total = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t.item())
-    npx_all = torch.tensor([npx_rank], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(npx_all)
-    npx_all = float(npx_all.item())                     # pixels per step over all ranks (weak: world x shard; strong: the fixed total)
-    value = npx_all * args.steps / (ms_total_max * 1e-3) / 1e6
-    status_bad = int((norm.last_status != 0).sum().item())
-
-    # ---- the two kernels of a step, each timed alone with CUDA events on the launching stream
-    import ctypes
-    M_src = torch.empty(B, 2, 3, dtype=torch.float64, device="cuda")
-    maxC = torch.empty(B, 2, dtype=torch.float64, device="cuda")
-    p = norm._params()
-    h, _ = nv.get_handle(local)
-    lib = nv.load_library()
-
-    def timed(fn, n):
-        for _ in range(3):
-            fn()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a.record()
-        for _ in range(n):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / n
-
-    stats_ms = timed(lambda: nv.check(lib.sb_fit(h, nv.ptr(dev_in), B, H, W, ctypes.byref(p), nv.ptr(M_src), nv.ptr(maxC), None,
-                                                 nv.stream_ptr(local))), args.steps)
-    scale = (torch.as_tensor(norm.maxC_target, device="cuda") / maxC).contiguous()
-    Mt = torch.as_tensor(norm.stain_matrix_target, device="cuda").contiguous()
-    out2 = torch.empty_like(dev_in)
-    k4_ms = timed(lambda: nv.check(lib.sb_recombine(h, nv.ptr(dev_in), nv.ptr(out2), B, H, W, nv.ptr(M_src), nv.ptr(scale), nv.ptr(Mt), 0.01,
-                                                    nv.stream_ptr(local))), args.steps)
-    k4_match = bool(torch.equal(out2, out)) if status_bad == 0 else None
-    # plain device-to-device copy in this process, same timing method: sanity check of the box against MEASURED_PEAKS.json
-    probe = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    probe2 = torch.empty_like(probe)
-    copy_ms = timed(lambda: probe2.copy_(probe), 5)
-    hbm_probe = 2 * probe.numel() / (copy_ms * 1e-3) / 1e9
-    del probe, probe2
-
-    # ---- end to end from pinned host memory through the public API
-    e2e = None
-    if not args.no_e2e:
-        e2e_steps = args.steps if B * H * W * 3 <= (2 << 30) else max(2, min(args.steps, 3))   # huge batches: few steps
-        host_out = torch.empty_like(host_in).pin_memory()     # result buffer reused across steps (as a streaming caller would)
-        for _ in range(3 if e2e_steps == args.steps else 1):
-            norm.transform(host_in, out=host_out)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            norm.transform(host_in, out=host_out)       # synchronous: returns when the last byte is back on the host
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        same = bool(torch.equal(host_out, out.cpu()))
-        e2e = {"value": round(npx_all * e2e_steps / dt / 1e6, 1), "unit": "Mpx/s", "steps": e2e_steps,
-               "h2d_bytes_per_step": int(npx_all * 3), "d2h_bytes_per_step": int(npx_all * 3 + world * 4 * B),
-               "matches_device_path": same}
-
+    line = run_workload(ctx, head, args.steps, args.warmup, headline=True)
+    subs = {}
+    if args.workload == "all":
+        sub_steps = max(3, min(args.steps, 5))
+        for name in MATRIX:
+            try:
+                subs[name] = run_workload(ctx, name, sub_steps, 3)
+            except Exception as e:                     # a failing sub-workload must not cost the headline line
+                subs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
     if rank == 0:
-        peak, peak_src = measured_peak()
-        med_step_ms = float(np.median(per_launch_ms))
-        stats_gbs = npx_rank * 3.0 / (stats_ms * 1e-3) / 1e9
-        k4_gbs = npx_rank * BYTES_PER_PX / (k4_ms * 1e-3) / 1e9
-        step_gbs = npx_rank * BYTES_PER_PX / (med_step_ms * 1e-3) / 1e9
-        line = {
-            "metric": f"Mpixels/sec stain-normalize ({method})", "value": round(value, 1), "unit": "Mpx/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total_max / args.steps, 4),
-            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-            "dtype": "f32 per-pixel arithmetic on u8 pixels, f64 per-tile reductions", "data": "synthetic",
-            "config": {"workload": desc, "tiles_per_gpu": B, "tile": [H, W], "method": method,
-                       "l2_policy": f"input {host_in.numel() / 1e6:.0f} MB + output per GPU, larger than the 126 MB L2; no flush needed",
-                       "flagged_tiles": status_bad, "kernels_per_step": "tile_pipeline_kernel + k4_prepare_normalize_kernel + ring_pointwise_kernel<K4Op>"},
-            "clocks": clocks.summary(),
-            "e2e": e2e,
-            "gpu_launches": int(launches),
-            # dominant kernel of the step: the fused per-tile statistics kernel (read-only: 3 algorithmic bytes per pixel)
-            "roofline": {"bound": "hbm", "kernel": "tile_pipeline_kernel (mask+moments, exact angular and concentration percentiles)",
-                         "achieved": round(stats_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(stats_gbs / peak, 4),
-                         "peak_source": peak_src, "algorithmic_bytes_per_px": 3.0, "launch_ms": round(stats_ms, 4),
-                         "share_of_step": round(stats_ms / med_step_ms, 3), "traffic": ncu_traffic(args.workload, "tile_pipeline_kernel")},
-            "roofline_k4": {"bound": "hbm", "kernel": "ring_pointwise_kernel<K4Op> (fused OD+recombine on the TMA ring)",
-                            "achieved": round(k4_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(k4_gbs / peak, 4),
-                            "algorithmic_bytes_per_px": BYTES_PER_PX, "launch_ms": round(k4_ms, 4), "share_of_step": round(k4_ms / med_step_ms, 3),
-                            "bytes_equal_transform_path": k4_match, "traffic": ncu_traffic(args.workload, "ring_pointwise_kernel<K4Op>")},
-            "roofline_step": {"bound": "hbm", "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(step_gbs / peak, 4),
-                              "algorithmic_bytes_per_px": BYTES_PER_PX, "step_ms_median": round(med_step_ms, 4)},
-            "hbm_probe_gbs": round(hbm_probe, 1),
-            "cpu_baseline": cpu,
-        }
+        # plain device-to-device copy in this process, same timing method: sanity check of the box against MEASURED_PEAKS.json
+        probe = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        probe2 = torch.empty_like(probe)
+        copy_ms = ctx.timed_alone(lambda: probe2.copy_(probe), 5)
+        line["hbm_probe_gbs"] = round(2 * probe.numel() / (copy_ms * 1e-3) / 1e9, 1)
+        line["cpu_baseline"] = cpu
+        line["lib_sha16"] = lib_sha16()
+        if subs:
+            line["workloads"] = subs
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -12,13 +12,23 @@
  *   - images are uint8, C-contiguous [B,H,W,3] RGB; "tile" = one [H,W,3] image; N = H*W.
  *   - stain matrices are double [B,2,3] (rows = stains, H first), maxC / scale / alpha / beta are double [B,2].
  *   - work is stream-ordered on `stream` (a cudaStream_t passed as void*); nothing synchronises unless stated.
- *   - the caller owns every buffer; the library allocates only inside sb_create / the *_host staging.
+ *   - the caller owns every image / matrix / status buffer.  The library allocates device memory in sb_create (constant
+ *     tables), in the *_host entry points (staging slots, kept in the handle) and, per call, a few hundred bytes per tile
+ *     of scratch (per-tile constants and statistics; 2 bytes per 16 pixels more for Vahadane on tiles > 512x512).  That
+ *     scratch comes from the workspace lent with sb_set_workspace() when one is set and large enough
+ *     (sb_workspace_bytes() says how much a batch needs), else from the device's stream-ordered memory pool
+ *     (cudaMallocAsync / cudaFreeAsync on the call's stream: no synchronisation, no cudaMalloc on the hot path).
+ *   - every entry point runs on the device of its handle and restores the caller's current device before returning;
+ *     a process may hold one handle per device.
+ *   - a tile's outputs do not depend on the batch it is in, on how the batch is chunked or sharded, or on the
+ *     cluster_size the launcher picks: per-tile sums are fixed-point integers (SURVEY section 8-e determinism).
  *   - per-tile int32 status word instead of raising mid-batch (bits below); outputs of flagged tiles are defined
  *     as documented per function.
  */
 #ifndef STAINB200_H
 #define STAINB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -70,6 +80,23 @@ const char* sb_last_cuda_error(void);
 int  sb_version(void);
 /* number of kernel launches issued through this handle since creation (bench.py's gpu_launches) */
 long long sb_launch_count(const sb_handle* h);
+
+/* Caller-owned scratch (SURVEY section 8-b "ownership").  sb_workspace_bytes: upper bound of the per-call scratch any
+ * entry point takes for a [B,H,W,3] batch.  sb_set_workspace lends `bytes` of DEVICE memory to the handle (NULL, 0
+ * takes it back); calls whose scratch fits use it instead of the stream-ordered pool.  The lender must keep it alive
+ * until the last call that used it has finished on its stream, and must not run calls of one handle on two streams at
+ * once while a workspace is set. */
+size_t sb_workspace_bytes(int B, int H, int W);
+int    sb_set_workspace(sb_handle* h, void* device_mem, size_t bytes);
+
+/* convert_RGB_to_OD -- stainlib/utils/stain_utils.py:101-112: od[i] = max(-ln(max(rgb[i], 1) / 255), 1e-6) for n_values
+ * uint8 values (any shape, flattened); od: device double [n_values] (float when out_f32 != 0). */
+int sb_rgb_to_od(sb_handle* h, const uint8_t* rgb, size_t n_values, void* od, int out_f32, void* stream);
+
+/* convert_OD_to_RGB -- stainlib/utils/stain_utils.py:114-124: rgb[i] = uint8(255 * exp(-max(od[i], 1e-6))), truncated.
+ * od: device double [n_values] (float when in_f32 != 0).  negative (device int32, may be NULL; zero it first) is set to 1
+ * when some od[i] < 0, where the reference asserts. */
+int sb_od_to_rgb(sb_handle* h, const void* od, int in_f32, size_t n_values, uint8_t* rgb, int32_t* negative, void* stream);
 
 /* LuminosityThresholdTissueLocator.get_tissue_mask -- stainlib/utils/stain_utils.py:32-48.
  * mask: uint8 [B,H,W] (1 = tissue).  status bit SB_STATUS_EMPTY_MASK where the reference would raise. */
@@ -166,10 +193,19 @@ int sb_luminosity_standardize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_
 
 /* HedColorAugmenter.transform -- augmenter.py:276-331 for given draws.  sigma/bias: device double [B,3] (H,E,D);
  * tiles whose mean/255 lies outside [cutoff_lo, cutoff_hi] are copied through (status bit 0 set to 1 = skipped).
- * log_base: 10 = scikit-image 0.16-0.17 (pinned by the reference's environment.yml), e = <= 0.15. */
+ * skimage_variant selects the definition of skimage.color.rgb2hed / hed2rgb (augmenter.py:295,319):
+ *   17  scikit-image 0.16-0.17 (pinned by the reference's environment.yml:107): -log_b(rgb + 2) @ inv(M), log_base 10
+ *       (pass log_base e for scikit-image <= 0.15);
+ *   18  scikit-image >= 0.18 (what the unpinned setup.py:11-18 installs today): max(0, ln(max(rgb,1e-6))/ln(1e-6) @ inv(M))
+ *       and exp(ln(1e-6) hed @ M) clipped to [0,1]; log_base is ignored. */
 int sb_hed_augment(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const double* sigma,
-                   const double* bias, double cutoff_lo, double cutoff_hi, double log_base, int32_t* status,
-                   void* stream);
+                   const double* bias, double cutoff_lo, double cutoff_hi, double log_base, int skimage_variant,
+                   int32_t* status, void* stream);
+/* The same for float patches (augmenter.py:288-291, 323-327: a float image in [0,1] is taken as it is and a float image
+ * is returned): rgb_in / rgb_out device float [B,H,W,3]. */
+int sb_hed_augment_f32(sb_handle* h, const float* rgb_in, float* rgb_out, int B, int H, int W, const double* sigma,
+                       const double* bias, double cutoff_lo, double cutoff_hi, double log_base, int skimage_variant,
+                       int32_t* status, void* stream);
 
 /* GrayscaleAugmentor.pop -- augmenter.py:390-401 for given draws alpha/beta: device double [B]. */
 int sb_grayscale_augment(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W,

@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY -- loads the *real* reference package from /root/reference (build container only).
+"""TEST INFRASTRUCTURE ONLY -- loads the *real* reference package from /root/reference (build container) or from the
+pip --target copy under baseline/_ref (git-ignored; travels to the GPU box for bench.py's CPU reference arm).
 
 ``import stainlib`` fails in this image because ``spams``, ``skimage`` and ``pylab`` are not installed
 (``stain_utils.py:3``, ``augmenter.py:5,10``).  This loader injects three stub modules so that the reference's own,
@@ -21,7 +22,7 @@ import types
 REFERENCE_ROOT = "/root/reference"
 
 
-def load_reference(n_iter_traindl=50):
+def load_reference(n_iter_traindl=50, root=None):
     import scipy.sparse as sp
     from oracle import stain_oracle as so
 
@@ -50,11 +51,12 @@ def load_reference(n_iter_traindl=50):
     sys.modules.setdefault("skimage", skimage)
     sys.modules.setdefault("skimage.color", color)
     sys.modules.setdefault("pylab", pylab)
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = root or REFERENCE_ROOT
+    if root not in sys.path:
+        sys.path.insert(0, root)
     for name in [m for m in sys.modules if m == "stainlib" or m.startswith("stainlib.")]:
         del sys.modules[name]
     ref = importlib.import_module("stainlib")
     importlib.import_module("stainlib.augmentation.augmenter")
-    assert ref.__file__.startswith(REFERENCE_ROOT), ref.__file__
+    assert ref.__file__.startswith(root), ref.__file__
     return ref

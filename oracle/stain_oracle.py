@@ -461,20 +461,40 @@ def hed2rgb(hed, log_base=10.0):
     return np.clip(out, -1.0, 1.0)
 
 
-def hed_augment(patch, sigmas, biases, cutoff_range=(0.05, 0.95), log_base=10.0):
-    """``HedColorAugmenter.transform`` -- ``augmenter.py:276-331`` for a fixed draw of (sigmas, biases)."""
+def rgb2hed_018(rgb):
+    """scikit-image >= 0.18 ``separate_stains(rgb, hed_from_rgb)`` [restated from the published source; PARITY UNPINNED]:
+    ``rgb = max(img_as_float(rgb), 1e-6); stains = (log(rgb) / log(1e-6)) @ conv; max(stains, 0)``."""
+    x = rgb.astype(np.float64) / 255.0 if rgb.dtype.kind != "f" else rgb.astype(np.float64)
+    x = np.maximum(x, 1e-6)
+    stains = np.reshape(np.log(x) / np.log(1e-6), (-1, 3)) @ HED_FROM_RGB
+    return np.reshape(np.maximum(stains, 0.0), rgb.shape)
+
+
+def hed2rgb_018(hed):
+    """scikit-image >= 0.18 ``combine_stains(hed, rgb_from_hed)``: ``exp(-(hed * -log(1e-6)) @ conv)`` clipped to [0, 1]."""
+    log_rgb = -(np.reshape(hed.astype(np.float64), (-1, 3)) * (-np.log(1e-6))) @ RGB_FROM_HED
+    return np.clip(np.reshape(np.exp(log_rgb), hed.shape), 0.0, 1.0)
+
+
+def hed_augment(patch, sigmas, biases, cutoff_range=(0.05, 0.95), log_base=10.0, skimage_version="0.17"):
+    """``HedColorAugmenter.transform`` -- ``augmenter.py:276-331`` for a fixed draw of (sigmas, biases).
+    ``skimage_version``: "0.17" (pinned by environment.yml:107) or "0.18" (the >= 0.18 definition of rgb2hed/hed2rgb)."""
+    if skimage_version == "0.18":
+        to_hed, to_rgb = (lambda p, _b: rgb2hed_018(p)), (lambda h, _b: hed2rgb_018(h))
+    else:
+        to_hed, to_rgb = rgb2hed, hed2rgb
     if patch.dtype.kind == "f":
         patch_mean = np.mean(a=patch)
     else:
         patch_mean = np.mean(a=patch.astype(dtype=np.float32)) / 255.0
     if cutoff_range[0] <= patch_mean <= cutoff_range[1]:
-        patch_hed = rgb2hed(patch, log_base)
+        patch_hed = to_hed(patch, log_base)
         for k in range(3):
             if sigmas[k] != 0.0:
                 patch_hed[:, :, k] *= 1.0 + sigmas[k]
             if biases[k] != 0.0:
                 patch_hed[:, :, k] += biases[k]
-        patch_rgb = hed2rgb(patch_hed, log_base)
+        patch_rgb = to_rgb(patch_hed, log_base)
         patch_transformed = np.clip(a=patch_rgb, a_min=0.0, a_max=1.0)
         if patch.dtype.kind != "f":
             patch_transformed *= 255.0

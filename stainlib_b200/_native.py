@@ -26,6 +26,7 @@ EXPORTS = [
     "sb_concentrations", "sb_recombine", "sb_stain_augment", "sb_reinhard_stats", "sb_reinhard_transform",
     "sb_luminosity_standardize", "sb_hed_augment", "sb_grayscale_augment",
     "sb_slide_grid", "sb_slide_moments", "sb_slide_angle_hist", "sb_slide_conc_hist", "sb_slide_dl_sums", "sb_decode_jpeg",
+    "sb_workspace_bytes", "sb_set_workspace", "sb_rgb_to_od", "sb_od_to_rgb", "sb_hed_augment_f32",
 ]
 
 
@@ -87,7 +88,13 @@ def load_library():
         lib.sb_reinhard_stats.argtypes = [vp, vp, ci, ci, ci, vp, vp, vp]
         lib.sb_reinhard_transform.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, ci, cd, vp, vp]
         lib.sb_luminosity_standardize.argtypes = [vp, vp, vp, ci, ci, ci, cd, vp]
-        lib.sb_hed_augment.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, cd, cd, cd, vp, vp]
+        lib.sb_hed_augment.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, cd, cd, cd, ci, vp, vp]
+        lib.sb_hed_augment_f32.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, cd, cd, cd, ci, vp, vp]
+        lib.sb_workspace_bytes.argtypes = [ci, ci, ci]
+        lib.sb_workspace_bytes.restype = ctypes.c_size_t
+        lib.sb_set_workspace.argtypes = [vp, vp, ctypes.c_size_t]
+        lib.sb_rgb_to_od.argtypes = [vp, vp, ctypes.c_size_t, vp, ci, vp]
+        lib.sb_od_to_rgb.argtypes = [vp, vp, ci, ctypes.c_size_t, vp, vp, vp]
         lib.sb_grayscale_augment.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp]
         lib.sb_decode_jpeg.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp]
         lib.sb_slide_grid.argtypes = [vp, ci, ci, ci]
@@ -96,7 +103,7 @@ def load_library():
         lib.sb_slide_conc_hist.argtypes = [vp, vp, ci, ci, ci, vp, cd, ci, vp, vp, vp]
         lib.sb_slide_dl_sums.argtypes = [vp, vp, ci, ci, ci, cd, vp, cd, ci, vp, vp]
         for name in EXPORTS:
-            if name not in ("sb_default_params", "sb_error_string", "sb_last_cuda_error", "sb_launch_count"):
+            if name not in ("sb_default_params", "sb_error_string", "sb_last_cuda_error", "sb_launch_count", "sb_workspace_bytes"):
                 getattr(lib, name).restype = ci
         _lib = lib
         return lib
@@ -139,6 +146,27 @@ def get_handle(device=None):
         h = hp
         _handles[idx] = h
     return h, idx
+
+
+def set_workspace(tensor, device=None):
+    """Lends ``tensor`` (a CUDA uint8 tensor, or None to take it back) to the device's handle as per-call scratch
+    (include/stainb200.h: sb_set_workspace); ``workspace_bytes(B, H, W)`` says how much a batch needs.  The tensor must
+    stay alive while it is lent: the handle cache keeps a reference."""
+    h, idx = get_handle(device if tensor is None else tensor.device)
+    if tensor is None:
+        check(load_library().sb_set_workspace(h, None, 0))
+        _workspaces.pop(idx, None)
+        return
+    assert tensor.is_cuda and tensor.dtype == torch.uint8 and tensor.is_contiguous()
+    check(load_library().sb_set_workspace(h, ctypes.c_void_p(tensor.data_ptr()), tensor.numel()))
+    _workspaces[idx] = tensor
+
+
+def workspace_bytes(B, H, W):
+    return int(load_library().sb_workspace_bytes(int(B), int(H), int(W)))
+
+
+_workspaces = {}
 
 
 def launch_count(device=None):

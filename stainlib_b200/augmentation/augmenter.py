@@ -16,6 +16,19 @@ from stainlib_b200.utils.excepts import InvalidRangeError
 from stainlib_b200.utils.stain_utils import LuminosityThresholdTissueLocator, get_concentrations, is_uint8_image
 
 HED_LOG_BASE = 10.0   # scikit-image 0.16-0.17 (pinned 0.17.2 in the reference's environment.yml:107); use np.e for <= 0.15
+# Which skimage.color.rgb2hed / hed2rgb the augmenters reproduce (augmenter.py:295,319): "0.17" = the version pinned by
+# the reference's environment.yml (-log10(rgb + 2) @ inv(M)); "0.18" = scikit-image >= 0.18, which is what the
+# reference's unpinned setup.py installs today (max(0, ln(max(rgb, 1e-6)) / ln(1e-6) @ inv(M)), no "+2").
+HED_SKIMAGE = "0.17"
+
+
+def _hed_variant(v):
+    v = str(HED_SKIMAGE if v is None else v)
+    if v in ("0.17", "0.16", "17"):
+        return 17
+    if v in ("0.18", "18") or v.startswith("0.19") or v.startswith("0.2"):
+        return 18
+    raise ValueError(f"unknown scikit-image variant {v!r}: use '0.17' or '0.18'")
 
 
 class AugmenterBase(object):
@@ -97,27 +110,63 @@ class HedColorAugmenter(ColorAugmenterBase):
         self._biases = [np.random.uniform(low=r[0], high=r[1], size=None) if r is not None else 0.0
                         for r in self._bias_ranges]
 
-    def transform(self, patch, sigmas=None, biases=None):
+    def transform(self, patch, sigmas=None, biases=None, skimage_version=None):
         """Apply the colour deformation (augmenter.py:276-331).  ``sigmas`` / ``biases`` ([B,3]) override the
-        instance's current draw for batched calls with per-tile parameters."""
-        if isinstance(patch, np.ndarray) and patch.dtype.kind == "f":
-            raise NotImplementedError("float patches are not supported by the CUDA path; pass uint8")
+        instance's current draw for batched calls with per-tile parameters.  Float patches (values in [0,1]) are
+        transformed as they are and come back as floats of the same dtype, like the reference (augmenter.py:288-291,
+        323-327).  ``skimage_version``: "0.17" / "0.18" (default: the module's HED_SKIMAGE)."""
+        import ctypes
+        variant = _hed_variant(skimage_version)
+        is_float = (isinstance(patch, np.ndarray) and patch.dtype.kind == "f") or \
+                   (isinstance(patch, torch.Tensor) and patch.dtype.is_floating_point)
+        lib = nv.load_library()
+        if is_float:
+            return self._transform_float(patch, sigmas, biases, variant)
         assert is_uint8_image(patch), "Image should be RGB uint8."
         b = nv.Batch(patch)
-        sg = np.broadcast_to(np.asarray(self._sigmas if sigmas is None else sigmas, dtype=np.float64), (b.B, 3))
-        bs = np.broadcast_to(np.asarray(self._biases if biases is None else biases, dtype=np.float64), (b.B, 3))
-        par = torch.as_tensor(np.ascontiguousarray(np.concatenate([sg, bs], axis=0))).to(b.dev.device)
+        par = self._params_on_device(b.B, sigmas, biases, b.dev.device)
         out = b.new_like()
         status = b.dev_tensor((b.B,), torch.int32)
-        import ctypes
-        nv.check(nv.load_library().sb_hed_augment(
+        nv.check(lib.sb_hed_augment(
             b.handle, nv.ptr(b.dev), nv.ptr(out), b.B, b.H, b.W, nv.ptr(par), ctypes.c_void_p(par.data_ptr() + b.B * 24),
-            float(self._cutoff_range[0]), float(self._cutoff_range[1]), float(HED_LOG_BASE), nv.ptr(status),
+            float(self._cutoff_range[0]), float(self._cutoff_range[1]), float(HED_LOG_BASE), variant, nv.ptr(status),
             nv.stream_ptr(b.idx)))
         self.last_status = status
         if b.single and b.kind == "numpy" and int(status[0]) == 1:
             return patch          # outside the cutoff the reference returns the same object (augmenter.py:329-331)
         return b.give_back(out)
+
+    def _params_on_device(self, B, sigmas, biases, device):
+        sg = np.broadcast_to(np.asarray(self._sigmas if sigmas is None else sigmas, dtype=np.float64), (B, 3))
+        bs = np.broadcast_to(np.asarray(self._biases if biases is None else biases, dtype=np.float64), (B, 3))
+        return torch.as_tensor(np.ascontiguousarray(np.concatenate([sg, bs], axis=0))).to(device)
+
+    def _transform_float(self, patch, sigmas, biases, variant):
+        import ctypes
+        is_np = isinstance(patch, np.ndarray)
+        t = torch.from_numpy(np.ascontiguousarray(patch)) if is_np else patch
+        assert t.dim() in (3, 4) and t.shape[-1] == 3, "Image should be RGB."
+        single = t.dim() == 3
+        h, idx = nv.get_handle(t.device if t.is_cuda else None)
+        dev = t.to(device=f"cuda:{idx}", dtype=torch.float32).contiguous()
+        if single:
+            dev = dev[None]
+        B, H, W = int(dev.shape[0]), int(dev.shape[1]), int(dev.shape[2])
+        par = self._params_on_device(B, sigmas, biases, dev.device)
+        out = torch.empty_like(dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev.device)
+        nv.check(nv.load_library().sb_hed_augment_f32(
+            h, nv.ptr(dev), nv.ptr(out), B, H, W, nv.ptr(par), ctypes.c_void_p(par.data_ptr() + B * 24),
+            float(self._cutoff_range[0]), float(self._cutoff_range[1]), float(HED_LOG_BASE), variant, nv.ptr(status),
+            nv.stream_ptr(idx)))
+        self.last_status = status
+        if single and is_np and int(status[0]) == 1:
+            return patch
+        out = out[0] if single else out
+        out = out.to(t.dtype)
+        if is_np:
+            return out.cpu().numpy()
+        return out if t.is_cuda else out.cpu()
 
 
 class HedColorAugmenter1(HedColorAugmenter):

@@ -67,6 +67,9 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
                  const double* Mt, const double* maxCt, double* M, double* maxC, int32_t* status, cudaStream_t stream) {
     if (!p) return SB_ERR_ARG;
     if (p->method != SB_METHOD_MACENKO && p->method != SB_METHOD_VAHADANE) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::Scratch scratch(h, stream);
     sb::PipeArgs a{};
     a.in = in; a.out = out; a.B = B; a.npx = H * W;
     a.aligned = is_aligned(in, out ? out : in, a.npx);
@@ -81,11 +84,11 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
     a.dl_anderson = p->dl_anderson < 0 ? 0 : (p->dl_anderson > sb::AA_MAX ? sb::AA_MAX : p->dl_anderson);
     a.Mt = Mt; a.maxCt = maxCt;
     // Vahadane re-reads the tissue mask in every dictionary pass; tiles whose per-CTA share exceeds the shared-memory
-    // cache (262,144 pixels) keep it in a stream-ordered global scratch instead of recomputing it
+    // cache (262,144 pixels) keep it in per-call scratch instead of recomputing it
     unsigned short* mask_scratch = nullptr;
     const int groups = (a.npx + sb::GROUP_PX - 1) / sb::GROUP_PX;
     if (p->method == SB_METHOD_VAHADANE && groups / a.cluster_size > 16384)
-        SB_CUDA(cudaMallocAsync(&mask_scratch, (size_t)B * groups * sizeof(unsigned short), stream));
+        SB_CUDA(scratch.get(&mask_scratch, (size_t)B * groups * sizeof(unsigned short)));
     a.mask_scratch = mask_scratch;
     {
         // bracket half-width: the rule in plan_bracket (sb_pipeline.cu) unless a sweep overrides it through the environment
@@ -97,34 +100,51 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
         a.bracket_sigmas = sig; a.bracket_pad = pad;
     }
     if (mode != sb::PIPE_NORMALIZE) {
+        sb::NvtxRange nvtx(mode == sb::PIPE_FIT ? "sb_fit: tile_pipeline" : "sb_extract: tile_pipeline");
         a.mode = mode; a.M_out = M; a.maxC_out = maxC; a.status = status;
         cudaError_t e = (cudaError_t)sb::launch_tile_pipeline(a, h->num_sms, stream);
-        if (mask_scratch) cudaFreeAsync(mask_scratch, stream);
         if (e != cudaSuccess) return cuda_fail(e, "tile_pipeline launch");
         h->launches += 1;
         return SB_OK;
     }
     // transform = fused per-tile statistics kernel (stain matrix + maxC of every source tile) followed by the
-    // TMA-ring recombine kernel on the same stream; the statistics go through a stream-ordered workspace unless the
-    // caller asked for them.
+    // TMA-ring recombine kernel on the same stream; the statistics go through per-call scratch unless the caller asked
+    // for them.
     double* ws = nullptr;
     const size_t need = (size_t)B * 8 * sizeof(double) + (size_t)B * sizeof(int32_t);
-    if (!M || !maxC || !status) SB_CUDA(cudaMallocAsync(&ws, need, stream));
+    if (!M || !maxC || !status) SB_CUDA(scratch.get(&ws, need));
     double* Mw = M ? M : ws;
     double* Cw = maxC ? maxC : ws + (size_t)B * 6;
     int32_t* Sw = status ? status : reinterpret_cast<int32_t*>(ws + (size_t)B * 8);
     a.mode = sb::PIPE_FIT; a.M_out = Mw; a.maxC_out = Cw; a.status = Sw;
-    cudaError_t e = (cudaError_t)sb::launch_tile_pipeline(a, h->num_sms, stream);
-    if (mask_scratch) cudaFreeAsync(mask_scratch, stream);
+    cudaError_t e;
+    {
+        sb::NvtxRange nvtx("sb_normalize: tile_pipeline (statistics)");
+        e = (cudaError_t)sb::launch_tile_pipeline(a, h->num_sms, stream);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "tile_pipeline launch");
     sb::PointArgs k{};
     k.in = in; k.out = out; k.B = B; k.npx = a.npx; k.aligned = a.aligned; k.tab = h->tab; k.lasso_lambda = p->lasso_lambda;
     const bool tma = a.aligned && getenv("SB_K4_NO_TMA") == nullptr;
-    e = (cudaError_t)sb::launch_recombine_normalize(k, h->num_sms, stream, tma, Mw, Cw, Mt, maxCt, Sw);
-    if (ws) cudaFreeAsync(ws, stream);
+    {
+        sb::NvtxRange nvtx("sb_normalize: K4 recombine");
+        e = (cudaError_t)sb::launch_recombine_normalize(k, scratch, tma, Mw, Cw, Mt, maxCt, Sw);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "recombine launch");
     h->launches += 3;
     return SB_OK;
+}
+
+// Bytes of per-call scratch the entry points take for a batch (upper bound over all of them).
+size_t workspace_bytes(int B, int H, int W) {
+    const size_t groups = ((size_t)H * W + sb::GROUP_PX - 1) / sb::GROUP_PX;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t n = 0;
+    n += up((size_t)B * groups * sizeof(unsigned short));                        // Vahadane mask bits of big tiles
+    n += up((size_t)B * 8 * sizeof(double) + (size_t)B * sizeof(int32_t));      // per-tile statistics of sb_normalize
+    n += up((size_t)B * 128);                                                    // per-tile constants of the ring operators
+    n += up((size_t)B * 16);                                                     // HED byte sums / counters
+    return n;
 }
 
 }  // namespace
@@ -164,7 +184,10 @@ int sb_create(int device, sb_handle** out) {
     if (!out) return SB_ERR_ARG;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return SB_ERR_NO_DEVICE;
-    SB_CUDA(cudaSetDevice(device));
+    sb_handle probe;
+    probe.device = device;
+    sb::DeviceGuard guard(&probe);          // runs on `device`, restores the caller's current device on return
+    if (!guard.ok) return SB_ERR_CUDA;
     cudaDeviceProp prop;
     SB_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return SB_ERR_NO_DEVICE;   // kernels are built for sm_100a only
@@ -213,7 +236,8 @@ int sb_create(int device, sb_handle** out) {
 
 int sb_destroy(sb_handle* h) {
     if (!h) return SB_ERR_ARG;
-    cudaSetDevice(h->device);
+    {
+    sb::DeviceGuard guard(h);
     for (int i = 0; i < sb_handle::NSLOT; ++i) {
         if (h->slot_in[i]) cudaFree(h->slot_in[i]);
         if (h->slot_out[i]) cudaFree(h->slot_out[i]);
@@ -227,6 +251,7 @@ int sb_destroy(sb_handle* h) {
     if (h->d_target) cudaFree(h->d_target);
     if (h->d_status) cudaFree(h->d_status);
     if (h->table_mem) cudaFree(h->table_mem);
+    }
     delete h;
     return SB_OK;
 }
@@ -237,6 +262,9 @@ int sb_tissue_mask(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double
     if (rc) return rc;
     if (!mask) return SB_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_tissue_mask");
     sb::PointArgs a{};
     a.in = rgb; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb, mask, a.npx) && (a.npx % 16 == 0);
     a.tab = h->tab; a.ybound = mask_ybound_f(luminosity_threshold); a.mask_out = mask; a.status = status;
@@ -294,6 +322,9 @@ int sb_slide_moments(sb_handle* h, const uint8_t* rgb, int B, int H, int W, doub
     sb::SlideArgs a;
     int rc = slide_args(h, rgb, B, H, W, luminosity_threshold, a);
     if (rc) return rc;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_slide pass");
     if (!partials) return SB_ERR_ARG;
     a.sums = partials;
     cudaError_t e = (cudaError_t)sb::launch_slide_pass(a, 0, sb::slide_grid(a, h->num_sms), (cudaStream_t)stream);
@@ -307,6 +338,9 @@ int sb_slide_angle_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, d
     sb::SlideArgs a;
     int rc = slide_args(h, rgb, B, H, W, luminosity_threshold, a);
     if (rc) return rc;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_slide pass");
     if (!V || !hist || (level != 1 && level != 2) || (level == 2 && !bins)) return SB_ERR_ARG;
     for (int k = 0; k < 6; ++k) a.V[k] = (float)V[k];
     for (int k = 0; k < 4; ++k) a.bins[k] = level == 2 ? bins[k] : 0u;
@@ -322,6 +356,9 @@ int sb_slide_dl_sums(sb_handle* h, const uint8_t* rgb, int B, int H, int W, doub
     sb::SlideArgs a;
     int rc = slide_args(h, rgb, B, H, W, luminosity_threshold, a);
     if (rc) return rc;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_slide pass");
     if (!D || !partials) return SB_ERR_ARG;
     sb::make_lasso_consts(D, dl_lambda, a.lk);
     a.sums = partials;
@@ -336,6 +373,9 @@ int sb_slide_conc_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, co
     sb::SlideArgs a;
     int rc = slide_args(h, rgb, B, H, W, 0.8, a);
     if (rc) return rc;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_slide pass");
     if (!M || !hist || (level != 1 && level != 2) || (level == 2 && !bins)) return SB_ERR_ARG;
     sb::make_lasso_consts(M, lasso_lambda, a.lk);
     for (int k = 0; k < 4; ++k) a.bins[k] = level == 2 ? bins[k] : 0u;
@@ -351,7 +391,9 @@ int sb_normalize_host(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int
     int rc = check_image_args(h, rgb_in, B, H, W);
     if (rc) return rc;
     if (!rgb_out || !M_target || !maxC_target || !p) return SB_ERR_ARG;
-    SB_CUDA(cudaSetDevice(h->device));
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_normalize_host");
     const size_t tile_bytes = (size_t)H * W * 3;
     if (chunk_tiles <= 0) {
         chunk_tiles = (int)(((size_t)12 << 20) / tile_bytes);   // 12 MB chunks: short fill/drain, still link-rate copies (tools/pcie_probe.py)
@@ -425,6 +467,9 @@ int sb_concentrations(sb_handle* h, const uint8_t* rgb, int B, int H, int W, con
     int rc = check_image_args(h, rgb, B, H, W);
     if (rc) return rc;
     if (!M || !C) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_concentrations");
     sb::PointArgs a{};
     a.in = rgb; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb, rgb, a.npx);
     a.tab = h->tab; a.M = M; a.lasso_lambda = lasso_lambda; a.conc_out = C;
@@ -439,13 +484,17 @@ int sb_recombine(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, i
     int rc = check_image_args(h, rgb_in, B, H, W);
     if (rc) return rc;
     if (!rgb_out || !M_src || !scale || !M_target) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_recombine (K4)");
+    sb::Scratch scratch(h, (cudaStream_t)stream);
     sb::PointArgs a{};
     a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb_in, rgb_out, a.npx);
     a.tab = h->tab; a.M = M_src; a.scale = scale; a.Mt = M_target; a.lasso_lambda = lasso_lambda;
     // TMA-staged ring when every tile is a whole number of 16-byte vectors; register-staged kernel otherwise
     const bool tma = a.aligned && getenv("SB_K4_NO_TMA") == nullptr;
     a.debug_copy = getenv("SB_K4_COPY") != nullptr;
-    cudaError_t e = (cudaError_t)sb::launch_recombine(a, h->num_sms, (cudaStream_t)stream, tma);
+    cudaError_t e = (cudaError_t)sb::launch_recombine(a, scratch, tma);
     if (e != cudaSuccess) return cuda_fail(e, "recombine launch");
     h->launches += 2;
     return SB_OK;
@@ -457,13 +506,53 @@ int sb_stain_augment(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int 
     int rc = check_image_args(h, rgb_in, B, H, W);
     if (rc) return rc;
     if (!rgb_out || !M || !alpha || !beta) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_stain_augment");
+    sb::Scratch scratch(h, (cudaStream_t)stream);
     sb::PointArgs a{};
     a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb_in, rgb_out, a.npx);
     a.tab = h->tab; a.M = M; a.scale = alpha; a.beta = beta; a.lasso_lambda = lasso_lambda;
     a.augment_background = augment_background; a.ybound = mask_ybound_f(luminosity_threshold);
     for (int c = 0; c < 3; ++c) a.ycoef[c] = (float)SB_RGB2LAB_COEFFS[3 + c];
-    cudaError_t e = (cudaError_t)sb::launch_stain_augment(a, h->num_sms, (cudaStream_t)stream);
+    cudaError_t e = (cudaError_t)sb::launch_stain_augment(a, scratch);
     if (e != cudaSuccess) return cuda_fail(e, "stain_augment launch");
+    h->launches += 1;
+    return SB_OK;
+}
+
+size_t sb_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return workspace_bytes(B, H, W);
+}
+
+int sb_set_workspace(sb_handle* h, void* device_mem, size_t bytes) {
+    if (!h || (device_mem == nullptr) != (bytes == 0)) return SB_ERR_ARG;
+    if (h->scratch_depth != 0) return SB_ERR_ARG;
+    h->user_ws = static_cast<unsigned char*>(device_mem);
+    h->user_ws_bytes = bytes;
+    h->user_ws_off = 0;
+    return SB_OK;
+}
+
+int sb_rgb_to_od(sb_handle* h, const uint8_t* rgb, size_t n_values, void* od, int out_f32, void* stream) {
+    if (!h || !rgb || !od || n_values == 0) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_rgb_to_od");
+    cudaError_t e = (cudaError_t)sb::launch_rgb_to_od(rgb, od, n_values, out_f32, h->tab.od64, h->num_sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "rgb_to_od launch");
+    h->launches += 1;
+    return SB_OK;
+}
+
+int sb_od_to_rgb(sb_handle* h, const void* od, int in_f32, size_t n_values, uint8_t* rgb, int32_t* negative, void* stream) {
+    if (!h || !od || !rgb || n_values == 0) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_od_to_rgb");
+    cudaError_t e = (cudaError_t)sb::launch_od_to_rgb(od, rgb, n_values, in_f32, negative, h->num_sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "od_to_rgb launch");
     h->launches += 1;
     return SB_OK;
 }

@@ -252,6 +252,108 @@ __global__ void __launch_bounds__(NT, 2) lab_tile_kernel(LabArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------ HED
+// Two definitions of skimage.color.rgb2hed / hed2rgb exist (call sites augmenter.py:295,319):
+//   variant 17 (scikit-image 0.16-0.17, pinned by the reference's environment.yml:107; base e before 0.16):
+//       hed = -log_b(rgb + 2) @ inv(M);  rgb' = clip(b^(-hed' @ M) - 2, -1, 1)                  -> affine in log space:
+//       log2(rgb' + 2) = log2(rgb + 2) @ A - c,  A = inv(M) diag(1+sigma) M,  c = (bias @ M) log2(b)
+//   variant 18 (scikit-image >= 0.18, what an unpinned `pip install scikit-image` gives today -- setup.py:11-18):
+//       hed = max(0, (ln(max(rgb, 1e-6)) / ln(1e-6)) @ inv(M));  rgb' = clip(exp(ln(1e-6) * (hed' @ M)), 0, 1)
+//       -> L = ln(max(rgb, 1e-6)) / ln(1e-6) (table), s = max(0, L @ inv(M)), log2(rgb') = s @ Q + r with
+//          Q = ln(1e-6) log2(e) diag(1+sigma) M,  r = ln(1e-6) log2(e) (bias @ M).
+// M = rgb_from_hed.  In both cases the result is clipped to [0,1], scaled by 255 and truncated (augmenter.py:320-325).
+struct HedMats { double M[9], Mi[9]; };
+__host__ __device__ inline HedMats hed_mats() {
+    HedMats h;
+    const double M[9] = {0.65, 0.70, 0.29, 0.07, 0.99, 0.11, 0.27, 0.57, 0.78};
+    for (int i = 0; i < 9; ++i) h.M[i] = M[i];
+    const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+    h.Mi[0] = (M[4] * M[8] - M[5] * M[7]) / det; h.Mi[1] = (M[2] * M[7] - M[1] * M[8]) / det; h.Mi[2] = (M[1] * M[5] - M[2] * M[4]) / det;
+    h.Mi[3] = (M[5] * M[6] - M[3] * M[8]) / det; h.Mi[4] = (M[0] * M[8] - M[2] * M[6]) / det; h.Mi[5] = (M[2] * M[3] - M[0] * M[5]) / det;
+    h.Mi[6] = (M[3] * M[7] - M[4] * M[6]) / det; h.Mi[7] = (M[1] * M[6] - M[0] * M[7]) / det; h.Mi[8] = (M[0] * M[4] - M[1] * M[3]) / det;
+    return h;
+}
+constexpr double HED18_LN = -13.815510557964274;          // ln(1e-6)
+constexpr double HED_LOG2E = 1.4426950408889634;
+// Per-tile constants of either variant: A[9] (row-major, input channel x output channel) and the additive c[3], such that
+// the exponent of output channel j is  c[j] + sum_i x_i A[3 i + j]  (x = table values for 17, clamped stains for 18).
+struct HedConsts { float A[9]; float c[3]; };
+__host__ __device__ inline void hed_consts(int variant, const double* sigma, const double* bias, double log_base, HedConsts& k) {
+    const HedMats h = hed_mats();
+    if (variant == 18) {
+        const double f = HED18_LN * HED_LOG2E;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) k.A[3 * i + j] = (float)(f * (1.0 + sigma[i]) * h.M[3 * i + j]);
+        for (int j = 0; j < 3; ++j) {
+            double v = 0.0;
+            for (int q = 0; q < 3; ++q) v += bias[q] * h.M[3 * q + j];
+            k.c[j] = (float)(f * v);
+        }
+        return;
+    }
+    const double l2b = log2(log_base);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double v = 0.0;
+            for (int q = 0; q < 3; ++q) v += h.Mi[3 * i + q] * (1.0 + sigma[q]) * h.M[3 * q + j];
+            k.A[3 * i + j] = (float)v;
+        }
+    for (int j = 0; j < 3; ++j) {
+        double v = 0.0;
+        for (int q = 0; q < 3; ++q) v += bias[q] * h.M[3 * q + j];
+        k.c[j] = (float)(-v * l2b);
+    }
+}
+// Table value of a uint8 channel for either variant.
+__device__ __forceinline__ float hed_table_value(int variant, int v) {
+    if (variant == 18) return (float)(log(fmax((double)v / 255.0, 1e-6)) / HED18_LN);
+    return (float)log2((double)v / 255.0 + 2.0);
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) { float d; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+// Two pixels on the packed f32x2 pipe: table values of the three channels -> six output bytes (low byte of each word).
+template <int V>
+__device__ __forceinline__ void hed_pair(const HedConsts& k, const float (&mi)[9], float2 lr, float2 lg, float2 lb, uint32_t (&bits)[6]) {
+    if (V == 18) {
+        // stains = max(0, L @ inv(M))
+        float2 s0 = __ffma2_rn(lb, dup(mi[6]), __ffma2_rn(lg, dup(mi[3]), __fmul2_rn(lr, dup(mi[0]))));
+        float2 s1 = __ffma2_rn(lb, dup(mi[7]), __ffma2_rn(lg, dup(mi[4]), __fmul2_rn(lr, dup(mi[1]))));
+        float2 s2 = __ffma2_rn(lb, dup(mi[8]), __ffma2_rn(lg, dup(mi[5]), __fmul2_rn(lr, dup(mi[2]))));
+        s0 = f2(fmaxf(s0.x, 0.f), fmaxf(s0.y, 0.f)); s1 = f2(fmaxf(s1.x, 0.f), fmaxf(s1.y, 0.f)); s2 = f2(fmaxf(s2.x, 0.f), fmaxf(s2.y, 0.f));
+        lr = s0; lg = s1; lb = s2;
+    }
+    const float2 e0 = __ffma2_rn(lb, dup(k.A[6]), __ffma2_rn(lg, dup(k.A[3]), __ffma2_rn(lr, dup(k.A[0]), dup(k.c[0]))));
+    const float2 e1 = __ffma2_rn(lb, dup(k.A[7]), __ffma2_rn(lg, dup(k.A[4]), __ffma2_rn(lr, dup(k.A[1]), dup(k.c[1]))));
+    const float2 e2 = __ffma2_rn(lb, dup(k.A[8]), __ffma2_rn(lg, dup(k.A[5]), __ffma2_rn(lr, dup(k.A[2]), dup(k.c[2]))));
+    const float off = V == 18 ? 0.f : -2.f;      // clip(2^e + off, 0, 1) * 255, truncated: one saturating FMA + one round-down FMA
+    bits[0] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e0.x), 1.f, off), 255.f, 8388608.f));
+    bits[1] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e1.x), 1.f, off), 255.f, 8388608.f));
+    bits[2] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e2.x), 1.f, off), 255.f, 8388608.f));
+    bits[3] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e0.y), 1.f, off), 255.f, 8388608.f));
+    bits[4] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e1.y), 1.f, off), 255.f, 8388608.f));
+    bits[5] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e2.y), 1.f, off), 255.f, 8388608.f));
+}
+// The 16 pixels of a group (12 packed words) through a lane-replicated table.
+template <int V, class TAB>
+__device__ __forceinline__ void hed_words(const HedConsts& k, const float (&mi)[9], const TAB tab, uint32_t lane_off, const uint32_t (&w)[12], uint32_t (&o)[12]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
+        // pixels: p0=(a0,a1,a2) p1=(a3,b0,b1) p2=(b2,b3,c0) p3=(c1,c2,c3)
+        uint32_t b01[6], b23[6];
+        hed_pair<V>(k, mi, f2(od_lookup(tab, wa, lane_off, 0), od_lookup(tab, wa, lane_off, 3)), f2(od_lookup(tab, wa, lane_off, 1), od_lookup(tab, wb, lane_off, 0)),
+                    f2(od_lookup(tab, wa, lane_off, 2), od_lookup(tab, wb, lane_off, 1)), b01);
+        hed_pair<V>(k, mi, f2(od_lookup(tab, wb, lane_off, 2), od_lookup(tab, wc, lane_off, 1)), f2(od_lookup(tab, wb, lane_off, 3), od_lookup(tab, wc, lane_off, 2)),
+                    f2(od_lookup(tab, wc, lane_off, 0), od_lookup(tab, wc, lane_off, 3)), b23);
+        o[3 * q] = pack4(b01[0], b01[1], b01[2], b01[3]);
+        o[3 * q + 1] = pack4(b01[4], b01[5], b23[0], b23[1]);
+        o[3 * q + 2] = pack4(b23[2], b23[3], b23[4], b23[5]);
+    }
+}
+__device__ __forceinline__ void hed_load_mi(float (&mi)[9]) {
+    const HedMats h = hed_mats();
+#pragma unroll
+    for (int i = 0; i < 9; ++i) mi[i] = (float)h.Mi[i];
+}
+
 struct HedArgs {
     const uint8_t* in;
     uint8_t* out;
@@ -259,53 +361,34 @@ struct HedArgs {
     const double* sigma;   // [B,3]
     const double* bias;    // [B,3]
     double cutoff_lo, cutoff_hi, log_base;
+    int variant;           // 17: scikit-image 0.16-0.17 (log_base, "+2" offset); 18: scikit-image >= 0.18 (see Hed18)
     int32_t* status;       // 1 = tile outside the cutoff (copied through)
     unsigned long long* sums;   // [B] workspace (zeroed): sum of all channel bytes
     unsigned* done;             // [B] workspace (zeroed): CTAs of the tile that have finished
 };
 
-__device__ __forceinline__ float fma_sat(float a, float b, float c) { float d; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
-
+template <int V>
 __global__ void __launch_bounds__(256, 3) hed_kernel(HedArgs a) {
-    // log2(v/255 + 2), replicated per lane with 256-byte rows like the OD table of K4: one PRMT builds the offset from
-    // the packed pixel word, the lookup is bank-conflict free
+    // table value of every uint8, replicated per lane with 256-byte rows like the OD table of K4: one PRMT builds the offset
+    // from the packed pixel word, the lookup is bank-conflict free
     extern __shared__ __align__(256) unsigned char l2_rep[];
     __shared__ float l2[256];
-    __shared__ float A[9], c[3];
+    __shared__ HedConsts kc;
     __shared__ int skip;
     __shared__ unsigned long long wsum[8];
     const int tile = blockIdx.x;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) l2[i] = (float)log2((double)i / 255.0 + 2.0);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) l2[i] = hed_table_value(V, i);
     __syncthreads();
     for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x)
         *reinterpret_cast<float*>(l2_rep + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = l2[i >> 5];
-    if (threadIdx.x == 0) {
-        // A = inv(M) diag(1+sigma) M, c = bias M  (M = rgb_from_hed), exponent scaled to base 2
-        const double M[9] = {0.65, 0.70, 0.29, 0.07, 0.99, 0.11, 0.27, 0.57, 0.78};
-        const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
-        double Mi[9];
-        Mi[0] = (M[4] * M[8] - M[5] * M[7]) / det; Mi[1] = (M[2] * M[7] - M[1] * M[8]) / det; Mi[2] = (M[1] * M[5] - M[2] * M[4]) / det;
-        Mi[3] = (M[5] * M[6] - M[3] * M[8]) / det; Mi[4] = (M[0] * M[8] - M[2] * M[6]) / det; Mi[5] = (M[2] * M[3] - M[0] * M[5]) / det;
-        Mi[6] = (M[3] * M[7] - M[4] * M[6]) / det; Mi[7] = (M[1] * M[6] - M[0] * M[7]) / det; Mi[8] = (M[0] * M[4] - M[1] * M[3]) / det;
-        const double l2b = log2(a.log_base);
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) {
-                double s = 0.0;
-                for (int k = 0; k < 3; ++k) s += Mi[3 * i + k] * (1.0 + a.sigma[(size_t)tile * 3 + k]) * M[3 * k + j];
-                A[3 * i + j] = (float)s;
-            }
-        for (int j = 0; j < 3; ++j) {
-            double s = 0.0;
-            for (int k = 0; k < 3; ++k) s += a.bias[(size_t)tile * 3 + k] * M[3 * k + j];
-            c[j] = (float)(s * l2b);
-        }
-    }
+    if (threadIdx.x == 0) hed_consts(V, a.sigma + (size_t)tile * 3, a.bias + (size_t)tile * 3, a.log_base, kc);
     __syncthreads();
     const uint8_t* tin = a.in + (size_t)tile * a.npx * 3;
     uint8_t* tout = a.out + (size_t)tile * a.npx * 3;
     const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
-    const float a00 = A[0], a01 = A[1], a02 = A[2], a10 = A[3], a11 = A[4], a12 = A[5], a20 = A[6], a21 = A[7], a22 = A[8];
-    const float c0 = -c[0], c1 = -c[1], c2 = -c[2];
+    const HedConsts k = kc;
+    float mi[9];
+    hed_load_mi(mi);
     const uint32_t lane_off = (threadIdx.x & 31) << 2;
     // The patch-mean gate (augmenter.py:288-293) needs the sum of ALL bytes of the tile -- a global dependency that would
     // cost a separate read pass.  Tiles outside the cutoff are rare, so every CTA transforms its share speculatively while
@@ -325,37 +408,8 @@ __global__ void __launch_bounds__(256, 3) hed_kernel(HedArgs a) {
             }
             acc += sg;
         }
-        {
-            // two pixels at a time on the packed f32x2 pipe; clip(b^e - 2, [0,1]) * 255 truncated (hed2rgb clip, then
-            // augmenter.py:320-325) = one saturating FMA and one round-down FMA onto 2^23 per value
-            auto px_pair = [&](float2 lr, float2 lg, float2 lb, uint32_t (&bits)[6]) {
-                const float2 e0 = __ffma2_rn(lb, dup(a20), __ffma2_rn(lg, dup(a10), __ffma2_rn(lr, dup(a00), dup(c0))));
-                const float2 e1 = __ffma2_rn(lb, dup(a21), __ffma2_rn(lg, dup(a11), __ffma2_rn(lr, dup(a01), dup(c1))));
-                const float2 e2 = __ffma2_rn(lb, dup(a22), __ffma2_rn(lg, dup(a12), __ffma2_rn(lr, dup(a02), dup(c2))));
-                bits[0] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e0.x), 1.f, -2.f), 255.f, 8388608.f));
-                bits[1] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e1.x), 1.f, -2.f), 255.f, 8388608.f));
-                bits[2] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e2.x), 1.f, -2.f), 255.f, 8388608.f));
-                bits[3] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e0.y), 1.f, -2.f), 255.f, 8388608.f));
-                bits[4] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e1.y), 1.f, -2.f), 255.f, 8388608.f));
-                bits[5] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e2.y), 1.f, -2.f), 255.f, 8388608.f));
-            };
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
-                // pixels: p0=(a0,a1,a2) p1=(a3,b0,b1) p2=(b2,b3,c0) p3=(c1,c2,c3)
-                uint32_t b01[6], b23[6];
-                px_pair(f2(od_lookup(l2_rep, wa, lane_off, 0), od_lookup(l2_rep, wa, lane_off, 3)),
-                        f2(od_lookup(l2_rep, wa, lane_off, 1), od_lookup(l2_rep, wb, lane_off, 0)),
-                        f2(od_lookup(l2_rep, wa, lane_off, 2), od_lookup(l2_rep, wb, lane_off, 1)), b01);
-                px_pair(f2(od_lookup(l2_rep, wb, lane_off, 2), od_lookup(l2_rep, wc, lane_off, 1)),
-                        f2(od_lookup(l2_rep, wb, lane_off, 3), od_lookup(l2_rep, wc, lane_off, 2)),
-                        f2(od_lookup(l2_rep, wc, lane_off, 0), od_lookup(l2_rep, wc, lane_off, 3)), b23);
-                o[3 * q] = pack4(b01[0], b01[1], b01[2], b01[3]);
-                o[3 * q + 1] = pack4(b01[4], b01[5], b23[0], b23[1]);
-                o[3 * q + 2] = pack4(b23[2], b23[3], b23[4], b23[5]);
-            }
-            store_group(tout, a.npx, g, a.aligned != 0, o);
-        }
+        hed_words<V>(k, mi, (const unsigned char*)l2_rep, lane_off, w, o);
+        store_group(tout, a.npx, g, a.aligned != 0, o);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -389,79 +443,40 @@ __global__ void __launch_bounds__(256, 3) hed_kernel(HedArgs a) {
 }
 
 // ---- HED on the TMA ring (sb_ring.cuh): the path for 16-byte aligned tiles; hed_kernel above serves the rest.
-struct HedConsts { float A[9]; float c[3]; };
 struct HedRingParams {
     const HedConsts* consts;       // [B]
     unsigned long long* sums;      // [B] zeroed: sum of all channel bytes of the tile (patch-mean gate)
 };
 
-// Per-tile A = inv(M) diag(1+sigma) M and c = bias M scaled to base 2 (M = rgb_from_hed), as in hed_kernel.
-__global__ void hed_prepare_kernel(int B, const double* __restrict__ sigma, const double* __restrict__ bias, double log_base, HedConsts* out) {
+// Per-tile constants (hed_consts) for the ring operator.
+__global__ void hed_prepare_kernel(int B, const double* __restrict__ sigma, const double* __restrict__ bias, double log_base, int variant, HedConsts* out) {
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= B) return;
-    const double M[9] = {0.65, 0.70, 0.29, 0.07, 0.99, 0.11, 0.27, 0.57, 0.78};
-    const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
-    double Mi[9];
-    Mi[0] = (M[4] * M[8] - M[5] * M[7]) / det; Mi[1] = (M[2] * M[7] - M[1] * M[8]) / det; Mi[2] = (M[1] * M[5] - M[2] * M[4]) / det;
-    Mi[3] = (M[5] * M[6] - M[3] * M[8]) / det; Mi[4] = (M[0] * M[8] - M[2] * M[6]) / det; Mi[5] = (M[2] * M[3] - M[0] * M[5]) / det;
-    Mi[6] = (M[3] * M[7] - M[4] * M[6]) / det; Mi[7] = (M[1] * M[6] - M[0] * M[7]) / det; Mi[8] = (M[0] * M[4] - M[1] * M[3]) / det;
-    const double l2b = log2(log_base);
     HedConsts k;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            double v = 0.0;
-            for (int q = 0; q < 3; ++q) v += Mi[3 * i + q] * (1.0 + sigma[(size_t)tile * 3 + q]) * M[3 * q + j];
-            k.A[3 * i + j] = (float)v;
-        }
-    for (int j = 0; j < 3; ++j) {
-        double v = 0.0;
-        for (int q = 0; q < 3; ++q) v += bias[(size_t)tile * 3 + q] * M[3 * q + j];
-        k.c[j] = (float)(-v * l2b);
-    }
+    hed_consts(variant, sigma + (size_t)tile * 3, bias + (size_t)tile * 3, log_base, k);
     out[tile] = k;
 }
 
-struct HedOp {
+template <int V>
+struct HedOpT {
     using Consts = HedConsts;
     using Params = HedRingParams;
     using Acc = unsigned;
     static constexpr int kLaneShift = 2;
     __device__ static void fill_table(unsigned char* tab, const Params&, int tid, int n) {
         for (int i = tid; i < 256 * 32; i += n)
-            *reinterpret_cast<float*>(tab + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = (float)log2((double)(i >> 5) / 255.0 + 2.0);
+            *reinterpret_cast<float*>(tab + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = hed_table_value(V, i >> 5);
     }
     __device__ static void acc_init(Acc& a) { a = 0u; }
-    __device__ static void pair(const Consts& k, float2 lr, float2 lg, float2 lb, uint32_t (&bits)[6]) {
-        const float2 e0 = __ffma2_rn(lb, dup(k.A[6]), __ffma2_rn(lg, dup(k.A[3]), __ffma2_rn(lr, dup(k.A[0]), dup(k.c[0]))));
-        const float2 e1 = __ffma2_rn(lb, dup(k.A[7]), __ffma2_rn(lg, dup(k.A[4]), __ffma2_rn(lr, dup(k.A[1]), dup(k.c[1]))));
-        const float2 e2 = __ffma2_rn(lb, dup(k.A[8]), __ffma2_rn(lg, dup(k.A[5]), __ffma2_rn(lr, dup(k.A[2]), dup(k.c[2]))));
-        bits[0] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e0.x), 1.f, -2.f), 255.f, 8388608.f));
-        bits[1] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e1.x), 1.f, -2.f), 255.f, 8388608.f));
-        bits[2] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e2.x), 1.f, -2.f), 255.f, 8388608.f));
-        bits[3] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e0.y), 1.f, -2.f), 255.f, 8388608.f));
-        bits[4] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e1.y), 1.f, -2.f), 255.f, 8388608.f));
-        bits[5] = __float_as_uint(__fmaf_rd(fma_sat(ex2_approx(e2.y), 1.f, -2.f), 255.f, 8388608.f));
-    }
-    struct Run {};
-    __device__ static Run begin_run(const Consts&, const Params&) { return Run{}; }
-    __device__ static void process(const Consts& k, const Params&, const Run&, const OdAbs tab, uint4* grp, Acc& acc) {
+    struct Run { float mi[9]; };
+    __device__ static Run begin_run(const Consts&, const Params&) { Run r; hed_load_mi(r.mi); return r; }
+    __device__ static void process(const Consts& k, const Params&, const Run& run, const OdAbs tab, uint4* grp, Acc& acc) {
         const uint4 va = grp[0], vb = grp[1], vc = grp[2];
         const uint32_t w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
         uint32_t o[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) acc += __vsadu4(w[i], 0u);           // the speculative transform also sums the input bytes
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
-            uint32_t b01[6], b23[6];
-            pair(k, f2(od_lookup(tab, wa, 0u, 0), od_lookup(tab, wa, 0u, 3)), f2(od_lookup(tab, wa, 0u, 1), od_lookup(tab, wb, 0u, 0)),
-                 f2(od_lookup(tab, wa, 0u, 2), od_lookup(tab, wb, 0u, 1)), b01);
-            pair(k, f2(od_lookup(tab, wb, 0u, 2), od_lookup(tab, wc, 0u, 1)), f2(od_lookup(tab, wb, 0u, 3), od_lookup(tab, wc, 0u, 2)),
-                 f2(od_lookup(tab, wc, 0u, 0), od_lookup(tab, wc, 0u, 3)), b23);
-            o[3 * q] = pack4(b01[0], b01[1], b01[2], b01[3]);
-            o[3 * q + 1] = pack4(b01[4], b01[5], b23[0], b23[1]);
-            o[3 * q + 2] = pack4(b23[2], b23[3], b23[4], b23[5]);
-        }
+        hed_words<V>(k, run.mi, tab, 0u, w, o);
         grp[0] = make_uint4(o[0], o[1], o[2], o[3]);
         grp[1] = make_uint4(o[4], o[5], o[6], o[7]);
         grp[2] = make_uint4(o[8], o[9], o[10], o[11]);
@@ -474,6 +489,59 @@ struct HedOp {
         acc = 0u;
     }
 };
+using HedOp = HedOpT<17>;
+using Hed18Op = HedOpT<18>;
+
+// ---- float patches (augmenter.py:288-291, 323-327): the reference takes float images in [0,1] as they are and returns
+// floats.  Not a hot path: one pass for the patch mean (fixed-point sum: deterministic), one pass for the transform with
+// accurate log2f / exp2f (the uint8 path's lookup table does not apply).
+__global__ void __launch_bounds__(256) hed_float_sum_kernel(const float* __restrict__ in, size_t n_per_tile, long long* __restrict__ sums) {
+    const int tile = blockIdx.x;
+    const float* t = in + (size_t)tile * n_per_tile;
+    long long acc = 0;
+    for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < n_per_tile; i += (size_t)gridDim.y * blockDim.x)
+        acc += __double2ll_rn((double)t[i] * 1099511627776.0);      // 2^40
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(reinterpret_cast<unsigned long long*>(&sums[tile]), (unsigned long long)acc);
+}
+template <int V>
+__global__ void __launch_bounds__(256) hed_float_kernel(const float* __restrict__ in, float* __restrict__ out, int npx, const double* __restrict__ sigma,
+                                                         const double* __restrict__ bias, double lo, double hi, double log_base,
+                                                         const long long* __restrict__ sums, int32_t* status) {
+    const int tile = blockIdx.x;
+    __shared__ HedConsts kc;
+    if (threadIdx.x == 0) hed_consts(V, sigma + (size_t)tile * 3, bias + (size_t)tile * 3, log_base, kc);
+    __syncthreads();
+    const double mean = (double)sums[tile] / 1099511627776.0 / (3.0 * (double)npx);
+    const bool skip = !(lo <= mean && mean <= hi);
+    if (threadIdx.x == 0 && blockIdx.y == 0 && status) status[tile] = skip ? 1 : 0;
+    const float* tin = in + (size_t)tile * npx * 3;
+    float* tout = out + (size_t)tile * npx * 3;
+    const HedConsts k = kc;
+    float mi[9];
+    hed_load_mi(mi);
+    for (int p = blockIdx.y * blockDim.x + threadIdx.x; p < npx; p += gridDim.y * blockDim.x) {
+        const float r = tin[3 * p], g = tin[3 * p + 1], b = tin[3 * p + 2];
+        if (skip) { tout[3 * p] = r; tout[3 * p + 1] = g; tout[3 * p + 2] = b; continue; }
+        float x0, x1, x2;
+        if (V == 18) {
+            const float inv = (float)(1.0 / (HED18_LN * HED_LOG2E));        // ln(x)/ln(1e-6) = log2(x) / (ln(1e-6) log2 e)
+            const float l0 = log2f(fmaxf(r, 1e-6f)) * inv, l1 = log2f(fmaxf(g, 1e-6f)) * inv, l2 = log2f(fmaxf(b, 1e-6f)) * inv;
+            x0 = fmaxf(fmaf(l2, mi[6], fmaf(l1, mi[3], l0 * mi[0])), 0.f);
+            x1 = fmaxf(fmaf(l2, mi[7], fmaf(l1, mi[4], l0 * mi[1])), 0.f);
+            x2 = fmaxf(fmaf(l2, mi[8], fmaf(l1, mi[5], l0 * mi[2])), 0.f);
+        } else {
+            x0 = log2f(r + 2.f); x1 = log2f(g + 2.f); x2 = log2f(b + 2.f);
+        }
+        const float off = V == 18 ? 0.f : -2.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float e = fmaf(x2, k.A[6 + j], fmaf(x1, k.A[3 + j], fmaf(x0, k.A[j], k.c[j])));
+            tout[3 * p + j] = fminf(fmaxf(exp2f(e) + off, 0.f), 1.f);
+        }
+    }
+}
 
 // Runs behind the ring kernel: evaluates the patch-mean gate of every tile (augmenter.py:288-293) and copies the input
 // back over the (rare) tiles that are to be left unchanged.  One CTA per tile; 16-byte aligned tiles.
@@ -580,11 +648,8 @@ int lab_lmax(double thr) {
 int launch_lab(sb_handle* hh, sb::LabArgs& a, cudaStream_t st) {
     sb_handle* h = hh;
     a.tab = h->tab;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(sb::lab_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sb::LabShared)) != cudaSuccess) return SB_ERR_CUDA;
-        attr = true;
-    }
+    static sb::DeviceOnce once;
+    if (sb::ensure_dyn_smem(once, sb::lab_tile_kernel, (int)sizeof(sb::LabShared)) != cudaSuccess) return SB_ERR_CUDA;
     int grid = h->num_sms * 2;
     if (grid > a.B) grid = a.B;
     sb::lab_tile_kernel<<<grid, sb::NT, sizeof(sb::LabShared), st>>>(a);
@@ -612,6 +677,9 @@ extern "C" {
 
 int sb_reinhard_stats(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double* means, double* stds, void* stream) {
     if (bad_img(h, rgb, B, H, W) || !means || !stds) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_reinhard_stats");
     sb::LabArgs a{};
     a.in = rgb; a.B = B; a.npx = H * W; a.aligned = aligned16(rgb, rgb, a.npx); a.mode = sb::REINHARD_STATS;
     a.means_out = means; a.stds_out = stds;
@@ -621,6 +689,9 @@ int sb_reinhard_stats(sb_handle* h, const uint8_t* rgb, int B, int H, int W, dou
 int sb_reinhard_transform(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const double* target_means,
                           const double* target_stds, int mask_background, double luminosity_threshold, int32_t* status, void* stream) {
     if (bad_img(h, rgb_in, B, H, W) || !rgb_out || !target_means || !target_stds) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_reinhard_transform");
     sb::LabArgs a{};
     a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = aligned16(rgb_in, rgb_out, a.npx); a.mode = sb::REINHARD_TRANSFORM;
     a.tmeans = target_means; a.tstds = target_stds; a.mask_background = mask_background; a.lmax = lab_lmax(luminosity_threshold);
@@ -630,6 +701,9 @@ int sb_reinhard_transform(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out,
 
 int sb_luminosity_standardize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, double percentile, void* stream) {
     if (bad_img(h, rgb_in, B, H, W) || !rgb_out) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_luminosity_standardize");
     sb::LabArgs a{};
     a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = aligned16(rgb_in, rgb_out, a.npx); a.mode = sb::LUM_STANDARDIZE;
     a.percentile = percentile;
@@ -637,50 +711,86 @@ int sb_luminosity_standardize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_
 }
 
 int sb_hed_augment(sb_handle* hh, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, const double* sigma, const double* bias,
-                   double cutoff_lo, double cutoff_hi, double log_base, int32_t* status, void* stream) {
+                   double cutoff_lo, double cutoff_hi, double log_base, int skimage_variant, int32_t* status, void* stream) {
     if (bad_img(hh, rgb_in, B, H, W) || !rgb_out || !sigma || !bias) return SB_ERR_ARG;
+    if (skimage_variant != 17 && skimage_variant != 18) return SB_ERR_ARG;
+    if (skimage_variant == 17 && !(log_base > 1.0)) return SB_ERR_ARG;
     sb_handle* h = hh;
     cudaStream_t st = (cudaStream_t)stream;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_hed_augment");
+    sb::Scratch scratch(h, st);
     const int npx = H * W, al = aligned16(rgb_in, rgb_out, npx);
     if (al) {
         // TMA ring: per-tile constants -> ring kernel (speculative transform + byte sums) -> gate kernel
         unsigned char* ws = nullptr;
         const size_t c_bytes = ((size_t)B * sizeof(sb::HedConsts) + 15) & ~(size_t)15;
-        if (cudaMallocAsync(&ws, c_bytes + (size_t)B * 8, st) != cudaSuccess) return SB_ERR_CUDA;
+        if (scratch.get(&ws, c_bytes + (size_t)B * 8) != cudaSuccess) return SB_ERR_CUDA;
         sb::HedConsts* consts = reinterpret_cast<sb::HedConsts*>(ws);
         unsigned long long* sums = reinterpret_cast<unsigned long long*>(ws + c_bytes);
         cudaMemsetAsync(sums, 0, (size_t)B * 8, st);
-        sb::hed_prepare_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, sigma, bias, log_base, consts);
+        sb::hed_prepare_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, sigma, bias, log_base, skimage_variant, consts);
         sb::RingGeom g{rgb_in, rgb_out, B, npx};
         sb::HedRingParams p{consts, sums};
-        int rc = sb::launch_ring<sb::HedOp>(g, p, h->num_sms, st);
+        int rc = skimage_variant == 18 ? sb::launch_ring<sb::Hed18Op>(g, p, h->num_sms, st) : sb::launch_ring<sb::HedOp>(g, p, h->num_sms, st);
         if (rc == 0) {
             sb::hed_gate_kernel<<<B, 256, 0, st>>>(rgb_in, rgb_out, npx, sums, cutoff_lo, cutoff_hi, status);
             rc = (int)cudaGetLastError();
         }
-        cudaFreeAsync(ws, st);
         if (rc != 0) return SB_ERR_CUDA;
         h->launches += 3;
         return SB_OK;
     }
     unsigned long long* sums = nullptr;                 // [B] byte sums followed by [B] finished-CTA counters
-    if (cudaMallocAsync(&sums, (size_t)B * 12, st) != cudaSuccess) return SB_ERR_CUDA;
+    if (scratch.get(&sums, (size_t)B * 12) != cudaSuccess) return SB_ERR_CUDA;
     if (cudaMemsetAsync(sums, 0, (size_t)B * 12, st) != cudaSuccess) return SB_ERR_CUDA;
     const dim3 grid = tile_grid(B, npx, h->num_sms);
     sb::HedArgs a{};
     a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = npx; a.aligned = al; a.sigma = sigma; a.bias = bias;
-    a.cutoff_lo = cutoff_lo; a.cutoff_hi = cutoff_hi; a.log_base = log_base; a.status = status; a.sums = sums;
+    a.cutoff_lo = cutoff_lo; a.cutoff_hi = cutoff_hi; a.log_base = log_base; a.variant = skimage_variant; a.status = status; a.sums = sums;
     a.done = reinterpret_cast<unsigned*>(sums + B);
-    static bool hed_attr = false;
-    if (!hed_attr) {
-        if (cudaFuncSetAttribute(sb::hed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sb::OD_REP_BYTES) != cudaSuccess) return SB_ERR_CUDA;
-        hed_attr = true;
+    static sb::DeviceOnce once17, once18;
+    if (skimage_variant == 18) {
+        if (sb::ensure_dyn_smem(once18, sb::hed_kernel<18>, sb::OD_REP_BYTES) != cudaSuccess) return SB_ERR_CUDA;
+        sb::hed_kernel<18><<<grid, 256, sb::OD_REP_BYTES, st>>>(a);
+    } else {
+        if (sb::ensure_dyn_smem(once17, sb::hed_kernel<17>, sb::OD_REP_BYTES) != cudaSuccess) return SB_ERR_CUDA;
+        sb::hed_kernel<17><<<grid, 256, sb::OD_REP_BYTES, st>>>(a);
     }
-    sb::hed_kernel<<<grid, 256, sb::OD_REP_BYTES, st>>>(a);
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(sums, st);
     if (e != cudaSuccess) return SB_ERR_CUDA;
     h->launches += 1;
+    return SB_OK;
+}
+
+int sb_hed_augment_f32(sb_handle* hh, const float* rgb_in, float* rgb_out, int B, int H, int W, const double* sigma, const double* bias,
+                       double cutoff_lo, double cutoff_hi, double log_base, int skimage_variant, int32_t* status, void* stream) {
+    if (bad_img(hh, rgb_in, B, H, W) || !rgb_out || !sigma || !bias) return SB_ERR_ARG;
+    if (skimage_variant != 17 && skimage_variant != 18) return SB_ERR_ARG;
+    if (skimage_variant == 17 && !(log_base > 1.0)) return SB_ERR_ARG;
+    sb_handle* h = hh;
+    cudaStream_t st = (cudaStream_t)stream;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_hed_augment_f32");
+    sb::Scratch scratch(h, st);
+    long long* sums = nullptr;
+    if (scratch.get(&sums, (size_t)B * 8) != cudaSuccess) return SB_ERR_CUDA;
+    if (cudaMemsetAsync(sums, 0, (size_t)B * 8, st) != cudaSuccess) return SB_ERR_CUDA;
+    const int npx = H * W;
+    int spans = (npx + 256 * 16 - 1) / (256 * 16);
+    const int want = (h->num_sms * 8 + B - 1) / B;
+    if (spans > want) spans = want;
+    if (spans < 1) spans = 1;
+    const dim3 grid(B, spans);
+    sb::hed_float_sum_kernel<<<grid, 256, 0, st>>>(rgb_in, (size_t)npx * 3, sums);
+    if (skimage_variant == 18)
+        sb::hed_float_kernel<18><<<grid, 256, 0, st>>>(rgb_in, rgb_out, npx, sigma, bias, cutoff_lo, cutoff_hi, log_base, sums, status);
+    else
+        sb::hed_float_kernel<17><<<grid, 256, 0, st>>>(rgb_in, rgb_out, npx, sigma, bias, cutoff_lo, cutoff_hi, log_base, sums, status);
+    if (cudaGetLastError() != cudaSuccess) return SB_ERR_CUDA;
+    h->launches += 2;
     return SB_OK;
 }
 
@@ -688,6 +798,9 @@ int sb_grayscale_augment(sb_handle* hh, const uint8_t* rgb_in, uint8_t* rgb_out,
                          const double* beta, void* stream) {
     if (bad_img(hh, rgb_in, B, H, W) || !rgb_out || !alpha || !beta) return SB_ERR_ARG;
     sb_handle* h = hh;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_grayscale_augment");
     sb::GrayArgs a{};
     a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = aligned16(rgb_in, rgb_out, a.npx); a.alpha = alpha; a.beta = beta;
     if (a.aligned) {

@@ -30,7 +30,9 @@ extern "C" {
 int sb_decode_jpeg(sb_handle* h, const uint8_t* const* jpeg, const size_t* nbytes, int B, int H, int W, uint8_t* rgb_out,
                    void* stream) {
     if (!h || !jpeg || !nbytes || !rgb_out || B <= 0 || H <= 0 || W <= 0 || h->device < 0 || h->device >= 64) return SB_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) return SB_ERR_CUDA;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_decode_jpeg (nvJPEG)");
     std::lock_guard<std::mutex> lock(g_mu);
     JpegState& js = g_jpeg[h->device];
     if (!js.handle) {

@@ -1,5 +1,7 @@
 // sb_kernels.h -- internal interface between the C-ABI layer (sb_api.cu) and the kernel translation units.
 #pragma once
+#include <atomic>
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges are no-ops unless a profiler is attached
 #include "sb_device.cuh"
 #include "../../include/stainb200.h"
 
@@ -20,7 +22,81 @@ struct sb_handle {
     double* d_target = nullptr;   // [6 + 2]
     int32_t* d_status = nullptr;
     size_t status_cap = 0;
+    // caller-lent per-call scratch (sb_set_workspace); null = the device's stream-ordered pool
+    unsigned char* user_ws = nullptr;
+    size_t user_ws_bytes = 0, user_ws_off = 0;
+    int scratch_depth = 0;
 };
+
+// ---- host-side helpers shared by the translation units that hold entry points / launchers
+namespace sb {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: one bit per device ordinal per kernel.
+struct DeviceOnce { std::atomic<unsigned long long> bits{0ull}; };
+template <class Kern>
+inline cudaError_t ensure_dyn_smem(DeviceOnce& once, Kern kernel, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (dev < 64 && (once.bits.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev < 64) once.bits.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(const sb_handle* h) {
+        if (!h) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; ok = false; return; }
+        if (prev != h->device) ok = cudaSetDevice(h->device) == cudaSuccess; else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// NVTX range around the launches of one entry point (tracing).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+// Per-call device scratch (per-tile constants, statistics, mask bits).  Served from the workspace the caller lent with
+// sb_set_workspace when it fits (bump allocation, reset when the outermost call returns: calls through one handle are
+// stream-ordered on one stream at a time, so the next call may reuse the bytes), else from the device's stream-ordered
+// memory pool (cudaMallocAsync / cudaFreeAsync on the call's stream -- no synchronisation either way).
+struct Scratch {
+    sb_handle* h;
+    cudaStream_t st;
+    void* pooled[6];
+    int n = 0;
+    Scratch(sb_handle* hh, cudaStream_t s) : h(hh), st(s) { h->scratch_depth += 1; }
+    cudaError_t get(void** p, size_t bytes) {
+        const size_t need = (bytes + 255) & ~(size_t)255;
+        if (h->user_ws && h->user_ws_off + need <= h->user_ws_bytes) {
+            *p = h->user_ws + h->user_ws_off;
+            h->user_ws_off += need;
+            return cudaSuccess;
+        }
+        if (n >= 6) return cudaErrorMemoryAllocation;
+        cudaError_t e = cudaMallocAsync(p, need, st);
+        if (e == cudaSuccess) pooled[n++] = *p;
+        return e;
+    }
+    template <class T> cudaError_t get(T** p, size_t bytes) { void* v = nullptr; cudaError_t e = get(&v, bytes); *p = static_cast<T*>(v); return e; }
+    ~Scratch() {
+        for (int i = 0; i < n; ++i) cudaFreeAsync(pooled[i], st);
+        if (--h->scratch_depth == 0) h->user_ws_off = 0;
+    }
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+};
+
+}  // namespace sb
 
 namespace sb {
 
@@ -83,10 +159,12 @@ struct PointArgs {
     int32_t* status;
 };
 int launch_mask(const PointArgs& a, int num_sms, cudaStream_t stream);
-int launch_recombine(const PointArgs& a, int num_sms, cudaStream_t stream, bool use_tma);
-int launch_recombine_normalize(const PointArgs& a, int num_sms, cudaStream_t stream, bool use_tma, const double* M_src,
+int launch_recombine(const PointArgs& a, Scratch& scratch, bool use_tma);
+int launch_recombine_normalize(const PointArgs& a, Scratch& scratch, bool use_tma, const double* M_src,
                                const double* maxC_src, const double* Mt, const double* maxCt, int32_t* status);
-int launch_stain_augment(const PointArgs& a, int num_sms, cudaStream_t stream);
+int launch_stain_augment(const PointArgs& a, Scratch& scratch);
 int launch_concentrations(const PointArgs& a, int num_sms, cudaStream_t stream);
+int launch_rgb_to_od(const uint8_t* in, void* out, size_t n, int f32, const double* od64, int num_sms, cudaStream_t stream);
+int launch_od_to_rgb(const void* od, uint8_t* out, size_t n, int f32, int* negative, int num_sms, cudaStream_t stream);
 
 }  // namespace sb

@@ -39,8 +39,9 @@ constexpr unsigned WQ_CAP = 160;   // entries per warp queue: drained to < 32 on
 
 struct __align__(16) PipeShared {
     unsigned hist[2 * L1_BINS];      // 32 KB: 2 x 4096 (level 1) or 4 x 2048 (level 2)
-    double red[NWARP][10];
-    double part[2][12];              // this CTA's partial sums (double-buffered; read by cluster peers)
+    long long red[NWARP][10];       // fixed-point partial sums (integers: associative, so any grouping gives the same bits)
+    long long part[2][12];           // this CTA's partial sums (double-buffered; read by cluster peers)
+    unsigned long long acc64[10];    // Vahadane: per-pass fixed-point accumulators, fed by one atomic per warp and unit
     double tot[12];
     unsigned wtot[NWARP];
     unsigned q_rank[4], q_bin[4], q_rem[4], q_key[4], q_hist[4], q_tmp[4];
@@ -70,12 +71,26 @@ __device__ __forceinline__ void tile_sync(int S) {
     if (S > 1) cg::this_cluster().sync(); else __syncthreads();
 }
 
-// Sums 9 doubles + a count over the block (fixed order) into sh->part[buf].
-__device__ __forceinline__ void block_reduce10(PipeShared* sh, int buf, double (&acc)[9], unsigned cnt) {
+// Per-tile sums are accumulated in FIXED POINT (int64): integer addition is associative, so the totals do not depend on
+// how the pixels are grouped into threads, warps, CTAs of a cluster, launches or ranks -- a tile gives the same bits
+// whatever cluster size the launcher picked (sharded == unsharded).  The fp32 value that enters a sum is
+// itself defined independently of the cluster size: the 16-pixel group sums of pass A, the warp x unit sums of the
+// Vahadane passes (see for_each_unit).
+constexpr float FIX_MOMENT = 4294967296.f;        // 2^32: group sums <= 16 * ln(255)^2 < 2^9, tiles <= 2^20 groups -> < 2^61
+constexpr float FIX_DL = 1073741824.f;            // 2^30: per-pixel terms <= ~2^7, tiles <= 2^24 pixels -> < 2^61
+__device__ __forceinline__ long long to_fix(float v, float scale) { return __float2ll_rn(v * scale); }
+__device__ __forceinline__ long long warp_sum_ll(long long x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// Sums 9 fixed-point values + a count over the block into sh->part[buf].
+__device__ __forceinline__ void block_reduce10(PipeShared* sh, int buf, long long (&acc)[9], unsigned cnt) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) acc[i] = warp_sum(acc[i]);
-    double c = warp_sum((double)cnt);
+    for (int i = 0; i < 9; ++i) acc[i] = warp_sum_ll(acc[i]);
+    const long long c = warp_sum_ll((long long)cnt);
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) sh->red[warp][i] = acc[i];
@@ -83,23 +98,24 @@ __device__ __forceinline__ void block_reduce10(PipeShared* sh, int buf, double (
     }
     __syncthreads();
     if (threadIdx.x < 10) {
-        double s = 0.0;
+        long long s = 0;
         for (int w = 0; w < NWARP; ++w) s += sh->red[w][threadIdx.x];
         sh->part[buf][threadIdx.x] = s;
     }
 }
 
-// After tile_sync: every CTA sums the partials of all cluster ranks in rank order -> sh->tot (identical everywhere).
-__device__ __forceinline__ void cluster_total10(PipeShared* sh, int buf, int S) {
+// After tile_sync: every CTA sums the partials of all cluster ranks -> sh->tot (identical everywhere); entries 0..8 are
+// scaled back by inv_scale, entry 9 is a plain count.
+__device__ __forceinline__ void cluster_total10(PipeShared* sh, int buf, int S, double inv_scale) {
     if (threadIdx.x < 10) {
-        double s = 0.0;
+        long long s = 0;
         if (S > 1) {
             cg::cluster_group cluster = cg::this_cluster();
             for (int r = 0; r < S; ++r) s += cluster.map_shared_rank(&sh->part[buf][0], r)[threadIdx.x];
         } else {
             s = sh->part[buf][threadIdx.x];
         }
-        sh->tot[threadIdx.x] = s;
+        sh->tot[threadIdx.x] = threadIdx.x < 9 ? (double)s * inv_scale : (double)s;
     }
     __syncthreads();
 }
@@ -511,6 +527,61 @@ __device__ __forceinline__ void for_each_sample_group(const uint8_t* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------- cluster-size independent sums
+// The Vahadane passes keep fp32 partial sums in registers (fp64 / int64 accumulators do not fit the register budget).  To
+// make them independent of the cluster size, the tile's groups are cut into U units of K*NT consecutive groups (K depends
+// on the tile size only); a cluster of S CTAs splits the tile at unit boundaries; inside a unit thread t always visits
+// the groups (u*K + i)*NT + t, i < K.  The fp32 sum of a (warp, unit) pair is therefore the same number for every S; it is
+// reduced over the warp by a fixed shuffle tree and enters the fixed-point accumulator with one atomic per warp.
+__device__ __forceinline__ int unit_groups(int G) {
+    const int k = G / (8 * NT);
+    return k < 1 ? 1 : (k > 16 ? 16 : k);
+}
+template <class F, class FL>
+__device__ __forceinline__ void for_each_unit(const uint8_t* __restrict__ tile, int npx, int K, int ub, int ue, int U, bool aligned, F&& f, FL&& flush) {
+    const int nfull = npx / GROUP_PX;
+    for (int u = ub; u < ue; ++u) {
+        for (int i = 0; i < K; ++i) {
+            const int g = (u * K + i) * NT + (int)threadIdx.x;
+            if (g < nfull) {
+                uint32_t w[12];
+                int nvalid;
+                load_group<true>(tile, npx, g, aligned, w, nvalid);
+                f(NoTail{}, w, GROUP_PX, g);
+            }
+        }
+        if (u == U - 1 && (npx % GROUP_PX) != 0 && threadIdx.x == 0) {      // the ragged last group rides with the last unit
+            uint32_t w[12];
+            int nvalid;
+            load_group<true>(tile, npx, nfull, false, w, nvalid);
+            f(IsTail{}, w, nvalid, nfull);
+        }
+        flush();
+    }
+}
+// The sample groups of [gb, ge) with one flush per warp step (gb is a multiple of 32 sample blocks, so a warp step always
+// covers the same 32 blocks whatever the cluster size).
+template <class F, class FL>
+__device__ __forceinline__ void for_each_sample_group_flush(const uint8_t* __restrict__ tile, int npx, int gb, int ge, bool aligned, F&& f, FL&& flush) {
+    const int nfull = npx / GROUP_PX;
+    const int jb = gb / SAMPLE_STRIDE;
+    int je = (ge + SAMPLE_STRIDE - 1) / SAMPLE_STRIDE;
+    if (je > nfull / SAMPLE_STRIDE) je = nfull / SAMPLE_STRIDE;
+    for (int j0 = jb + (int)(threadIdx.x & ~31u); j0 < je; j0 += NT) {
+        const int j = j0 + (int)(threadIdx.x & 31u);
+        if (j < je) {
+            const int g = sample_group_of_block(j);
+            if (g >= gb && g < ge) {
+                uint32_t w[12];
+                int nvalid;
+                load_group<true>(tile, npx, g, aligned, w, nvalid);
+                f(NoTail{}, w, GROUP_PX, g);
+            }
+        }
+        flush();
+    }
+}
+
 template <int METHOD>
 __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -521,7 +592,10 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
     const int cluster_id = blockIdx.x / S, n_clusters = gridDim.x / S;
     const int npx = a.npx;
     const int G = (npx + GROUP_PX - 1) / GROUP_PX;
-    const int gb = (int)(((long long)G * crank) / S), ge = (int)(((long long)G * (crank + 1)) / S);
+    // a cluster splits the tile at unit boundaries (see for_each_unit)
+    const int UK = unit_groups(G), U = (G + UK * NT - 1) / (UK * NT);
+    const int ub = (U * crank) / S, ue = (U * (crank + 1)) / S;
+    const int gb = min(ub * UK * NT, G), ge = min(ue * UK * NT, G);
     const size_t tile_bytes = (size_t)npx * 3;
     const bool aligned = a.aligned != 0;
     const uint32_t lane_off = (threadIdx.x & 31) << 3;      // {od, gamma} pairs: 8 bytes per lane
@@ -532,6 +606,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
     const bool cache_mask = cache_smem || a.mask_scratch != nullptr;
 
     fill_odg_rep(od_rep, a.tab.od, a.tab.gamma, NT);
+    if (threadIdx.x < 10) sh->acc64[threadIdx.x] = 0ull;
     __syncthreads();
     int pbuf = 0;   // parity of sh->part
 
@@ -542,9 +617,9 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
 
         if (METHOD == SB_METHOD_MACENKO) {
             // ------------------------------------------------------------------ A: mask + moments
-            double acc[9];
+            long long acc[9];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+            for (int i = 0; i < 9; ++i) acc[i] = 0;
             unsigned cnt = 0;
             for_each_group<true>(tin, npx, gb, ge, aligned, [&](auto tail, const uint32_t (&w)[12], int nvalid, int) {
                 constexpr bool TAIL = decltype(tail)::value;
@@ -556,12 +631,13 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     if (TAIL && i >= nvalid) y = yc.bound;
                     accum_if_tissue(y, yc.bound, r.x, g.x, b.x, f, cnt);
                 });
+                // the fp32 sums of ONE 16-pixel group enter the fixed-point accumulators: independent of the thread layout
 #pragma unroll
-                for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
+                for (int i = 0; i < 9; ++i) acc[i] += to_fix(f[i], FIX_MOMENT);
             });
             block_reduce10(sh, pbuf, acc, cnt);
             tile_sync(S);
-            cluster_total10(sh, pbuf, S);
+            cluster_total10(sh, pbuf, S, 1.0 / (double)FIX_MOMENT);
             pbuf ^= 1;
             n_tissue = (unsigned)sh->tot[9];
             if (threadIdx.x == 0) {
@@ -818,13 +894,13 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     if (is_sample_group(g, nfull)) cnt_sample += __popc(mbits);
                     if (cache_mask) *(cache_smem ? mask_slot(sh->hist, g - gb) : a.mask_scratch + (size_t)tile * G + g) = (unsigned short)mbits;
                 });
-                double acc[9];
+                long long acc[9];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) acc[i] = 0.0;
-                acc[0] = (double)cnt_sample;
+                for (int i = 0; i < 9; ++i) acc[i] = 0;
+                acc[0] = (long long)cnt_sample;
                 block_reduce10(sh, pbuf, acc, cnt_tissue);
                 tile_sync(S);
-                cluster_total10(sh, pbuf, S);
+                cluster_total10(sh, pbuf, S, 1.0);
                 pbuf ^= 1;
             }
             n_tissue = (unsigned)sh->tot[9];
@@ -841,18 +917,26 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                 if (threadIdx.x == 0) { if (phase == 0 || !use_sample) aa_reset(sh->aa); else aa_carry(sh->aa); sh->dl_stop = 0; }
                 for (int it = 0; it < n_it; ++it) {
                     const LassoK lk = sh->lk;
-                    double acc[9];
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) acc[i] = 0.0;
                     // Sparse-code the tissue pixels of a group and add their a a^T / x a^T terms.  Atoms on the unit sphere (the
                     // usual case: the norm constraint is active) take the compare-free LASSO two pixels at a time on the packed
                     // f32x2 pipe with packed accumulators; atoms inside the ball take the general KKT form.
-                    // Partial sums stay in fp32 for the thread's whole share of the pass (<= a few thousand non-negative terms,
-                    // relative error ~1e-6, far below the 1e-5 the dictionary is converged to) and enter the fixed-order fp64
-                    // block reduction once per pass: the fp64 accumulators would not fit the register budget of this loop.
+                    // Partial sums stay in fp32 for one UNIT of the thread's share (<= 256 pixels, non-negative terms) and are
+                    // flushed -- warp shuffle tree, one fixed-point atomic per warp -- at the unit boundary (for_each_unit): the
+                    // fp64 / int64 accumulators would not fit the register budget of this loop, and the unit structure makes
+                    // the sums independent of the cluster size.
                     float2 f[9];
 #pragma unroll
                     for (int i = 0; i < 9; ++i) f[i] = make_float2(0.f, 0.f);
+                    auto flush = [&]() {
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) {
+                            float v = f[i].x + f[i].y;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                            if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(&sh->acc64[i], (unsigned long long)to_fix(v, FIX_DL));
+                            f[i] = make_float2(0.f, 0.f);
+                        }
+                    };
                     auto accumulate_general = [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
                         const uint32_t mbits = cache_mask ? *(cache_smem ? mask_slot(sh->hist, g - gb) : a.mask_scratch + (size_t)tile * G + g)
                                                           : mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
@@ -884,18 +968,20 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                         };
                     };
                     auto run_pass = [&](auto&& body) {
-                        if (phase == 0) for_each_sample_group(tin, npx, gb, ge, aligned, body);
-                        else for_each_group<true>(tin, npx, gb, ge, aligned, body);
+                        if (phase == 0) for_each_sample_group_flush(tin, npx, gb, ge, aligned, body, flush);
+                        else for_each_unit(tin, npx, UK, ub, ue, U, aligned, body, flush);
                     };
                     const int lm = lasso_mode_of(lk.rg00, lk.rg11, lk.g01);
                     if (lm == LASSO_UNIT_POS) run_pass(accumulate_unit(LassoMode<LASSO_UNIT_POS>{}));
                     else if (lm == LASSO_UNIT_NEG) run_pass(accumulate_unit(LassoMode<LASSO_UNIT_NEG>{}));
                     else run_pass(accumulate_general);
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) acc[i] = (double)f[i].x + (double)f[i].y;
-                    block_reduce10(sh, pbuf, acc, 0u);
+                    __syncthreads();
+                    if (threadIdx.x < 10) {
+                        sh->part[pbuf][threadIdx.x] = threadIdx.x < 9 ? (long long)sh->acc64[threadIdx.x] : 0ll;
+                        sh->acc64[threadIdx.x] = 0ull;
+                    }
                     tile_sync(S);
-                    cluster_total10(sh, pbuf, S);
+                    cluster_total10(sh, pbuf, S, 1.0 / (double)FIX_DL);
                     pbuf ^= 1;
                     if (threadIdx.x == 0) {
                         const double* t = sh->tot;
@@ -1152,12 +1238,11 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
 
 template <int METHOD>
 static int launch_tile_pipeline_t(const PipeArgs& a, int num_sms, cudaStream_t stream) {
-    static bool attr_set = false;
+    static DeviceOnce once;      // per instantiation
     const size_t smem = OD_REP_BYTES + sizeof(PipeShared);
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tile_pipeline_kernel<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = ensure_dyn_smem(once, tile_pipeline_kernel<METHOD>, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
     }
     const int S = a.cluster_size;
     int ctas_per_sm = 2;
@@ -1331,12 +1416,11 @@ int slide_grid(const SlideArgs& a, int num_sms) {
 
 template <int PASS>
 static int launch_slide_pass_t(const SlideArgs& a, int grid, cudaStream_t stream) {
-    static bool attr_set = false;
+    static DeviceOnce once;      // per instantiation
     const size_t smem = OD_REP_BYTES + 2 * L1_BINS * sizeof(unsigned);
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(slide_pass_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = ensure_dyn_smem(once, slide_pass_kernel<PASS>, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
     }
     slide_pass_kernel<PASS><<<grid, SLIDE_NT, smem, stream>>>(a);
     return (int)cudaGetLastError();

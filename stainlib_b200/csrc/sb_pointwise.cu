@@ -275,23 +275,77 @@ struct AugOp {
     __device__ static void finish_run(const Params&, int, Acc&) {}
 };
 
-int launch_stain_augment(const PointArgs& a, int num_sms, cudaStream_t stream) {
+int launch_stain_augment(const PointArgs& a, Scratch& scratch) {
+    const int num_sms = scratch.h->num_sms;
+    cudaStream_t stream = scratch.st;
     if (a.aligned) {
         AugConsts* consts = nullptr;
-        cudaError_t e = cudaMallocAsync(&consts, (size_t)a.B * sizeof(AugConsts), stream);
+        cudaError_t e = scratch.get(&consts, (size_t)a.B * sizeof(AugConsts));
         if (e != cudaSuccess) return (int)e;
         aug_prepare_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a, consts);
         AugRingParams p{};
         p.consts = consts; p.od = a.tab.od; p.gamma = a.tab.gamma;
         p.ycoef[0] = a.ycoef[0]; p.ycoef[1] = a.ycoef[1]; p.ycoef[2] = a.ycoef[2]; p.ybound = a.ybound;
         p.all_px = a.augment_background != 0;
-        const int rc = launch_ring<AugOp>(RingGeom{a.in, a.out, a.B, a.npx}, p, num_sms, stream);
-        cudaFreeAsync(consts, stream);
-        return rc;
+        return launch_ring<AugOp>(RingGeom{a.in, a.out, a.B, a.npx}, p, num_sms, stream);
     }
     stain_augment_kernel<<<point_grid(a, num_sms, 4), PT, 0, stream>>>(a);
     return (int)cudaGetLastError();
 }
+// ------------------------------------------------------------------------------------------- RGB <-> optical density
+// convert_RGB_to_OD (stain_utils.py:101-112): OD = max(-ln(max(v, 1) / 255), 1e-6) is a function of one uint8, so the
+// kernel is a 256-entry float64 table lookup: 1 B read, 8 B (or 4 B) written per value.  One thread converts 16 bytes.
+template <typename T>
+__global__ void __launch_bounds__(256) rgb_to_od_kernel(const uint8_t* __restrict__ in, T* __restrict__ out, size_t n, const double* __restrict__ od64) {
+    __shared__ T tab[256];
+    tab[threadIdx.x] = (T)od64[threadIdx.x];
+    __syncthreads();
+    const size_t nvec = n / 16;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+        uint32_t w[4];
+        if (vec_ok) { const uint4 x = ldg_stream(reinterpret_cast<const uint4*>(in) + v); w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; }
+        else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { w[i] = 0; for (int j = 0; j < 4; ++j) w[i] |= (uint32_t)in[v * 16 + i * 4 + j] << (8 * j); }
+        }
+        T* dst = out + v * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dst[i] = tab[(w[i >> 2] >> (8 * (i & 3))) & 255u];
+    }
+    // ragged tail (< 16 values)
+    if (blockIdx.x == 0 && threadIdx.x < (n & 15)) { const size_t i = nvec * 16 + threadIdx.x; out[i] = tab[in[i]]; }
+}
+// convert_OD_to_RGB (stain_utils.py:114-124): uint8(255 * exp(-max(OD, 1e-6))), truncation toward zero; min_out[0] is
+// lowered below zero when any OD is negative (the reference asserts OD.min() >= 0).
+template <typename T>
+__global__ void __launch_bounds__(256) od_to_rgb_kernel(const T* __restrict__ od, uint8_t* __restrict__ out, size_t n, int* __restrict__ negative) {
+    int neg = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double x = (double)od[i];
+        neg |= (x < 0.0);
+        const double v = 255.0 * exp(-fmax(x, 1e-6));
+        out[i] = (uint8_t)(int)v;
+    }
+    if (neg && negative) atomicOr(negative, 1);
+}
+int launch_rgb_to_od(const uint8_t* in, void* out, size_t n, int f32, const double* od64, int num_sms, cudaStream_t stream) {
+    size_t blocks = (n / 16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > (size_t)num_sms * 8) blocks = (size_t)num_sms * 8;
+    if (f32) rgb_to_od_kernel<float><<<(int)blocks, 256, 0, stream>>>(in, static_cast<float*>(out), n, od64);
+    else rgb_to_od_kernel<double><<<(int)blocks, 256, 0, stream>>>(in, static_cast<double*>(out), n, od64);
+    return (int)cudaGetLastError();
+}
+int launch_od_to_rgb(const void* od, uint8_t* out, size_t n, int f32, int* negative, int num_sms, cudaStream_t stream) {
+    size_t blocks = (n + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > (size_t)num_sms * 16) blocks = (size_t)num_sms * 16;
+    if (f32) od_to_rgb_kernel<float><<<(int)blocks, 256, 0, stream>>>(static_cast<const float*>(od), out, n, negative);
+    else od_to_rgb_kernel<double><<<(int)blocks, 256, 0, stream>>>(static_cast<const double*>(od), out, n, negative);
+    return (int)cudaGetLastError();
+}
+
 int launch_concentrations(const PointArgs& a, int num_sms, cudaStream_t stream) {
     concentrations_kernel<<<point_grid(a, num_sms, 8), PT, 0, stream>>>(a);
     return (int)cudaGetLastError();

@@ -156,11 +156,10 @@ struct K4Op {
 static int launch_k4(const PointArgs& a, int num_sms, cudaStream_t stream, const K4Consts* consts, bool use_tma) {
     if (use_tma)   // 512 compute threads x 6 slots of 24 KB (chunks divide 256^2 and 512^2 tiles evenly) on the generic ring
         return launch_ring<K4Op>(RingGeom{a.in, a.out, a.B, a.npx}, K4RingParams{consts, a.tab.od, a.debug_copy}, num_sms, stream);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(recombine_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OD_REP_BYTES);
+    static DeviceOnce once;
+    {
+        cudaError_t e = ensure_dyn_smem(once, recombine_v2_kernel, OD_REP_BYTES);
         if (e != cudaSuccess) return (int)e;
-        attr = true;
     }
     const int G = (a.npx + GROUP_PX - 1) / GROUP_PX;
     // each CTA fills a 64 KB table, so give it at least ~64k pixels; aim for >= 2 waves of (SMs x 3) CTAs
@@ -173,25 +172,21 @@ static int launch_k4(const PointArgs& a, int num_sms, cudaStream_t stream, const
     return (int)cudaGetLastError();
 }
 
-int launch_recombine(const PointArgs& a, int num_sms, cudaStream_t stream, bool use_tma) {
+int launch_recombine(const PointArgs& a, Scratch& scratch, bool use_tma) {
     K4Consts* consts = nullptr;
-    cudaError_t e = cudaMallocAsync(&consts, (size_t)a.B * sizeof(K4Consts), stream);
+    cudaError_t e = scratch.get(&consts, (size_t)a.B * sizeof(K4Consts));
     if (e != cudaSuccess) return (int)e;
-    k4_prepare_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a, consts);
-    const int rc = launch_k4(a, num_sms, stream, consts, use_tma);
-    cudaFreeAsync(consts, stream);
-    return rc;
+    k4_prepare_kernel<<<(a.B + 127) / 128, 128, 0, scratch.st>>>(a, consts);
+    return launch_k4(a, scratch.h->num_sms, scratch.st, consts, use_tma);
 }
 
-int launch_recombine_normalize(const PointArgs& a, int num_sms, cudaStream_t stream, bool use_tma, const double* M_src,
+int launch_recombine_normalize(const PointArgs& a, Scratch& scratch, bool use_tma, const double* M_src,
                                const double* maxC_src, const double* Mt, const double* maxCt, int32_t* status) {
     K4Consts* consts = nullptr;
-    cudaError_t e = cudaMallocAsync(&consts, (size_t)a.B * sizeof(K4Consts), stream);
+    cudaError_t e = scratch.get(&consts, (size_t)a.B * sizeof(K4Consts));
     if (e != cudaSuccess) return (int)e;
-    k4_prepare_normalize_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a.B, M_src, maxC_src, Mt, maxCt, a.lasso_lambda, status, consts);
-    const int rc = launch_k4(a, num_sms, stream, consts, use_tma);
-    cudaFreeAsync(consts, stream);
-    return rc;
+    k4_prepare_normalize_kernel<<<(a.B + 127) / 128, 128, 0, scratch.st>>>(a.B, M_src, maxC_src, Mt, maxCt, a.lasso_lambda, status, consts);
+    return launch_k4(a, scratch.h->num_sms, scratch.st, consts, use_tma);
 }
 
 }  // namespace sb

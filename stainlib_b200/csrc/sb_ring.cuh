@@ -162,11 +162,10 @@ static int launch_ring(const RingGeom& g, const typename Op::Params& p, int num_
     static_assert(GT % 32 == 0 && GT + 32 <= 1024, "block size");
     static_assert(OD_REP_BYTES + NSTAGE * CHUNK_BYTES + 1024 + RING_BAR_BYTES <= RING_SMEM_BYTES, "ring does not fit");
     static_assert(2 * NSTAGE * 8 <= RING_BAR_BYTES, "barrier area");
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(ring_pointwise_kernel<Op, GT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM_BYTES);
+    static DeviceOnce once;      // one per instantiation (function-local static of a function template)
+    {
+        cudaError_t e = ensure_dyn_smem(once, ring_pointwise_kernel<Op, GT, NSTAGE>, RING_SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
-        attr = true;
     }
     const size_t tile_bytes = (size_t)g.npx * 3;
     const int cpt = (int)((tile_bytes + CHUNK_BYTES - 1) / CHUNK_BYTES);

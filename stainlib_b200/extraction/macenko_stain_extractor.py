@@ -21,12 +21,13 @@ class MacenkoStainExtractor(ABCStainExtractor):
     last_status = None
 
     @staticmethod
-    def get_stain_matrix(I, luminosity_threshold=0.8, angular_percentile=99):
+    def get_stain_matrix(I, luminosity_threshold=0.8, angular_percentile=99, cluster_size=None):
         """Stain matrix estimation via the method of M. Macenko et al. -- one fused CUDA pass sequence per tile
-        (mask + OD moments, fp64 eigenvectors, exact angular percentiles).  2x3 float64 (numpy image) or [B,2,3]."""
+        (mask + OD moments, fp64 eigenvectors, exact angular percentiles).  2x3 float64 (numpy image) or [B,2,3].
+        ``cluster_size`` (extension; 1/2/4/8 CTAs per tile, default automatic) changes the schedule, never the result."""
         assert is_uint8_image(I), "Image should be RGB uint8."
         p = nv.default_params(nv.SB_METHOD_MACENKO, luminosity_threshold=float(luminosity_threshold),
-                              angular_percentile=float(angular_percentile))
+                              angular_percentile=float(angular_percentile), cluster_size=cluster_size)
         M, st = _extract(I, p)
         MacenkoStainExtractor.last_status = st
         return M

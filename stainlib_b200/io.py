@@ -33,15 +33,20 @@ _STREAMS = {}      # device index -> (s_in, s_comp, s_out): kept across calls (s
 _SLOTS = {}        # (device index, chunk shape) -> three device input slots
 
 
-def stream_host_batches(op, host_in, host_out=None, chunk_tiles=0, device=None):
+def stream_host_batches(op, host_in, host_out=None, chunk_tiles=0, device=None, keep_on_device=False):
     """``host_out[i] = op(host_in[i])`` tile batch by tile batch with copies and compute overlapped.
 
     op: callable taking and returning a uint8 [b,H,W,3] CUDA tensor (e.g. ``lambda x: rein.transform(hed.transform(x))``).
     host_in / host_out: uint8 [B,H,W,3] CPU tensors, pinned for full speed.  chunk_tiles = 0 picks ~96 MB chunks: the
-    per-chunk cost of the Python-level operator calls (~0.2 ms) wants chunks of at least tens of MB.  Returns host_out."""
+    per-chunk cost of the Python-level operator calls (~0.2 ms) wants chunks of at least tens of MB.  Returns host_out.
+    ``keep_on_device=True``: the results stay in HBM (one [B,H,W,3] CUDA tensor is returned, nothing is copied back) --
+    the case of a training loop that consumes the normalised tiles on the GPU."""
     _, idx = nv.get_handle(device)
     dev = torch.device("cuda", idx)
-    if host_out is None:
+    dev_out = None
+    if keep_on_device:
+        dev_out = torch.empty(host_in.shape, dtype=torch.uint8, device=dev)
+    elif host_out is None:
         host_out = torch.empty_like(host_in, pin_memory=host_in.is_pinned())
     B = host_in.shape[0]
     tile_bytes = int(host_in[0].numel())
@@ -68,14 +73,19 @@ def stream_host_batches(op, host_in, host_out=None, chunk_tiles=0, device=None):
         slot, nt = c % n_slot, min(chunk_tiles, B - t0)
         if c >= n_slot:
             s_in.wait_event(ev_comp[slot])              # the slot's previous input has been consumed
-            s_comp.wait_event(ev_out[slot])             # ... and its previous output copied out
+            if not keep_on_device:
+                s_comp.wait_event(ev_out[slot])         # ... and its previous output copied out
         with torch.cuda.stream(s_in):
             d_in[slot][:nt].copy_(host_in[t0:t0 + nt], non_blocking=True)
             ev_in[slot].record(s_in)
         with torch.cuda.stream(s_comp):
             s_comp.wait_event(ev_in[slot])
             d_out[slot] = op(d_in[slot][:nt])
+            if keep_on_device:
+                dev_out[t0:t0 + nt].copy_(d_out[slot])
             ev_comp[slot].record(s_comp)
+        if keep_on_device:
+            continue
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_comp[slot])
             host_out[t0:t0 + nt].copy_(d_out[slot], non_blocking=True)
@@ -84,4 +94,7 @@ def stream_host_batches(op, host_in, host_out=None, chunk_tiles=0, device=None):
     s_out.synchronize()
     s_comp.synchronize()
     s_in.synchronize()
+    if keep_on_device:
+        cur.wait_stream(s_comp)
+        return dev_out
     return host_out

@@ -128,22 +128,52 @@ def normalize_matrix_rows(A):
     return A / np.linalg.norm(A, axis=1)[:, None]
 
 
-_OD_LUT = np.maximum(-1 * np.log(np.maximum(np.arange(256), 1) / 255), 1e-6)
+def _to_cuda(x, dtype=None):
+    """numpy / CPU tensor / CUDA tensor -> (contiguous CUDA tensor, kind) for the flat element-wise entry points."""
+    if isinstance(x, np.ndarray):
+        kind, t = "numpy", torch.from_numpy(np.ascontiguousarray(x))
+    elif isinstance(x, torch.Tensor):
+        kind, t = ("cuda" if x.is_cuda else "cpu"), x
+    else:
+        raise AssertionError("expected a numpy array or a torch tensor")
+    _, idx = nv.get_handle(t.device if t.is_cuda else None)
+    t = t.to(f"cuda:{idx}")
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.contiguous(), kind, idx
 
 
-def convert_RGB_to_OD(I):
-    """stain_utils.py:101-112: OD = max(-ln(max(I,1)/255), 1e-6) -- a 256-entry table lookup (float64).
-    Convenience export only; the kernels apply the same table inline."""
-    if isinstance(I, torch.Tensor):
-        return torch.as_tensor(_OD_LUT, device=I.device)[I.long()]
-    return _OD_LUT[I]
+def _from_cuda(t, kind):
+    if kind == "numpy":
+        return t.cpu().numpy()
+    return t.cpu() if kind == "cpu" else t
+
+
+def convert_RGB_to_OD(I, dtype=None):
+    """stain_utils.py:101-112: OD = max(-ln(max(I,1)/255), 1e-6), a 256-entry float64 table lookup on the GPU
+    (``sb_rgb_to_od``).  Returns float64 like the reference (``dtype=torch.float32`` halves the bytes written for
+    tensor batches); the kernels of the hot path apply the same table inline and never materialise an OD image."""
+    t, kind, idx = _to_cuda(I)
+    assert t.dtype == torch.uint8, "Image should be RGB uint8."
+    f32 = dtype in (torch.float32, np.float32)
+    out = torch.empty(t.shape, dtype=torch.float32 if f32 else torch.float64, device=t.device)
+    if t.numel():
+        h, _ = nv.get_handle(idx)
+        nv.check(nv.load_library().sb_rgb_to_od(h, nv.ptr(t), t.numel(), nv.ptr(out), int(f32), nv.stream_ptr(idx)))
+    return _from_cuda(out, kind)
 
 
 def convert_OD_to_RGB(OD):
-    """stain_utils.py:114-124."""
-    if isinstance(OD, torch.Tensor):
-        assert OD.min() >= 0, "Negative optical density."
-        return (255 * torch.exp(-1 * torch.clamp(OD, min=1e-6))).to(torch.uint8)
-    assert OD.min() >= 0, "Negative optical density."
-    OD = np.maximum(OD, 1e-6)
-    return (255 * np.exp(-1 * OD)).astype(np.uint8)
+    """stain_utils.py:114-124: uint8(255 * exp(-max(OD, 1e-6))) on the GPU (``sb_od_to_rgb``); asserts OD >= 0 like the
+    reference."""
+    t, kind, idx = _to_cuda(OD)
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    out = torch.empty(t.shape, dtype=torch.uint8, device=t.device)
+    neg = torch.zeros(1, dtype=torch.int32, device=t.device)
+    if t.numel():
+        h, _ = nv.get_handle(idx)
+        nv.check(nv.load_library().sb_od_to_rgb(h, nv.ptr(t), int(t.dtype == torch.float32), t.numel(), nv.ptr(out), nv.ptr(neg),
+                                                nv.stream_ptr(idx)))
+    assert int(neg.item()) == 0, "Negative optical density."
+    return _from_cuda(out, kind)

@@ -148,3 +148,121 @@ def test_stain_augmentor_batch(sb):
         o.fit(tiles[i])
         mx, frac = lsb_stats(out[i], o.pop(alphas=al[i], betas=be[i]))
         assert mx <= 1 and frac >= 0.999, (i, mx, frac)
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (67, 53)])
+def test_hed_skimage018_variant(sb, shape):
+    """scikit-image >= 0.18 definition of rgb2hed / hed2rgb (the one an unpinned install of the reference uses today):
+    aligned tiles take the TMA ring operator, the odd shape takes the register-staged kernel.  <= 1 LSB, >= 99.9 % equal
+    (plain difference: the operator clips)."""
+    rng = np.random.default_rng(5)
+    tiles = synth_batch(70, 3, *shape)
+    sig, bia = rng.uniform(-0.1, 0.1, (3, 3)), rng.uniform(-0.1, 0.1, (3, 3))
+    h = sb.HedLightColorAugmenter()
+    out = h.transform(torch.from_numpy(tiles).cuda(), sigmas=sig, biases=bia, skimage_version="0.18").cpu().numpy()
+    for i in range(3):
+        ref = so.hed_augment(tiles[i], sig[i], bia[i], skimage_version="0.18")
+        mx, frac = lsb_stats(out[i], ref)
+        assert mx <= 1 and frac >= 0.999, (i, mx, frac)
+    one = h.transform(tiles[0], sigmas=sig[0], biases=bia[0], skimage_version="0.18")
+    assert np.array_equal(one, out[0])
+    # the two definitions are different functions: the variant switch must actually change the result
+    assert not np.array_equal(out[0], h.transform(tiles[0], sigmas=sig[0], biases=bia[0]))
+
+
+@pytest.mark.parametrize("version", ["0.17", "0.18"])
+def test_hed_float_patches(sb, version):
+    """augmenter.py:288-291, 323-327: a float patch in [0,1] is transformed as it is and a float patch comes back.
+    Tolerance 5e-6 absolute (fp32 log2f / exp2f against the float64 restatement)."""
+    rng = np.random.default_rng(9)
+    tile = synth_batch(80, 1, 96, 80)[0]
+    for dt in (np.float32, np.float64):
+        patch = (tile.astype(np.float64) / 255.0).astype(dt)
+        h = sb.HedLightColorAugmenter()
+        np.random.seed(3)
+        h.randomize()
+        got = h.transform(patch, skimage_version=version)
+        ref = so.hed_augment(patch, h._sigmas, h._biases, skimage_version=version)
+        assert got.dtype == dt and got.shape == patch.shape
+        assert np.abs(got.astype(np.float64) - ref).max() < 5e-6
+    white = np.ones((32, 32, 3), np.float32)
+    assert sb.HedLightColorAugmenter().transform(white) is white          # outside the cutoff: same object
+    tb = torch.from_numpy(np.stack([patch.astype(np.float32), white[:1].repeat(96, 0).repeat(80, 1)[:96, :80]])).cuda()
+    sig, bia = rng.uniform(-0.1, 0.1, (2, 3)), rng.uniform(-0.1, 0.1, (2, 3))
+    h = sb.HedLightColorAugmenter()
+    out = h.transform(tb, sigmas=sig, biases=bia, skimage_version=version)
+    assert out.is_cuda and out.dtype == torch.float32 and h.last_status.cpu().tolist() == [0, 1]
+    assert torch.equal(out[1], tb[1])
+    ref = so.hed_augment(tb[0].cpu().numpy(), sig[0], bia[0], skimage_version=version)
+    assert np.abs(out[0].cpu().numpy().astype(np.float64) - ref).max() < 5e-6
+
+
+def test_convert_rgb_od_roundtrip(sb, golden):
+    """convert_RGB_to_OD / convert_OD_to_RGB (stain_utils.py:101-124) through their CUDA entry points, against the
+    reference's own output (golden od/*) and the oracle."""
+    from stainlib_b200.utils.stain_utils import convert_OD_to_RGB, convert_RGB_to_OD
+    for name in ("s_64", "odd_67x53"):
+        src = golden[f"in/{name}/src"]
+        od = convert_RGB_to_OD(src)
+        assert od.dtype == np.float64 and od.shape == src.shape
+        assert np.array_equal(od, golden[f"od/{name}"])                   # bit-exact: a 256-entry float64 table
+    ramp = np.arange(256, dtype=np.uint8).reshape(1, 256, 1).repeat(3, axis=2)
+    assert np.array_equal(convert_RGB_to_OD(ramp), so.convert_RGB_to_OD(ramp))
+    batch = torch.from_numpy(synth_batch(90, 2, 40, 56)).cuda()
+    odb = convert_RGB_to_OD(batch)
+    assert odb.is_cuda and odb.dtype == torch.float64 and odb.shape == batch.shape
+    assert np.array_equal(odb.cpu().numpy(), so.convert_RGB_to_OD(batch.cpu().numpy()))
+    od32 = convert_RGB_to_OD(batch, dtype=torch.float32)
+    assert od32.dtype == torch.float32 and torch.equal(od32, odb.float())
+    # OD -> RGB: exp in float64 on both sides; a value may differ by one where 255*exp(-OD) is within an ulp of an integer
+    rng = np.random.default_rng(0)
+    OD = rng.uniform(0.0, 5.6, (33, 47, 3))
+    got, ref = convert_OD_to_RGB(OD), so.convert_OD_to_RGB(OD)
+    assert got.dtype == np.uint8 and np.array_equal(got, ref)
+    mx, frac = lsb_stats(convert_OD_to_RGB(od), so.convert_OD_to_RGB(golden["od/odd_67x53"]))
+    assert mx <= 1 and frac >= 0.98, (mx, frac)
+    with pytest.raises(AssertionError):
+        convert_OD_to_RGB(np.array([[[0.1, -0.2, 0.3]]]))
+
+
+def test_caller_owned_workspace(sb):
+    """sb_workspace_bytes / sb_set_workspace: with a lent workspace the results are the same bytes."""
+    from stainlib_b200 import _native as nv
+    tgt = synth_tile(1, 128, kind="target")
+    batch = torch.from_numpy(synth_batch(120, 6, 128)).cuda()
+    n = sb.ExtractiveStainNormalizer("vahadane")
+    n.fit(tgt)
+    ref = n.transform(batch)
+    need = nv.workspace_bytes(6, 128, 128)
+    assert need > 0
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    nv.set_workspace(ws)
+    try:
+        assert torch.equal(n.transform(batch), ref)
+        h = sb.HedLightColorAugmenter()
+        a = h.transform(batch)
+        nv.set_workspace(None)
+        assert torch.equal(h.transform(batch), a)
+    finally:
+        nv.set_workspace(None)
+
+
+def test_two_devices_one_process(sb):
+    """One handle per device in one process: kernels with > 48 KB of dynamic shared memory must opt in on EVERY device,
+    entry points must run on their handle's device and leave the caller's current device alone."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    tgt = synth_tile(1, 128, kind="target")
+    batch = torch.from_numpy(synth_batch(130, 3, 128))
+    n = sb.ExtractiveStainNormalizer("macenko")
+    n.fit(tgt)
+    a = n.transform(batch.to("cuda:0"))
+    assert torch.cuda.current_device() == 0
+    b = n.transform(batch.to("cuda:1"))
+    assert torch.cuda.current_device() == 0 and b.device.index == 1
+    assert torch.equal(a.cpu(), b.cpu())
+    r = sb.ReinhardStainNormalizer()
+    r.fit(tgt)
+    assert torch.equal(r.transform(batch.to("cuda:1")).cpu(), r.transform(batch.to("cuda:0")).cpu())
+    h = sb.HedLightColorAugmenter()
+    assert torch.equal(h.transform(batch.to("cuda:1")).cpu(), h.transform(batch.to("cuda:0")).cpu())

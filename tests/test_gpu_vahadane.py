@@ -28,7 +28,7 @@ def test_vahadane_vs_golden(sb, golden, name):
     v.fit(golden[f"in/{name}/tgt"])
     np.testing.assert_allclose(v.stain_matrix_target, golden[f"vahadane/{name}/M_target"], rtol=0, atol=1e-4)
     np.testing.assert_allclose(v.maxC_target, golden[f"vahadane/{name}/maxC_target"], rtol=1e-3)
-    mx, frac = lsb_stats(v.transform(golden[f"in/{name}/src"]), golden[f"vahadane/{name}/out"])
+    mx, frac = lsb_stats(v.transform(golden[f"in/{name}/src"]), golden[f"vahadane/{name}/out"], wrap=True)
     assert mx <= 1 and frac >= 0.99, (mx, frac)
 
 
@@ -56,11 +56,10 @@ def test_vahadane_batch_and_clusters(sb):
         v.fit(tgt)
         outs.append(v.transform(batch).cpu().numpy())
     for o in outs[1:]:
-        mx, frac = lsb_stats(o, outs[0])
-        assert mx <= 1 and frac >= 0.999
+        assert np.array_equal(o, outs[0])          # cluster-size independent to the last byte (fixed-point sums)
     o = so.ExtractiveStainNormalizer("vahadane", n_iter=30, solver="fullbatch")
     o.fit(tgt)
-    mx, frac = lsb_stats(outs[0][2], o.transform(batch[2].cpu().numpy()))
+    mx, frac = lsb_stats(outs[0][2], o.transform(batch[2].cpu().numpy()), wrap=True)
     assert mx <= 1 and frac >= 0.99, (mx, frac)
 
 
@@ -89,9 +88,45 @@ def test_vahadane_accelerated_clusters_and_image(sb):
         outs.append(v.transform(batch).cpu().numpy())
         Ms.append(sb.VahadaneStainExtractor.get_stain_matrix(batch[1].cpu().numpy()))
     for o in outs[1:]:
-        mx, frac = lsb_stats(o, outs[0])
-        assert mx <= 1 and frac >= 0.999
+        assert np.array_equal(o, outs[0])          # cluster-size independent to the last byte (fixed-point sums)
+    for m in Ms[1:]:
+        assert np.array_equal(m, Ms[0])
     o = so.ExtractiveStainNormalizer("vahadane")
     o.fit(tgt)
-    mx, frac = lsb_stats(outs[0][2], o.transform(batch[2].cpu().numpy()))
+    mx, frac = lsb_stats(outs[0][2], o.transform(batch[2].cpu().numpy()), wrap=True)
     assert mx <= 1 and frac >= 0.99, (mx, frac)
+
+
+@pytest.mark.parametrize("size", [512, 1024])
+def test_vahadane_image_parity_large_tiles(sb, size):
+    """Image-level parity of the default (accelerated) Vahadane transform against the CPU restatement of the same
+    schedule on 512^2 and 1024^2 tiles (tolerance: <= 1 LSB with wrap, >= 99 % of the bytes equal -- the stain matrix
+    agrees to ~1e-5, which moves a byte only where 255*exp(.) sits within 1e-4 of an integer)."""
+    tgt = synth_tile(1, size, kind="target")
+    src = synth_tile(40 + size, size)
+    v = sb.ExtractiveStainNormalizer("vahadane")
+    v.fit(tgt)
+    o = so.ExtractiveStainNormalizer("vahadane")
+    o.fit(tgt)
+    np.testing.assert_allclose(v.stain_matrix_target, o.stain_matrix_target, rtol=0, atol=3e-5)
+    mx, frac = lsb_stats(v.transform(src), o.transform(src), wrap=True)
+    assert mx <= 1 and frac >= 0.99, (size, mx, frac)
+
+
+def test_vahadane_host_device_and_shards_bytes_equal(sb):
+    """the host-streamed path (small chunks -> a different cluster size per launch), the device path on the
+    whole batch and any split of the batch must give identical bytes."""
+    tgt = synth_tile(1, 256, kind="target")
+    batch = torch.from_numpy(synth_batch(310, 12, 256))
+    v = sb.ExtractiveStainNormalizer("vahadane")
+    v.fit(tgt)
+    ref = v.transform(batch.cuda()).cpu()
+    host = v.transform(batch.pin_memory(), chunk_tiles=5)
+    assert torch.equal(host, ref)
+    parts = torch.cat([v.transform(batch[:1].cuda()).cpu(), v.transform(batch[1:7].cuda()).cpu(), v.transform(batch[7:].cuda()).cpu()])
+    assert torch.equal(parts, ref)
+    for S in (1, 2, 4, 8):
+        vs = sb.ExtractiveStainNormalizer("vahadane", cluster_size=S)
+        vs.fit(tgt)
+        assert np.array_equal(vs.stain_matrix_target, v.stain_matrix_target), S
+        assert torch.equal(vs.transform(batch.cuda()).cpu(), ref), S
