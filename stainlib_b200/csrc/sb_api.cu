@@ -99,12 +99,21 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
         }
         a.bracket_sigmas = sig; a.bracket_pad = pad;
     }
+    // Macenko statistics: streaming passes over the whole batch (sb_stream.cu) for 16-byte aligned tiles of >= 32,768
+    // pixels; the fused per-tile kernel otherwise, when a cluster size is requested explicitly, or with SB_NO_STREAM set.
+    // Both give the same bits.
+    static const bool no_stream = getenv("SB_NO_STREAM") != nullptr;
+    auto run_stats = [&](const sb::PipeArgs& pa) -> cudaError_t {
+        if (!no_stream && p->cluster_size == 0 && sb::stream_pipeline_eligible(pa)) return (cudaError_t)sb::launch_stream_pipeline(pa, scratch);
+        cudaError_t e = (cudaError_t)sb::launch_tile_pipeline(pa, h->num_sms, stream);
+        if (e == cudaSuccess) h->launches += 1;
+        return e;
+    };
     if (mode != sb::PIPE_NORMALIZE) {
-        sb::NvtxRange nvtx(mode == sb::PIPE_FIT ? "sb_fit: tile_pipeline" : "sb_extract: tile_pipeline");
+        sb::NvtxRange nvtx(mode == sb::PIPE_FIT ? "sb_fit: statistics" : "sb_extract: statistics");
         a.mode = mode; a.M_out = M; a.maxC_out = maxC; a.status = status;
-        cudaError_t e = (cudaError_t)sb::launch_tile_pipeline(a, h->num_sms, stream);
-        if (e != cudaSuccess) return cuda_fail(e, "tile_pipeline launch");
-        h->launches += 1;
+        cudaError_t e = run_stats(a);
+        if (e != cudaSuccess) return cuda_fail(e, "statistics launch");
         return SB_OK;
     }
     // transform = fused per-tile statistics kernel (stain matrix + maxC of every source tile) followed by the
@@ -119,10 +128,10 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
     a.mode = sb::PIPE_FIT; a.M_out = Mw; a.maxC_out = Cw; a.status = Sw;
     cudaError_t e;
     {
-        sb::NvtxRange nvtx("sb_normalize: tile_pipeline (statistics)");
-        e = (cudaError_t)sb::launch_tile_pipeline(a, h->num_sms, stream);
+        sb::NvtxRange nvtx("sb_normalize: statistics");
+        e = run_stats(a);
     }
-    if (e != cudaSuccess) return cuda_fail(e, "tile_pipeline launch");
+    if (e != cudaSuccess) return cuda_fail(e, "statistics launch");
     sb::PointArgs k{};
     k.in = in; k.out = out; k.B = B; k.npx = a.npx; k.aligned = a.aligned; k.tab = h->tab; k.lasso_lambda = p->lasso_lambda;
     const bool tma = a.aligned && getenv("SB_K4_NO_TMA") == nullptr;
@@ -131,7 +140,7 @@ int run_pipeline(sb_handle* h, int mode, const uint8_t* in, uint8_t* out, int B,
         e = (cudaError_t)sb::launch_recombine_normalize(k, scratch, tma, Mw, Cw, Mt, maxCt, Sw);
     }
     if (e != cudaSuccess) return cuda_fail(e, "recombine launch");
-    h->launches += 3;
+    h->launches += 2;
     return SB_OK;
 }
 
@@ -144,6 +153,7 @@ size_t workspace_bytes(int B, int H, int W) {
     n += up((size_t)B * 8 * sizeof(double) + (size_t)B * sizeof(int32_t));      // per-tile statistics of sb_normalize
     n += up((size_t)B * 128);                                                    // per-tile constants of the ring operators
     n += up((size_t)B * 16);                                                     // HED byte sums / counters
+    n += sb::stream_scratch_bytes(B, H * W);                                           // streaming statistics: per-tile state + key lists
     return n;
 }
 

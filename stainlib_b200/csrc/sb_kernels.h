@@ -72,7 +72,7 @@ struct NvtxRange {
 struct Scratch {
     sb_handle* h;
     cudaStream_t st;
-    void* pooled[6];
+    void* pooled[16];
     int n = 0;
     Scratch(sb_handle* hh, cudaStream_t s) : h(hh), st(s) { h->scratch_depth += 1; }
     cudaError_t get(void** p, size_t bytes) {
@@ -82,7 +82,7 @@ struct Scratch {
             h->user_ws_off += need;
             return cudaSuccess;
         }
-        if (n >= 6) return cudaErrorMemoryAllocation;
+        if (n >= 16) return cudaErrorMemoryAllocation;
         cudaError_t e = cudaMallocAsync(p, need, st);
         if (e == cudaSuccess) pooled[n++] = *p;
         return e;
@@ -120,9 +120,16 @@ struct PipeArgs {
     int32_t* status;      // [B] or null
     unsigned short* mask_scratch;   // Vahadane, tiles too big for the shared-memory mask cache: [B][groups] or null
     float bracket_sigmas, bracket_pad;   // half-width of the sampled rank brackets: sigmas * binomial sigma + pad (sample ranks)
+    // optional indirection (fallback of the streaming path): process tiles tile_list[0 .. *tile_count) instead of 0 .. B
+    const int* tile_list;
+    const int* tile_count;
 };
 
 int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream);
+// Streaming (one launch per pass over the whole batch) Macenko statistics: sb_stream.cu.  Same outputs as the fused kernel.
+bool stream_pipeline_eligible(const PipeArgs& a);
+size_t stream_scratch_bytes(int B, int npx);
+int launch_stream_pipeline(const PipeArgs& a, Scratch& scratch);
 
 // ---- slide-level fit passes (sb_pipeline.cu): 0 moments, 1/2 angle histograms (level 1/2), 3/4 concentration histograms
 struct SlideArgs {
