@@ -377,13 +377,16 @@ class Ctx(object):
             return pool[:B].contiguous()
         return pool.repeat(-(-B // pool.shape[0]), 1, 1, 1)[:B].contiguous()
 
-    def timed_device(self, fn, steps, warmup):
+    def timed_device(self, fn, steps, warmup, on_timed_start=None):
         """W warm-up steps, then K steps between CUDA events on the current stream; total ms as the max over ranks, the
         per-step list of this rank, the clocks sampled during the timed region."""
         torch = self.torch
+        out = None
         for _ in range(warmup):
             out = fn()
         self.barrier()
+        if on_timed_start is not None:
+            on_timed_start()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         with ClockSampler(self.local) as clocks:
             ev[0].record()
@@ -471,12 +474,12 @@ def run_extractive(ctx, name, steps, warmup, headline):
     npx_rank = B * H * W
     npx_all = ctx.allreduce(npx_rank, "sum")            # pixels per step over all ranks (weak: world x shard; strong: the fixed total)
 
-    out = None
-    for _ in range(warmup):                            # (keeps the previous result alive like the timed loop does, so that both
-        out = norm.transform(dev_in)                   #  output blocks of the caching allocator exist before the timed region)
-    l0 = nv.launch_count(ctx.local)
-    out, ms_total, per_step_ms, clocks = ctx.timed_device(lambda: norm.transform(dev_in), steps, 0)
-    launches = nv.launch_count(ctx.local) - l0
+    # (the warm-up steps run inside timed_device with the same "previous result stays alive while the next is produced"
+    #  pattern as the timed loop, so that both output blocks of the caching allocator exist before the timed region)
+    counter = {"l0": 0}
+    out, ms_total, per_step_ms, clocks = ctx.timed_device(lambda: norm.transform(dev_in), steps, warmup,
+                                                          on_timed_start=lambda: counter.update(l0=nv.launch_count(ctx.local)))
+    launches = nv.launch_count(ctx.local) - counter["l0"]
     value = npx_all * steps / (ms_total * 1e-3) / 1e6
     status_bad = int((norm.last_status != 0).sum().item())
 
@@ -594,12 +597,9 @@ def run_operator(ctx, name, steps, warmup):
                  ("ring_pointwise_kernel<AugOp> (StainAugmentor.pop)", lambda: aug.pop(alphas=al, betas=be))]
         dtype = "f32 per-pixel arithmetic on u8 pixels, fixed-point per-tile sums"
     step = lambda: op_chunk(dev_in, 0)
-    out = None
-    for _ in range(warmup):
-        out = step()
-    l0 = nv.launch_count(ctx.local)
-    out, ms_total, per_step_ms, clocks = ctx.timed_device(step, steps, 0)
-    launches = nv.launch_count(ctx.local) - l0
+    counter = {"l0": 0}
+    out, ms_total, per_step_ms, clocks = ctx.timed_device(step, steps, warmup, on_timed_start=lambda: counter.update(l0=nv.launch_count(ctx.local)))
+    launches = nv.launch_count(ctx.local) - counter["l0"]
     value = npx_all * steps / (ms_total * 1e-3) / 1e6
     part_ms = [ctx.timed_alone(fn, max(2, min(steps, 10))) for _, fn in parts]
 

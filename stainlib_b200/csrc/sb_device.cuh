@@ -159,7 +159,7 @@ __device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2,
 // 2-atom non-negative LASSO in closed form (oracle: lasso_pos2; reference call site stain_utils.py:78).
 struct LassoK {
     float m00, m01, m02, m10, m11, m12;  // dictionary rows (stain vectors)
-    float lam;
+    float lam, lam1;                     // l1 weight of atom 0 / atom 1 (equal except in the normalised form of make_dict_lasso_consts)
     float i00, i01, i11;                 // inverse Gram matrix
     float rg00, rg11, g01;               // 1/G00, 1/G11, G01
 };
@@ -195,7 +195,7 @@ __device__ __forceinline__ void lasso2_select(float a0, float a1, float u0, floa
 template <int LM>
 __device__ __forceinline__ void lasso2_unit(const LassoK& k, float o0, float o1, float o2, float& c0, float& c1) {
     const float u0 = fmaf(k.m02, o2, fmaf(k.m01, o1, fmaf(k.m00, o0, -k.lam)));
-    const float u1 = fmaf(k.m12, o2, fmaf(k.m11, o1, fmaf(k.m10, o0, -k.lam)));
+    const float u1 = fmaf(k.m12, o2, fmaf(k.m11, o1, fmaf(k.m10, o0, -k.lam1)));
     const float a0 = fmaf(k.i01, u1, k.i00 * u0);
     const float a1 = fmaf(k.i11, u1, k.i01 * u0);
     lasso2_select<LM>(a0, a1, u0, u1, c0, c1);
@@ -211,9 +211,42 @@ __host__ __device__ inline void make_lasso_consts(const double M[6], double lam,
     const double det = g00 * g11 - g01 * g01;
     k.m00 = (float)M[0]; k.m01 = (float)M[1]; k.m02 = (float)M[2];
     k.m10 = (float)M[3]; k.m11 = (float)M[4]; k.m12 = (float)M[5];
-    k.lam = (float)lam;
+    k.lam = (float)lam; k.lam1 = (float)lam;
     k.i00 = (float)(g11 / det); k.i01 = (float)(-g01 / det); k.i11 = (float)(g00 / det);
     k.rg00 = (float)(1.0 / g00); k.rg11 = (float)(1.0 / g11); k.g01 = (float)g01;
+}
+
+// The same problem for a dictionary whose atoms are NOT on the unit sphere (iterates of the Vahadane dictionary learning:
+// the Anderson step leaves the norms slightly below 1), in normalised form: with d^_j = d_j / |d_j| and beta_j = alpha_j |d_j|
+// the objective reads  1/2 |x - sum beta_j d^_j|^2 + sum (lambda / |d_j|) beta_j  -- unit Gram diagonal, one l1 weight per
+// atom -- so the packed compare-free solver applies to every iterate.  The passes accumulate their sums in beta space;
+// dict_scale_sums takes them back: alpha_j = s_j beta_j with s_j = 1 / |d_j|.  An atom that has died (zero vector) gets a
+// zero direction and a weight that keeps its code at zero.
+__host__ __device__ inline void dict_scales(const double D[6], double s[2]) {
+    for (int j = 0; j < 2; ++j) {
+        const double n2 = D[3 * j] * D[3 * j] + D[3 * j + 1] * D[3 * j + 1] + D[3 * j + 2] * D[3 * j + 2];
+        s[j] = n2 > 1e-60 ? 1.0 / sqrt(n2) : 0.0;
+    }
+}
+__host__ __device__ inline void make_dict_lasso_consts(const double D[6], double lam, LassoK& k) {
+    double s[2];
+    dict_scales(D, s);
+    double dn[6];
+    for (int j = 0; j < 2; ++j)
+        for (int c = 0; c < 3; ++c) dn[3 * j + c] = D[3 * j + c] * s[j];
+    const double g01 = dn[0] * dn[3] + dn[1] * dn[4] + dn[2] * dn[5];
+    const double det = 1.0 - g01 * g01;
+    k.m00 = (float)dn[0]; k.m01 = (float)dn[1]; k.m02 = (float)dn[2];
+    k.m10 = (float)dn[3]; k.m11 = (float)dn[4]; k.m12 = (float)dn[5];
+    k.lam = s[0] > 0.0 ? (float)(lam * s[0]) : 1.0f;
+    k.lam1 = s[1] > 0.0 ? (float)(lam * s[1]) : 1.0f;
+    k.i00 = (float)(1.0 / det); k.i01 = (float)(-g01 / det); k.i11 = (float)(1.0 / det);
+    k.rg00 = 1.0f; k.rg11 = 1.0f; k.g01 = (float)g01;
+}
+// t = (sum b0 b0, sum b0 b1, sum b1 b1, sum x b0 (3), sum x b1 (3)) in beta space -> alpha space.
+__host__ __device__ inline void dict_scale_sums(double* t, const double s[2]) {
+    t[0] *= s[0] * s[0]; t[1] *= s[0] * s[1]; t[2] *= s[1] * s[1];
+    for (int c = 0; c < 3; ++c) { t[3 + c] *= s[0]; t[6 + c] *= s[1]; }
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -293,7 +326,7 @@ __device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
 template <int LM>
 __device__ __forceinline__ void lasso2_unit_pair(const LassoK& k, const float2 o0, const float2 o1, const float2 o2, float2& c0, float2& c1) {
     const float2 u0 = __ffma2_rn(dup(k.m02), o2, __ffma2_rn(dup(k.m01), o1, __ffma2_rn(dup(k.m00), o0, dup(-k.lam))));
-    const float2 u1 = __ffma2_rn(dup(k.m12), o2, __ffma2_rn(dup(k.m11), o1, __ffma2_rn(dup(k.m10), o0, dup(-k.lam))));
+    const float2 u1 = __ffma2_rn(dup(k.m12), o2, __ffma2_rn(dup(k.m11), o1, __ffma2_rn(dup(k.m10), o0, dup(-k.lam1))));
     const float2 a0 = __ffma2_rn(dup(k.i01), u1, __fmul2_rn(dup(k.i00), u0));
     const float2 a1 = __ffma2_rn(dup(k.i11), u1, __fmul2_rn(dup(k.i01), u0));
     lasso2_select<LM>(a0.x, a1.x, u0.x, u1.x, c0.x, c1.x);

@@ -29,17 +29,19 @@ struct __align__(16) PipeShared {
     double ang[4], cs[4];            // the four selected angles; cos/sin of the two interpolated ones
     unsigned brk_a[2], brk_b[2];
     float fast_lo[2], fast_hi[2];    // conservative float thresholds that let most pixels skip the exact key
-    unsigned wq[NWARP][WQ_CAP];      // per-warp compaction queues of the rare pixels that need the exact key
     int wq_overflow;
     int s_ok;
     float V[6];
     LassoK lk;
     int flags;
     double D[6];                     // Vahadane dictionary, rows = atoms
-    AAState aa;                      // Anderson history of the dictionary iteration (thread 0)
     int dl_stop;                     // the current phase has converged (residual below DL_SAMPLE_TOL / DL_FULL_TOL)
     double Msrc[6];
     double maxC[2];
+    // ---- the members below are used by the fused kernel only: the per-tile kernels of the streaming path allocate the
+    // structure up to here (offsetof(PipeShared, aa)) to fit six CTAs per SM
+    AAState aa;                      // Anderson history of the dictionary iteration (thread 0)
+    unsigned wq[NWARP][WQ_CAP];      // per-warp compaction queues of the rare pixels that need the exact key
 };
 
 __device__ __forceinline__ void tile_sync(int S) {
@@ -508,7 +510,7 @@ __device__ __forceinline__ void for_each_sample_group(const uint8_t* __restrict_
 // on the tile size only); a cluster of S CTAs splits the tile at unit boundaries; inside a unit thread t always visits
 // the groups (u*K + i)*NT + t, i < K.  The fp32 sum of a (warp, unit) pair is therefore the same number for every S; it is
 // reduced over the warp by a fixed shuffle tree and enters the fixed-point accumulator with one atomic per warp.
-__device__ __forceinline__ int unit_groups(int G) {
+__host__ __device__ __forceinline__ int unit_groups(int G) {
     const int k = G / (8 * NT);
     return k < 1 ? 1 : (k > 16 ? 16 : k);
 }

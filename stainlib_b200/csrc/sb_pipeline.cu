@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                 const double r0[3] = {0.65, 0.70, 0.29}, r1[3] = {0.07, 0.99, 0.11};
                 const double n0 = sqrt(r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]), n1 = sqrt(r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
                 for (int k = 0; k < 3; ++k) { sh->D[k] = r0[k] / n0; sh->D[3 + k] = r1[k] / n1; }
-                make_lasso_consts(sh->D, a.dl_lambda, sh->lk);
+                make_dict_lasso_consts(sh->D, a.dl_lambda, sh->lk);
             }
             __syncthreads();
             // V0: tissue mask -> one bit per pixel (reused by every iteration); tissue counts of the tile and of its sample
@@ -392,19 +392,6 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                             f[i] = make_float2(0.f, 0.f);
                         }
                     };
-                    auto accumulate_general = [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
-                        const uint32_t mbits = cache_mask ? *(cache_smem ? mask_slot(sh->hist, g - gb) : a.mask_scratch + (size_t)tile * G + g)
-                                                          : mask16<decltype(tail)::value>(od_rep, lane_off, w, yc, nvalid);
-                        for_each_px_od(od_rep, lane_off, w, [&](int i, float o0, float o1, float o2) {
-                            float c0, c1;
-                            lasso2(lk, o0, o1, o2, c0, c1);
-                            const bool m = (mbits & (1u << i)) != 0;
-                            c0 = m ? c0 : 0.f; c1 = m ? c1 : 0.f;
-                            f[0].x = fmaf(c0, c0, f[0].x); f[1].x = fmaf(c0, c1, f[1].x); f[2].x = fmaf(c1, c1, f[2].x);
-                            f[3].x = fmaf(o0, c0, f[3].x); f[4].x = fmaf(o1, c0, f[4].x); f[5].x = fmaf(o2, c0, f[5].x);
-                            f[6].x = fmaf(o0, c1, f[6].x); f[7].x = fmaf(o1, c1, f[7].x); f[8].x = fmaf(o2, c1, f[8].x);
-                        });
-                    };
                     auto accumulate_unit = [&](auto unit) {
                         return [&](auto tail, const uint32_t (&w)[12], int nvalid, int g) {
                             constexpr int LM = decltype(unit)::value;
@@ -426,10 +413,10 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                         if (phase == 0) for_each_sample_group_flush(tin, npx, gb, ge, aligned, body, flush);
                         else for_each_unit(tin, npx, UK, ub, ue, U, aligned, body, flush);
                     };
-                    const int lm = lasso_mode_of(lk.rg00, lk.rg11, lk.g01);
-                    if (lm == LASSO_UNIT_POS) run_pass(accumulate_unit(LassoMode<LASSO_UNIT_POS>{}));
-                    else if (lm == LASSO_UNIT_NEG) run_pass(accumulate_unit(LassoMode<LASSO_UNIT_NEG>{}));
-                    else run_pass(accumulate_general);
+                    // (make_dict_lasso_consts normalises the atoms: every iterate takes the packed compare-free solver; the sums
+                    //  are in its beta space and are scaled back below)
+                    if (lk.g01 >= 0.f) run_pass(accumulate_unit(LassoMode<LASSO_UNIT_POS>{}));
+                    else run_pass(accumulate_unit(LassoMode<LASSO_UNIT_NEG>{}));
                     __syncthreads();
                     if (threadIdx.x < 10) {
                         sh->part[pbuf][threadIdx.x] = threadIdx.x < 9 ? (long long)sh->acc64[threadIdx.x] : 0ll;
@@ -439,6 +426,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                     cluster_total10(sh, pbuf, S, 1.0 / (double)FIX_DL);
                     pbuf ^= 1;
                     if (threadIdx.x == 0) {
+                        { double sc[2]; dict_scales(sh->D, sc); dict_scale_sums(sh->tot, sc); }
                         const double* t = sh->tot;
                         // Mairal et al. 2010 Alg. 2, one block-coordinate sweep; D rows = atoms.
                         double FD[6];
@@ -465,7 +453,7 @@ __global__ void __launch_bounds__(NT, 2) tile_pipeline_kernel(PipeArgs a) {
                         const double tol = phase == 0 ? DL_SAMPLE_TOL : DL_FULL_TOL;
                         if (a.dl_anderson > 0 && rn2 < tol * tol) sh->dl_stop = 1;      // this step is still applied, then the phase ends
                         aa_step(sh->aa, a.dl_anderson, sh->D, FD);
-                        make_lasso_consts(sh->D, a.dl_lambda, sh->lk);
+                        make_dict_lasso_consts(sh->D, a.dl_lambda, sh->lk);
                     }
                     __syncthreads();
                     if (sh->dl_stop) break;

@@ -71,6 +71,21 @@ struct __align__(16) ConcConsts {
     int pad;
 };
 
+// Vahadane (vahadane_stain_extractor.py:19-43; the dictionary iteration of the fused kernel, one launch per pass)
+struct __align__(16) DictState {
+    double D[6];                  // dictionary, rows = atoms
+    unsigned long long sums[10];  // fixed-point (FIX_DL) sums of the running pass: a a^T (3), x a_0 (3), x a_1 (3)
+    AAState aa;                   // Anderson history of the fixed-point iteration
+    int it, n_it;                 // full passes done / allowed
+    int pad[2];
+};
+struct __align__(16) DictConsts {
+    LassoK lk;                    // 13 floats
+    int lm;                       // LASSO_GENERAL / LASSO_UNIT_POS / LASSO_UNIT_NEG
+    int mode;                     // 0 = the tile takes part in the next pass, 1 = skip (converged, flagged, fallback)
+    int pad;
+};
+
 // ------------------------------------------------------------------------------------------------ lookups
 // {od, gamma} pair table at an absolute 64 KB-aligned shared address (one PRMT = the LDS.64 address).
 template <class F>
@@ -94,6 +109,18 @@ __device__ __forceinline__ void for_each_pair_od_abs(const OdAbs& t, const uint3
           f2(od_lookup(t, a, 0u, 2), od_lookup(t, b, 0u, 1)));
         f(4 * q + 2, f2(od_lookup(t, b, 0u, 2), od_lookup(t, c, 0u, 1)), f2(od_lookup(t, b, 0u, 3), od_lookup(t, c, 0u, 2)),
           f2(od_lookup(t, c, 0u, 0), od_lookup(t, c, 0u, 3)));
+    }
+}
+// od-only table, one pixel at a time (general LASSO form of the Vahadane passes).
+template <class F>
+__device__ __forceinline__ void for_each_px_od_abs(const OdAbs& t, const uint32_t (&w)[12], F&& f) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        f(4 * q + 0, od_lookup(t, a, 0u, 0), od_lookup(t, a, 0u, 1), od_lookup(t, a, 0u, 2));
+        f(4 * q + 1, od_lookup(t, a, 0u, 3), od_lookup(t, b, 0u, 0), od_lookup(t, b, 0u, 1));
+        f(4 * q + 2, od_lookup(t, b, 0u, 2), od_lookup(t, b, 0u, 3), od_lookup(t, c, 0u, 0));
+        f(4 * q + 3, od_lookup(t, c, 0u, 1), od_lookup(t, c, 0u, 2), od_lookup(t, c, 0u, 3));
     }
 }
 // Plain 256-entry {od, gamma} table in shared memory for the per-tile kernels (1/16 of the pixels: bank conflicts are
@@ -128,7 +155,7 @@ struct WarpScratch {
 // and are processed 32 at a time with all lanes busy) and two staging buffers for the keys that go to the tile's global
 // key lists (flushed 32 at a time: one atomic and one coalesced 128-byte store per 32 keys).
 template <class Op>
-__global__ void __launch_bounds__(RR_GT + 32, 1) ring_reduce_kernel(RingGeom g, typename Op::Params p, int chunks_per_tile, long long total_chunks) {
+__global__ void __launch_bounds__(RR_GT + 32, 1) ring_reduce_kernel(RingGeom g, typename Op::Params p, int chunks_per_tile, int unit_chunks) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t base = smem_u32(smem);
     const uint32_t tab_addr = (base + RR_HEAD_BYTES + 0xFFFFu) & ~0xFFFFu;
@@ -143,14 +170,22 @@ __global__ void __launch_bounds__(RR_GT + 32, 1) ring_reduce_kernel(RingGeom g, 
         return s < n_front ? smem + RR_HEAD_BYTES + (size_t)s * RR_CHUNK : tab_ptr + OD_REP_BYTES + (size_t)(s - n_front) * RR_CHUNK;
     };
     const size_t tile_bytes = (size_t)g.npx * 3;
-    const long long c_begin = total_chunks * blockIdx.x / gridDim.x, c_end = total_chunks * (blockIdx.x + 1) / gridDim.x;
+    // The CTA's share: a contiguous range of UNITS (unit_chunks consecutive chunks of one tile; 1 for the Macenko passes, the
+    // unit of for_each_unit for the Vahadane passes, whose fp32 partial sums are defined per unit), as a range of chunks.
+    const int upt = (chunks_per_tile + unit_chunks - 1) / unit_chunks;
+    const long long total_units = (long long)upt * g.B;
+    auto unit_chunk = [&](long long u) -> long long { return u >= total_units ? (long long)chunks_per_tile * g.B : (u / upt) * chunks_per_tile + (u % upt) * unit_chunks; };
+    const long long c_begin = unit_chunk(total_units * blockIdx.x / gridDim.x), c_end = unit_chunk(total_units * (blockIdx.x + 1) / gridDim.x);
     const int n_local = (int)(c_end - c_begin);
-    auto chunk_geom = [&](long long c, int& tile, size_t& off, uint32_t& bytes) {
-        tile = (int)(c / chunks_per_tile);
-        off = (size_t)(c % chunks_per_tile) * RR_CHUNK;
-        const size_t rem = tile_bytes - off;
-        bytes = (uint32_t)(rem < (size_t)RR_CHUNK ? rem : (size_t)RR_CHUNK);
-    };
+    {
+        // nothing to do in this CTA's range (e.g. a Vahadane pass after every tile has converged): leave before the table fill
+        int any = 0;
+        if (n_local > 0) {
+            const int t_first = (int)(c_begin / chunks_per_tile), t_last = (int)((c_end - 1) / chunks_per_tile);
+            for (int t = t_first + (int)threadIdx.x; t <= t_last; t += RR_GT + 32) any |= Op::tile_active(p, t) ? 1 : 0;
+        }
+        if (!__syncthreads_or(any)) return;
+    }
     if (threadIdx.x == RR_GT) {
         for (int s = 0; s < RR_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], RR_GT / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -159,16 +194,28 @@ __global__ void __launch_bounds__(RR_GT + 32, 1) ring_reduce_kernel(RingGeom g, 
     Op::fill_table(tab_ptr, p, (int)threadIdx.x, RR_GT + 32);
     __syncthreads();
 
+    // Producer and consumers walk the same list of runs (chunks of one tile inside the CTA's range) and both skip the tiles
+    // the Op declares inactive (flagged / fallback / converged tiles: their bytes never leave HBM); n counts loaded chunks.
     if (threadIdx.x >= RR_GT) {
         // ------------------------------------------------------------------ producer warp (one elected lane)
         if (threadIdx.x == RR_GT) {
-            for (int i = 0; i < n_local; ++i) {
-                const int s = i % RR_STAGES;
-                if (i >= RR_STAGES) mbar_wait(&done[s], (uint32_t)(((i / RR_STAGES) - 1) & 1));     // the slot's previous chunk has been consumed
-                int tile; size_t off; uint32_t bytes;
-                chunk_geom(c_begin + i, tile, off, bytes);
-                mbar_expect_tx(&full[s], bytes);
-                bulk_load(stage_ptr(s), g.in + (size_t)tile * tile_bytes + off, bytes, &full[s]);
+            int n = 0;
+            for (int i = 0; i < n_local;) {
+                const int tile = (int)((c_begin + i) / chunks_per_tile);
+                const int first_in_tile = (int)((c_begin + i) - (long long)tile * chunks_per_tile);
+                int run = chunks_per_tile - first_in_tile;
+                if (run > n_local - i) run = n_local - i;
+                i += run;
+                if (!Op::tile_active(p, tile)) continue;
+                for (int j = 0; j < run; ++j, ++n) {
+                    const int s = n % RR_STAGES;
+                    if (n >= RR_STAGES) mbar_wait(&done[s], (uint32_t)(((n / RR_STAGES) - 1) & 1));     // the slot's previous chunk has been consumed
+                    const size_t off = (size_t)(first_in_tile + j) * RR_CHUNK;
+                    const size_t rem = tile_bytes - off;
+                    const uint32_t bytes = (uint32_t)(rem < (size_t)RR_CHUNK ? rem : (size_t)RR_CHUNK);
+                    mbar_expect_tx(&full[s], bytes);
+                    bulk_load(stage_ptr(s), g.in + (size_t)tile * tile_bytes + off, bytes, &full[s]);
+                }
             }
         }
         return;
@@ -178,21 +225,27 @@ __global__ void __launch_bounds__(RR_GT + 32, 1) ring_reduce_kernel(RingGeom g, 
     WarpScratch wq{queues + (threadIdx.x >> 5) * RR_WARP_WORDS, 0u, 0u, 0u};
     typename Op::Acc acc;
     Op::acc_init(acc);
-    int i = 0;
-    while (i < n_local) {
+    int n = 0;
+    for (int i = 0; i < n_local;) {
         const int tile = (int)((c_begin + i) / chunks_per_tile);
         const int first_in_tile = (int)((c_begin + i) - (long long)tile * chunks_per_tile);
         int run = chunks_per_tile - first_in_tile;
         if (run > n_local - i) run = n_local - i;
+        i += run;
+        if (!Op::tile_active(p, tile)) continue;
         const typename Op::Consts k = Op::load_consts(p, tile);
-        for (int j = 0; j < run; ++j, ++i) {
-            const int s = i % RR_STAGES;
-            const size_t off = (size_t)(first_in_tile + j) * RR_CHUNK;
+        int in_unit = first_in_tile % unit_chunks;      // (CTA ranges start at unit boundaries: 0 except for unit_chunks == 1)
+        for (int j = 0; j < run; ++j, ++n) {
+            const int s = n % RR_STAGES;
+            const int ci = first_in_tile + j;
+            const size_t off = (size_t)ci * RR_CHUNK;
             const size_t rem = tile_bytes - off;
             const uint32_t bytes = (uint32_t)(rem < (size_t)RR_CHUNK ? rem : (size_t)RR_CHUNK);
             unsigned char* buf = stage_ptr(s);
-            mbar_wait(&full[s], (uint32_t)((i / RR_STAGES) & 1));
-            Op::process(k, p, tab, buf, threadIdx.x * 48u < bytes, (unsigned)(off / 3), wq, acc, tile);
+            mbar_wait(&full[s], (uint32_t)((n / RR_STAGES) & 1));
+            if (++in_unit == unit_chunks || ci + 1 == chunks_per_tile) in_unit = 0;
+            const bool unit_end = in_unit == 0;
+            Op::process(k, p, tab, buf, threadIdx.x * 48u < bytes, (unsigned)(off / 3), wq, acc, tile, unit_end);
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&done[s]);
         }
@@ -201,7 +254,7 @@ __global__ void __launch_bounds__(RR_GT + 32, 1) ring_reduce_kernel(RingGeom g, 
 }
 
 template <class Op>
-static int launch_ring_reduce(const RingGeom& g, const typename Op::Params& p, int num_sms, cudaStream_t stream) {
+static int launch_ring_reduce(const RingGeom& g, const typename Op::Params& p, int num_sms, cudaStream_t stream, int unit_chunks = 1) {
     static_assert(OD_REP_BYTES + RR_STAGES * RR_CHUNK + RR_HEAD_BYTES + 1024 <= RING_SMEM_BYTES, "ring does not fit");
     static DeviceOnce once;
     {
@@ -210,10 +263,10 @@ static int launch_ring_reduce(const RingGeom& g, const typename Op::Params& p, i
     }
     const size_t tile_bytes = (size_t)g.npx * 3;
     const int cpt = (int)((tile_bytes + RR_CHUNK - 1) / RR_CHUNK);
-    const long long total = (long long)cpt * g.B;
+    const long long total = (long long)((cpt + unit_chunks - 1) / unit_chunks) * g.B;
     int grid = num_sms;
     if ((long long)grid > total) grid = (int)total;
-    ring_reduce_kernel<Op><<<grid, RR_GT + 32, RING_SMEM_BYTES, stream>>>(g, p, cpt, total);
+    ring_reduce_kernel<Op><<<grid, RR_GT + 32, RING_SMEM_BYTES, stream>>>(g, p, cpt, unit_chunks);
     return (int)cudaGetLastError();
 }
 
@@ -235,13 +288,13 @@ __device__ __forceinline__ uint32_t group_px(const unsigned char* grp, int i) {
     const uint32_t lo = gw[wi], hi = gw[wi < 11 ? wi + 1 : 11];
     return __funnelshift_r(lo, hi, (o & 3) * 8) & 0x00FFFFFFu;
 }
-// Pushes the packed RGB of the pixels flagged in `bits` (16-bit mask over this lane's group at grp) into the warp's
-// queue and processes 32 queued pixels with proc(rgb) whenever that many are ready; all lanes call.
-// Two phases: a warp prefix sum of the per-lane counts gives every lane its slots, then each lane writes its own pixels
-// (a short divergent loop with no votes); only when the warp's pixels do not fit the queue at once (rare) do they go in
-// round by round, one per lane, with a drain between rounds.
+// Pushes the packed RGB of the pixels flagged in `bits` (16-bit mask over this lane's group, the warp's 32 groups start
+// at wgrp) into the warp's queue and processes 32 queued pixels with proc(rgb) whenever that many are ready; all lanes call.
+// A warp prefix sum of the per-lane counts gives every lane its slots; each lane drops one small descriptor (lane, pixel)
+// per flagged pixel -- a short divergent loop of a few instructions --, then the warp expands the descriptors to RGB words
+// with all lanes busy.  Only when the warp's pixels do not fit the queue at once (rare) do they go in round by round.
 template <class P>
-__device__ __forceinline__ void rq_push_flagged(WarpScratch& ws, unsigned bits, const unsigned char* grp, P&& proc) {
+__device__ __forceinline__ void rq_push_flagged(WarpScratch& ws, unsigned bits, const unsigned char* wgrp, P&& proc) {
     const unsigned lane = threadIdx.x & 31u;
     if (!__any_sync(0xffffffffu, bits != 0u)) return;
     const unsigned c = __popc(bits);
@@ -253,11 +306,21 @@ __device__ __forceinline__ void rq_push_flagged(WarpScratch& ws, unsigned bits, 
     }
     const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
     if (ws.qlen + total <= (unsigned)RQ_CAP) {
-        unsigned dst = ws.qlen + incl - c;
+        unsigned* q = ws.w + ws.qlen;
+        unsigned dst = incl - c;
+        const unsigned tag = lane << 4;
         while (bits != 0u) {
-            const int i = __ffs(bits) - 1;
+            q[dst++] = tag | (unsigned)(__ffs(bits) - 1);
             bits &= bits - 1u;
-            ws.w[dst++] = group_px(grp, i);
+        }
+        __syncwarp();
+#pragma unroll
+        for (unsigned r = 0; r < 2; ++r) {
+            const unsigned e = r * 32u + lane;
+            if (e < total) {
+                const unsigned d = q[e];
+                q[e] = group_px(wgrp + (d >> 4) * 48u, (int)(d & 15u));     // each lane rewrites the slot it read
+            }
         }
         ws.qlen += total;
         while (ws.qlen >= 32u) {
@@ -271,7 +334,7 @@ __device__ __forceinline__ void rq_push_flagged(WarpScratch& ws, unsigned bits, 
     unsigned m;
     while ((m = __ballot_sync(0xffffffffu, bits != 0u)) != 0u) {
         if (bits != 0u) {
-            ws.w[ws.qlen + __popc(m & ((1u << lane) - 1u))] = group_px(grp, __ffs(bits) - 1);
+            ws.w[ws.qlen + __popc(m & ((1u << lane) - 1u))] = group_px(wgrp + lane * 48u, __ffs(bits) - 1);
             bits &= bits - 1u;
         }
         ws.qlen += __popc(m);                             // < 32 on entry: at most 63 entries
@@ -336,6 +399,8 @@ struct StreamParams {
     const AngleConsts* aconsts;
     const ConcConsts* cconsts;
     unsigned* lists;              // [B][2][SLIST_CAP]
+    struct DictState* dstate;     // Vahadane: per-tile dictionary, sums of the current pass, Anderson history
+    const struct DictConsts* dconsts;
     unsigned short* mask;         // [B][groups]: 16 tissue bits per 16-pixel group, written by pass 1, read by pass 3
     int groups;                   // 16-pixel groups per tile
     const float* od;
@@ -376,8 +441,9 @@ struct MomentOp {
             : "+f"(f[0]), "+f"(f[1]), "+f"(f[2]), "+f"(f[3]), "+f"(f[4]), "+f"(f[5]), "+f"(f[6]), "+f"(f[7]), "+f"(f[8]), "+r"(mbits)
             : "f"(y), "f"(bound), "f"(o0), "f"(o1), "f"(o2), "r"(bit));
     }
+    __device__ static bool tile_active(const Params&, int) { return true; }
     __device__ static void process(const Consts&, const Params& p, const OdAbs tab, const unsigned char* buf, bool active, unsigned px0, WarpScratch&,
-                                   Acc& acc, int tile) {
+                                   Acc& acc, int tile, bool) {
         if (!active) return;
         uint32_t w[12];
         load_group_smem(buf, true, w);
@@ -390,7 +456,7 @@ struct MomentOp {
             accum_mask(tissue_y(yc, r.y, g.y, b.y), yc.bound, r.x, g.x, b.x, f, mbits, 1u << i);
         });
         acc.cnt += __popc(mbits);
-        p.mask[(size_t)tile * p.groups + (px0 >> 4) + threadIdx.x] = (unsigned short)mbits;      // pass 3 does not recompute the mask
+        p.mask[(unsigned)tile * (unsigned)p.groups + (px0 >> 4) + threadIdx.x] = (unsigned short)mbits;      // pass 3 does not recompute the mask
 #pragma unroll
         for (int i = 0; i < 9; ++i) acc.s[i] += to_fix(f[i], FIX_MOMENT);
     }
@@ -440,11 +506,12 @@ struct AngleOp {
         stage_append(ws.w + RQ_CAP, ws.n0, has && key >= k.ka0 && key < k.kb0, key, &len[0], list0);
         stage_append(ws.w + 2 * RQ_CAP, ws.n1, has && key >= k.ka1 && key < k.kb1, key, &len[1], list0 + SLIST_CAP);
     }
+    __device__ static bool tile_active(const Params& p, int tile) { return p.aconsts[tile].mode == 0; }
     __device__ static void process(const Consts& k, const Params& p, const OdAbs tab, const unsigned char* buf, bool active, unsigned px0,
-                                   WarpScratch& ws, Acc& acc, int tile) {
+                                   WarpScratch& ws, Acc& acc, int tile, bool) {
         if (k.mode != 0) return;                        // warp-uniform (per-tile constant)
         unsigned mbits = 0;
-        if (active) mbits = p.mask[(size_t)tile * p.groups + (px0 >> 4) + threadIdx.x];     // issued first: the group's arithmetic hides it
+        if (active) mbits = p.mask[(unsigned)tile * (unsigned)p.groups + (px0 >> 4) + threadIdx.x];     // issued first: the group's arithmetic hides it (< 2^26 groups per round)
         uint32_t w[12];
         load_group_smem(buf, active, w);
         const float2 a0 = dup(k.n1[0]), a1 = dup(k.n1[1]), a2 = dup(k.n1[2]);
@@ -458,7 +525,7 @@ struct AngleOp {
             fastbits |= set_gt(fminf(h1.y, h2.y), margin) & (2u << i);
         });
         acc.below1 += __popc(mbits & fastbits);
-        rq_push_flagged(ws, mbits & ~fastbits, buf + threadIdx.x * 48u, [&](bool has, uint32_t rgb) { exact(k, p, tab, ws, acc, tile, has, rgb); });
+        rq_push_flagged(ws, mbits & ~fastbits, buf + (threadIdx.x & ~31u) * 48u, [&](bool has, uint32_t rgb) { exact(k, p, tab, ws, acc, tile, has, rgb); });
     }
     __device__ static void finish_run(const Consts& k, const Params& p, const OdAbs tab, WarpScratch& ws, Acc& acc, int tile) {
         if (k.mode == 0) {
@@ -556,10 +623,11 @@ struct ConcOp {
                 : "+r"(slow) : "f"(x0.y), "f"(x1.y), "f"(half0), "f"(half1), "r"(2u << i));
         });
         if (active) { acc.n0 += n0; acc.n1 += n1; } else slow = 0;
-        rq_push_flagged(ws, slow, buf + threadIdx.x * 48u, [&](bool has, uint32_t rgb) { exact<LM>(k, p, tab, ws, acc, tile, has, rgb); });
+        rq_push_flagged(ws, slow, buf + (threadIdx.x & ~31u) * 48u, [&](bool has, uint32_t rgb) { exact<LM>(k, p, tab, ws, acc, tile, has, rgb); });
     }
+    __device__ static bool tile_active(const Params& p, int tile) { return p.cconsts[tile].mode == 0; }
     __device__ static void process(const Consts& k, const Params& p, const OdAbs tab, const unsigned char* buf, bool active, unsigned,
-                                   WarpScratch& ws, Acc& acc, int tile) {
+                                   WarpScratch& ws, Acc& acc, int tile, bool) {
         if (k.mode != 0) return;
         if (k.lm == LASSO_UNIT_POS) body<LASSO_UNIT_POS>(k, p, tab, buf, active, ws, acc, tile);
         else body<LASSO_UNIT_NEG>(k, p, tab, buf, active, ws, acc, tile);
@@ -584,6 +652,112 @@ struct ConcOp {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ Vahadane passes
+// V0: tissue bits of every group (kept for all dictionary passes), tissue count of the tile and of its 1-in-16 sample.
+struct MaskOp {
+    using Consts = Empty;
+    using Params = StreamParams;
+    struct Acc { unsigned tissue, sample; };
+    static constexpr int kLaneShift = 2;
+    __device__ static void fill_table(unsigned char* tab, const Params& p, int tid, int n) {
+        for (int i = tid; i < 256 * 32; i += n)
+            *reinterpret_cast<float*>(tab + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = (float)p.gamma[i >> 5];
+    }
+    __device__ static Consts load_consts(const Params&, int) { return Empty{}; }
+    __device__ static bool tile_active(const Params&, int) { return true; }
+    __device__ static void acc_init(Acc& a) { a.tissue = a.sample = 0; }
+    __device__ static void process(const Consts&, const Params& p, const OdAbs tab, const unsigned char* buf, bool active, unsigned px0, WarpScratch&,
+                                   Acc& acc, int tile, bool) {
+        if (!active) return;
+        uint32_t w[12];
+        load_group_smem(buf, true, w);
+        const float2 cr = dup(p.ycoef[0]), cg = dup(p.ycoef[1]), cb = dup(p.ycoef[2]);
+        const float bound = p.ybound;
+        unsigned mbits = 0;
+        // Y = 871 g[R] + 2929 g[G] + 296 g[B]: integers below 2^24, exact in fp32 in any order -- two pixels per FFMA2
+        for_each_pair_od_abs(tab, w, [&](int i, float2 g0, float2 g1, float2 g2) {
+            const float2 y = __ffma2_rn(g2, cb, __ffma2_rn(g1, cg, __fmul2_rn(g0, cr)));
+            mbits |= set_lt(y.x, bound) & (1u << i);
+            mbits |= set_lt(y.y, bound) & (2u << i);
+        });
+        const int g = (int)(px0 >> 4) + (int)threadIdx.x;
+        p.mask[(unsigned)tile * (unsigned)p.groups + (unsigned)g] = (unsigned short)mbits;
+        const unsigned c = __popc(mbits);
+        acc.tissue += c;
+        if (is_sample_group(g, p.groups)) acc.sample += c;
+    }
+    __device__ static void finish_run(const Consts&, const Params& p, const OdAbs, WarpScratch&, Acc& acc, int tile) {
+        const unsigned t = warp_sum_u(acc.tissue), sm = warp_sum_u(acc.sample);
+        if ((threadIdx.x & 31) == 0) {
+            if (t) atomicAdd(&p.state[tile].mom[9], (unsigned long long)t);
+            if (sm) atomicAdd(&p.state[tile].mom[0], (unsigned long long)sm);
+        }
+        acc_init(acc);
+    }
+};
+
+// One full dictionary pass: sparse-code the tissue pixels under the tile's current dictionary, accumulate a a^T and x a^T.
+// The partial sums are the ones of the fused kernel, bit for bit: fp32 per thread over the groups of one UNIT (the ring
+// hands units to CTAs whole, and thread t of a chunk holds the group thread t of the fused kernel visits), reduced over
+// the warp by the same shuffle tree, then fixed point.
+struct DictOp {
+    using Consts = DictConsts;
+    using Params = StreamParams;
+    struct Acc { float2 f[9]; long long s[9]; };
+    static constexpr int kLaneShift = 2;
+    __device__ static void fill_table(unsigned char* tab, const Params& p, int tid, int n) {
+        for (int i = tid; i < 256 * 32; i += n)
+            *reinterpret_cast<float*>(tab + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = p.od[i >> 5];
+    }
+    __device__ static Consts load_consts(const Params& p, int tile) { return p.dconsts[tile]; }
+    __device__ static bool tile_active(const Params& p, int tile) { return p.dconsts[tile].mode == 0; }
+    __device__ static void acc_init(Acc& a) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { a.f[i] = make_float2(0.f, 0.f); a.s[i] = 0; }
+    }
+    template <int LM>
+    __device__ static __forceinline__ void add_unit(const LassoK& lk, const OdAbs tab, const uint32_t (&w)[12], uint32_t mbits, float2 (&f)[9]) {
+        for_each_pair_od_abs(tab, w, [&](int i, float2 o0, float2 o1, float2 o2) {
+            float2 c0, c1;
+            lasso2_unit_pair<LM>(lk, o0, o1, o2, c0, c1);
+            const bool ma = (mbits & (1u << i)) != 0, mb = (mbits & (2u << i)) != 0;
+            c0.x = ma ? c0.x : 0.f; c1.x = ma ? c1.x : 0.f;
+            c0.y = mb ? c0.y : 0.f; c1.y = mb ? c1.y : 0.f;
+            f[0] = __ffma2_rn(c0, c0, f[0]); f[1] = __ffma2_rn(c0, c1, f[1]); f[2] = __ffma2_rn(c1, c1, f[2]);
+            f[3] = __ffma2_rn(o0, c0, f[3]); f[4] = __ffma2_rn(o1, c0, f[4]); f[5] = __ffma2_rn(o2, c0, f[5]);
+            f[6] = __ffma2_rn(o0, c1, f[6]); f[7] = __ffma2_rn(o1, c1, f[7]); f[8] = __ffma2_rn(o2, c1, f[8]);
+        });
+    }
+    __device__ static void process(const Consts& k, const Params& p, const OdAbs tab, const unsigned char* buf, bool active, unsigned px0, WarpScratch&,
+                                   Acc& acc, int tile, bool unit_end) {
+        if (active) {
+            const uint32_t mbits = p.mask[(unsigned)tile * (unsigned)p.groups + (px0 >> 4) + threadIdx.x];
+            uint32_t w[12];
+            load_group_smem(buf, true, w);
+            if (k.lm == LASSO_UNIT_POS) add_unit<LASSO_UNIT_POS>(k.lk, tab, w, mbits, acc.f);
+            else add_unit<LASSO_UNIT_NEG>(k.lk, tab, w, mbits, acc.f);
+        }
+        if (unit_end) {                                  // warp-uniform
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                float v = acc.f[i].x + acc.f[i].y;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                acc.s[i] += to_fix(v, FIX_DL);            // (lane 0 holds the warp's sum)
+                acc.f[i] = make_float2(0.f, 0.f);
+            }
+        }
+    }
+    __device__ static void finish_run(const Consts&, const Params& p, const OdAbs, WarpScratch&, Acc& acc, int tile) {
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+                if (acc.s[i] != 0) atomicAdd(&p.dstate[tile].sums[i], (unsigned long long)acc.s[i]);
+        }
+        acc_init(acc);
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ per-tile kernels
 struct TileKernelArgs {
     PipeArgs a;
@@ -595,9 +769,10 @@ struct TileKernelArgs {
     int* fb_count;
 };
 struct TileShared {
-    PipeShared ps;
     float2 tab[256];
+    PipeShared ps;                // allocated without its fused-kernel-only tail (see PipeShared)
 };
+constexpr size_t TILE_SHARED_BYTES = offsetof(TileShared, ps) + offsetof(PipeShared, aa);
 
 __device__ __forceinline__ void fill_small_table(float2* tab, const Tables& t) {
     for (int i = threadIdx.x; i < 256; i += NT) tab[i] = make_float2(t.od[i], (float)t.gamma[i]);
@@ -732,6 +907,76 @@ __global__ void __launch_bounds__(NT) plan_angle_kernel(TileKernelArgs k) {
     }
 }
 
+// C0 of the fused kernel: concentration keys of the 1-in-16 sample under the tile's stain matrix (sh->lk) -> brackets and
+// float windows for pass 5.  Whole block calls; the hist buffer is free.
+__device__ __forceinline__ void plan_conc_block(const TileKernelArgs& k, int tile, TileShared* ts, PipeShared* sh) {
+    const PipeArgs& a = k.a;
+    TileState& st = k.state[tile];
+    const int npx = a.npx, G = npx / GROUP_PX;
+    const uint8_t* __restrict__ tin = a.in + (size_t)tile * npx * 3;
+    // ---- C0: concentration keys of the 1-in-16 sample
+    zero_hist(sh);
+    const LassoK lk = sh->lk;
+    unsigned c_lo, c_hi;
+    { double fr; percentile_index((unsigned)npx, a.conc_pct, c_lo, c_hi, fr); }
+    unsigned scnt = 0;
+    for_each_sample_group(tin, npx, 0, G, true, [&](auto, const uint32_t (&w)[12], int, int) {
+        scnt += GROUP_PX;
+        for_each_px_odg_small(ts->tab, w, [&](int, float2 r, float2 g, float2 b) {
+            float c0, c1;
+            lasso2(lk, r.x, g.x, b.x, c0, c1);
+            atomicAdd(&sh->hist[conc_key(c0) >> L2_BITS], 1u);
+            atomicAdd(&sh->hist[L1_BINS + (conc_key(c1) >> L2_BITS)], 1u);
+        });
+    });
+    scnt = warp_sum_u(scnt);
+    if ((threadIdx.x & 31) == 0 && scnt) atomicAdd(&sh->s_cnt, scnt);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned n_s = sh->s_cnt;
+        if (n_s >= 1024u) {
+            plan_bracket((unsigned)npx, n_s, c_lo, sh->q_rank[0], sh->q_rank[1], a.bracket_sigmas, a.bracket_pad);
+            sh->q_rank[2] = sh->q_rank[0]; sh->q_rank[3] = sh->q_rank[1];
+            for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
+            sh->s_ok = 1;
+        } else {
+            tile_to_fallback(k, tile);
+        }
+    }
+    __syncthreads();
+    if (!sh->s_ok) return;
+    select_ranks<L1_BINS>(sh, sh->hist, 1, sh->q_rank, 2, sh->q_bin, sh->q_rem);
+    select_ranks<L1_BINS>(sh, sh->hist + L1_BINS, 1, sh->q_rank + 2, 2, sh->q_bin + 2, sh->q_rem + 2);
+    if (threadIdx.x == 0) {
+        ConcConsts c;
+        c.lk = sh->lk;
+        unsigned ka[2], kb[2];
+        float mid[2], half[2];
+        bool ok = true;
+        for (int j = 0; j < 2; ++j) {
+            ka[j] = sh->q_bin[2 * j] << L2_BITS;
+            kb[j] = (sh->q_bin[2 * j + 1] + 1u) << L2_BITS;
+            // a bracket that touches zero (a stain absent from >= 99 % of the tile) or the top of the key range: robust path
+            ok = ok && ka[j] >= 64u && kb[j] + 64u < (1u << KEY_BITS);
+            // concentrations outside [lo, hi] (64 key units of slack around the bracket) need no exact key
+            const double lo = ok ? (double)float_below(conc_from_key(ka[j] - 64u)) : 0.0;
+            const double hi = ok ? (double)float_above(conc_from_key(kb[j] + 64u)) : 1.0;
+            mid[j] = (float)(0.5 * (lo + hi));
+            half[j] = float_above(fmax(hi - (double)mid[j], (double)mid[j] - lo) * (1.0 + 1e-6));
+            ok = ok && lo > 0.0;
+        }
+        if (!ok) tile_to_fallback(k, tile);
+        else {
+            c.mid0 = mid[0]; c.half0 = half[0]; c.mid1 = mid[1]; c.half1 = half[1];
+            c.ka0 = ka[0]; c.kb0 = kb[0]; c.ka1 = ka[1]; c.kb1 = kb[1];
+            c.lm = lasso_mode_of(c.lk.rg00, c.lk.rg11, c.lk.g01);
+            c.mode = 0; c.pad = 0;
+            k.cconsts[tile] = c;
+            st.cbrk[0] = ka[0]; st.cbrk[1] = kb[0]; st.cbrk[2] = ka[1]; st.cbrk[3] = kb[1];
+        }
+    }
+}
+
 // 4: exact angular percentiles from the bracket lists -> stain matrix (macenko_stain_extractor.py:29-44); then the sample of
 // the concentrations -> brackets (C0 of the fused kernel).
 __global__ void __launch_bounds__(NT) select_angle_kernel(TileKernelArgs k) {
@@ -813,67 +1058,7 @@ __global__ void __launch_bounds__(NT) select_angle_kernel(TileKernelArgs k) {
     }
     __syncthreads();
     if (sh->flags != 0 || a.mode < PIPE_FIT) return;
-    // ---- C0: concentration keys of the 1-in-16 sample
-    zero_hist(sh);
-    const LassoK lk = sh->lk;
-    unsigned c_lo, c_hi;
-    { double fr; percentile_index((unsigned)npx, a.conc_pct, c_lo, c_hi, fr); }
-    unsigned scnt = 0;
-    for_each_sample_group(tin, npx, 0, G, true, [&](auto, const uint32_t (&w)[12], int, int) {
-        scnt += GROUP_PX;
-        for_each_px_odg_small(ts->tab, w, [&](int, float2 r, float2 g, float2 b) {
-            float c0, c1;
-            lasso2(lk, r.x, g.x, b.x, c0, c1);
-            atomicAdd(&sh->hist[conc_key(c0) >> L2_BITS], 1u);
-            atomicAdd(&sh->hist[L1_BINS + (conc_key(c1) >> L2_BITS)], 1u);
-        });
-    });
-    scnt = warp_sum_u(scnt);
-    if ((threadIdx.x & 31) == 0 && scnt) atomicAdd(&sh->s_cnt, scnt);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned n_s = sh->s_cnt;
-        if (n_s >= 1024u) {
-            plan_bracket((unsigned)npx, n_s, c_lo, sh->q_rank[0], sh->q_rank[1], a.bracket_sigmas, a.bracket_pad);
-            sh->q_rank[2] = sh->q_rank[0]; sh->q_rank[3] = sh->q_rank[1];
-            for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
-            sh->s_ok = 1;
-        } else {
-            tile_to_fallback(k, tile);
-        }
-    }
-    __syncthreads();
-    if (!sh->s_ok) return;
-    select_ranks<L1_BINS>(sh, sh->hist, 1, sh->q_rank, 2, sh->q_bin, sh->q_rem);
-    select_ranks<L1_BINS>(sh, sh->hist + L1_BINS, 1, sh->q_rank + 2, 2, sh->q_bin + 2, sh->q_rem + 2);
-    if (threadIdx.x == 0) {
-        ConcConsts c;
-        c.lk = sh->lk;
-        unsigned ka[2], kb[2];
-        float mid[2], half[2];
-        bool ok = true;
-        for (int j = 0; j < 2; ++j) {
-            ka[j] = sh->q_bin[2 * j] << L2_BITS;
-            kb[j] = (sh->q_bin[2 * j + 1] + 1u) << L2_BITS;
-            // a bracket that touches zero (a stain absent from >= 99 % of the tile) or the top of the key range: robust path
-            ok = ok && ka[j] >= 64u && kb[j] + 64u < (1u << KEY_BITS);
-            // concentrations outside [lo, hi] (64 key units of slack around the bracket) need no exact key
-            const double lo = ok ? (double)float_below(conc_from_key(ka[j] - 64u)) : 0.0;
-            const double hi = ok ? (double)float_above(conc_from_key(kb[j] + 64u)) : 1.0;
-            mid[j] = (float)(0.5 * (lo + hi));
-            half[j] = float_above(fmax(hi - (double)mid[j], (double)mid[j] - lo) * (1.0 + 1e-6));
-            ok = ok && lo > 0.0;
-        }
-        if (!ok) tile_to_fallback(k, tile);
-        else {
-            c.mid0 = mid[0]; c.half0 = half[0]; c.mid1 = mid[1]; c.half1 = half[1];
-            c.ka0 = ka[0]; c.kb0 = kb[0]; c.ka1 = ka[1]; c.kb1 = kb[1];
-            c.lm = lasso_mode_of(c.lk.rg00, c.lk.rg11, c.lk.g01);
-            c.mode = 0; c.pad = 0;
-            k.cconsts[tile] = c;
-            st.cbrk[0] = ka[0]; st.cbrk[1] = kb[0]; st.cbrk[2] = ka[1]; st.cbrk[3] = kb[1];
-        }
-    }
+    plan_conc_block(k, tile, ts, sh);
 }
 
 // 6: exact 99th percentiles of the two concentrations (normalizer.py:36,47) from the bracket lists.
@@ -925,11 +1110,265 @@ __global__ void __launch_bounds__(NT) select_conc_kernel(TileKernelArgs k) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ Vahadane per-tile kernels
+// One block-coordinate sweep of the dictionary update (Mairal et al. 2010, Alg. 2) from the sums of a pass -- the
+// thread-0 code of the fused kernel, operation for operation.  t = (A00, A01, A11, B[:,0] (3), B[:,1] (3)); D rows = atoms.
+__device__ inline void dl_sweep(const double* t, const double* D, double* FD) {
+    for (int q = 0; q < 6; ++q) FD[q] = D[q];
+    const double Aj[2][2] = {{t[0], t[1]}, {t[1], t[2]}};
+    for (int j = 0; j < 2; ++j) {
+        if (Aj[j][j] > 1e-12) {
+            double u[3], nrm = 0.0;
+            for (int q = 0; q < 3; ++q) {
+                const double Da = FD[q] * Aj[0][j] + FD[3 + q] * Aj[1][j];
+                u[q] = (t[3 + 3 * j + q] - Da) / Aj[j][j] + FD[3 * j + q];
+                u[q] = u[q] > 0.0 ? u[q] : 0.0;
+                nrm += u[q] * u[q];
+            }
+            nrm = sqrt(nrm);
+            const double sc = 1.0 / (nrm > 1.0 ? nrm : 1.0);
+            for (int q = 0; q < 3; ++q) FD[3 * j + q] = u[q] * sc;
+        }
+    }
+}
+// vahadane_stain_extractor.py:38-43: H first, rows normalised.  Returns false for a non-finite matrix.
+__device__ inline bool dl_finish_matrix(const double* D, double* M) {
+    const bool swap = D[0] < D[3];
+    const double* h = swap ? D + 3 : D;
+    const double* e = swap ? D : D + 3;
+    const double nh = sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]), ne = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+    bool ok = true;
+    for (int q = 0; q < 3; ++q) { M[q] = h[q] / nh; M[3 + q] = e[q] / ne; ok = ok && isfinite(M[q]) && isfinite(M[3 + q]); }
+    return ok;
+}
+struct DictKernelArgs {
+    TileKernelArgs k;
+    DictState* dstate;
+    DictConsts* dconsts;
+    const unsigned short* mask;
+};
+// Thread 0: the dictionary iteration of a tile has ended -> stain matrix, outputs; the tile leaves the dictionary passes.
+__device__ inline void dl_tile_done(const DictKernelArgs& d, int tile, const double* D) {
+    const TileKernelArgs& k = d.k;
+    d.dconsts[tile].mode = 1;
+    double M[6];
+    if (!dl_finish_matrix(D, M)) { tile_flagged(k, tile, SB_STATUS_DEGENERATE); return; }
+    for (int q = 0; q < 6; ++q) { k.state[tile].Msrc[q] = M[q]; if (k.a.M_out) k.a.M_out[(size_t)tile * 6 + q] = M[q]; }
+    if (k.a.mode < PIPE_FIT && k.a.status) k.a.status[tile] = 0;
+}
+
+// Warm start of the dictionary on the 1-in-16 sample (phase 0 of the fused kernel): the sample passes of a tile need no
+// other tile, so ONE launch runs them all, tile per CTA, to the residual DL_SAMPLE_TOL.  Most of a tile's time here is
+// the serial fp64 dictionary update + Anderson step between passes, so the CTAs are small (128 threads, eight per SM):
+// what overlaps one tile's serial step is the other tiles' passes.  The partial sums are those of the fused kernel bit
+// for bit: fp32 per lane over one warp step (32 consecutive sample blocks), shuffle tree, fixed point.
+constexpr int DLS_NT = 128;
+struct __align__(16) DlSampleShared {
+    float2 tab[256];
+    long long red[DLS_NT / 32][10];
+    double tot[10];
+    double D[6];
+    LassoK lk;
+    AAState aa;
+    int dl_stop, flags;
+};
+__global__ void __launch_bounds__(DLS_NT, 8) dl_sample_kernel(DictKernelArgs d) {
+    __shared__ DlSampleShared shm;
+    DlSampleShared* sh = &shm;
+    const TileKernelArgs& k = d.k;
+    const PipeArgs& a = k.a;
+    const int tile = blockIdx.x;
+    const int npx = a.npx, G = npx / GROUP_PX;
+    const uint8_t* __restrict__ tin = a.in + (size_t)tile * npx * 3;
+    TileState& st = k.state[tile];
+    DictState& ds = d.dstate[tile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 256; i += DLS_NT) sh->tab[i] = make_float2(a.tab.od[i], (float)a.tab.gamma[i]);
+    if (threadIdx.x == 0) {
+        const unsigned n_tissue = (unsigned)st.mom[9];
+        st.n_tissue = n_tissue;
+        sh->flags = 0;
+        d.dconsts[tile].mode = 1;
+        k.aconsts[tile].mode = 1;
+        k.cconsts[tile].mode = 1;
+        if (n_tissue < 1u) { sh->flags = SB_STATUS_EMPTY_MASK; tile_flagged(k, tile, SB_STATUS_EMPTY_MASK); }
+        const double r0[3] = {0.65, 0.70, 0.29}, r1[3] = {0.07, 0.99, 0.11};
+        const double n0 = sqrt(r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]), n1 = sqrt(r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
+        for (int q = 0; q < 3; ++q) { sh->D[q] = r0[q] / n0; sh->D[3 + q] = r1[q] / n1; }
+        make_dict_lasso_consts(sh->D, a.dl_lambda, sh->lk);
+        aa_reset(sh->aa);
+        sh->dl_stop = 0;
+    }
+    __syncthreads();
+    if (sh->flags != 0) return;
+    const bool use_sample = a.dl_sample_iters > 0 && (double)st.mom[0] >= 1024.0;
+    const unsigned short* mrow = d.mask + (size_t)tile * G;
+    const int n_blk = G / SAMPLE_STRIDE;                 // sample blocks of the tile (npx is a multiple of 16)
+    if (use_sample) {
+        for (int it = 0; it < a.dl_sample_iters; ++it) {
+            const LassoK lk = sh->lk;
+            const int lm = lk.g01 >= 0.f ? LASSO_UNIT_POS : LASSO_UNIT_NEG;
+            if (lane < 10) sh->red[warp][lane] = 0;
+            __syncwarp();
+            // warp step: 32 consecutive sample blocks, one per lane (the same 32 blocks, on the same lanes, as in the fused kernel)
+            for (int j0 = (int)(threadIdx.x & ~31u); j0 < n_blk; j0 += DLS_NT) {
+                const int j = j0 + lane;
+                float2 f[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) f[i] = make_float2(0.f, 0.f);
+                if (j < n_blk) {
+                    const int g = sample_group_of_block(j);
+                    uint32_t w[12];
+                    int nvalid;
+                    load_group<true>(tin, npx, g, true, w, nvalid);
+                    const uint32_t mbits = mrow[g];
+                    const float2* tb = sh->tab;
+                    {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {             // same pixel pairing as for_each_pair_od
+                            const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
+                            const float2 oa[3] = {f2(tb[wa & 255u].x, tb[wa >> 24].x), f2(tb[(wa >> 8) & 255u].x, tb[wb & 255u].x),
+                                                  f2(tb[(wa >> 16) & 255u].x, tb[(wb >> 8) & 255u].x)};
+                            const float2 ob[3] = {f2(tb[(wb >> 16) & 255u].x, tb[(wc >> 8) & 255u].x), f2(tb[wb >> 24].x, tb[(wc >> 16) & 255u].x),
+                                                  f2(tb[wc & 255u].x, tb[wc >> 24].x)};
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const float2 o0 = h ? ob[0] : oa[0], o1 = h ? ob[1] : oa[1], o2 = h ? ob[2] : oa[2];
+                                const int i = 4 * q + 2 * h;
+                                float2 c0, c1;
+                                if (lm == LASSO_UNIT_POS) lasso2_unit_pair<LASSO_UNIT_POS>(lk, o0, o1, o2, c0, c1);
+                                else lasso2_unit_pair<LASSO_UNIT_NEG>(lk, o0, o1, o2, c0, c1);
+                                const bool ma = (mbits & (1u << i)) != 0, mb = (mbits & (2u << i)) != 0;
+                                c0.x = ma ? c0.x : 0.f; c1.x = ma ? c1.x : 0.f;
+                                c0.y = mb ? c0.y : 0.f; c1.y = mb ? c1.y : 0.f;
+                                f[0] = __ffma2_rn(c0, c0, f[0]); f[1] = __ffma2_rn(c0, c1, f[1]); f[2] = __ffma2_rn(c1, c1, f[2]);
+                                f[3] = __ffma2_rn(o0, c0, f[3]); f[4] = __ffma2_rn(o1, c0, f[4]); f[5] = __ffma2_rn(o2, c0, f[5]);
+                                f[6] = __ffma2_rn(o0, c1, f[6]); f[7] = __ffma2_rn(o1, c1, f[7]); f[8] = __ffma2_rn(o2, c1, f[8]);
+                            }
+                        }
+                    }
+                }
+                // flush of the warp step: shuffle tree, fixed point, the warp's own accumulator row (no atomics: integer
+                // addition is associative, so this equals the fused kernel's one atomic per warp step)
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    float v = f[i].x + f[i].y;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                    if (lane == 0) sh->red[warp][i] += to_fix(v, FIX_DL);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 9) {
+                long long t = 0;
+                for (int wv = 0; wv < DLS_NT / 32; ++wv) t += sh->red[wv][threadIdx.x];
+                sh->tot[threadIdx.x] = (double)t * (1.0 / (double)FIX_DL);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double FD[6];
+                { double sc[2]; dict_scales(sh->D, sc); dict_scale_sums(sh->tot, sc); }
+                dl_sweep(sh->tot, sh->D, FD);
+                double rn2 = 0.0;
+                for (int q = 0; q < 6; ++q) rn2 += (FD[q] - sh->D[q]) * (FD[q] - sh->D[q]);
+                if (a.dl_anderson > 0 && rn2 < DL_SAMPLE_TOL * DL_SAMPLE_TOL) sh->dl_stop = 1;      // this step is still applied
+                aa_step(sh->aa, a.dl_anderson, sh->D, FD);
+                make_dict_lasso_consts(sh->D, a.dl_lambda, sh->lk);
+            }
+            __syncthreads();
+            if (sh->dl_stop) break;
+        }
+    }
+    if (threadIdx.x == 0) {
+        // phase 1 starts: the full passes inherit the difference history of the sample passes (aa_carry), or start afresh
+        if (use_sample) aa_carry(sh->aa); else aa_reset(sh->aa);
+        for (int q = 0; q < 6; ++q) ds.D[q] = sh->D[q];
+        for (int q = 0; q < 10; ++q) ds.sums[q] = 0ull;
+        ds.aa = sh->aa;
+        ds.it = 0;
+        ds.n_it = a.dl_iters + ((a.dl_sample_iters > 0 && !use_sample) ? 4 : 0);
+        if (ds.n_it <= 0) dl_tile_done(d, tile, sh->D);
+        else {
+            DictConsts c;
+            c.lk = sh->lk; c.lm = c.lk.g01 >= 0.f ? LASSO_UNIT_POS : LASSO_UNIT_NEG; c.mode = 0; c.pad = 0;
+            d.dconsts[tile] = c;
+        }
+    }
+}
+
+// After every full pass: dictionary update + Anderson step of every tile still iterating.  One warp per tile: the lanes
+// move the tile's Anderson state between global and shared memory (coalesced), lane 0 runs the serial fp64 step on it.
+constexpr int DL_UPD_THREADS = 32;
+__global__ void __launch_bounds__(DL_UPD_THREADS) dl_update_kernel(DictKernelArgs d) {
+    __shared__ AAState aa;
+    static_assert(sizeof(AAState) % 8 == 0, "AAState is copied as 8-byte words");
+    const int tile = blockIdx.x;
+    const PipeArgs& a = d.k.a;
+    if (d.dconsts[tile].mode != 0) return;
+    DictState& ds = d.dstate[tile];
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&ds.aa);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&aa);
+        for (int i = threadIdx.x; i < (int)(sizeof(AAState) / 8); i += DL_UPD_THREADS) dst[i] = src[i];
+    }
+    __syncwarp();
+    int done = 0;
+    if (threadIdx.x == 0) {
+        double t[9], D[6], FD[6];
+        for (int q = 0; q < 9; ++q) { t[q] = (double)(long long)ds.sums[q] * (1.0 / (double)FIX_DL); ds.sums[q] = 0ull; }
+        for (int q = 0; q < 6; ++q) D[q] = ds.D[q];
+        { double sc[2]; dict_scales(D, sc); dict_scale_sums(t, sc); }
+        dl_sweep(t, D, FD);
+        double rn2 = 0.0;
+        for (int q = 0; q < 6; ++q) rn2 += (FD[q] - D[q]) * (FD[q] - D[q]);
+        const bool stop = a.dl_anderson > 0 && rn2 < DL_FULL_TOL * DL_FULL_TOL;      // this step is still applied, then the iteration ends
+        aa_step(aa, a.dl_anderson, D, FD);
+        ds.it += 1;
+        for (int q = 0; q < 6; ++q) ds.D[q] = D[q];
+        if (stop || ds.it >= ds.n_it) { dl_tile_done(d, tile, D); done = 1; }
+        else {
+            DictConsts c;
+            make_dict_lasso_consts(D, a.dl_lambda, c.lk);
+            c.lm = c.lk.g01 >= 0.f ? LASSO_UNIT_POS : LASSO_UNIT_NEG; c.mode = 0; c.pad = 0;
+            d.dconsts[tile] = c;
+        }
+    }
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done) return;
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&aa);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&ds.aa);
+        for (int i = threadIdx.x; i < (int)(sizeof(AAState) / 8); i += DL_UPD_THREADS) dst[i] = src[i];
+    }
+}
+
+// Vahadane, fit / transform: brackets of the concentration pass from the tile's stain matrix (C0).
+__global__ void __launch_bounds__(NT) vahadane_plan_conc_kernel(TileKernelArgs k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileShared* ts = reinterpret_cast<TileShared*>(smem_raw);
+    PipeShared* sh = &ts->ps;
+    const int tile = blockIdx.x;
+    TileState& st = k.state[tile];
+    if (st.path != PATH_STREAM) return;
+    fill_small_table(ts->tab, k.a.tab);
+    if (threadIdx.x == 0) {
+        sh->flags = 0;
+        for (int q = 0; q < 6; ++q) sh->Msrc[q] = st.Msrc[q];
+        make_lasso_consts(sh->Msrc, k.a.lasso_lambda, sh->lk);
+        if (lasso_mode_of(sh->lk.rg00, sh->lk.rg11, sh->lk.g01) == LASSO_GENERAL) { tile_to_fallback(k, tile); sh->flags = -1; }
+        sh->s_cnt = 0; sh->s_ok = 0;
+    }
+    __syncthreads();
+    if (sh->flags != 0) return;
+    plan_conc_block(k, tile, ts, sh);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 constexpr int STREAM_SUB_BATCH = 4096;              // tiles per round of passes: bounds the key-list scratch at 256 MB
 
 bool stream_pipeline_eligible(const PipeArgs& a) {
-    return a.method == SB_METHOD_MACENKO && a.aligned && a.npx >= 32768 && (a.npx % GROUP_PX) == 0 && a.tile_list == nullptr;
+    return (a.method == SB_METHOD_MACENKO || a.method == SB_METHOD_VAHADANE) && a.aligned && a.npx >= 32768 && (a.npx % GROUP_PX) == 0 &&
+           a.tile_list == nullptr;
 }
 static size_t up256(size_t b) { return (b + 255) & ~(size_t)255; }
 // Tiles per round of passes: at most STREAM_SUB_BATCH, and at most 2^30 pixels (128 MB of tissue bits).
@@ -942,7 +1381,8 @@ static int stream_sub_batch(int B, int npx) {
 size_t stream_scratch_bytes(int B, int npx) {
     const size_t n = (size_t)stream_sub_batch(B, npx);
     return up256(n * sizeof(TileState)) + up256(n * sizeof(AngleConsts)) + up256(n * sizeof(ConcConsts)) +
-           up256(n * 2 * SLIST_CAP * sizeof(unsigned)) + up256((n + 1) * sizeof(int)) + up256(n * (size_t)(npx / GROUP_PX) * sizeof(unsigned short));
+           up256(n * 2 * SLIST_CAP * sizeof(unsigned)) + up256((n + 1) * sizeof(int)) + up256(n * (size_t)(npx / GROUP_PX) * sizeof(unsigned short)) +
+           up256(n * sizeof(DictState)) + up256(n * sizeof(DictConsts));
 }
 
 int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
@@ -958,8 +1398,16 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
     if ((e = scratch.get(&lists, (size_t)nsub * 2 * SLIST_CAP * sizeof(unsigned))) != cudaSuccess) return (int)e;
     if ((e = scratch.get(&fb, (size_t)(nsub + 1) * sizeof(int))) != cudaSuccess) return (int)e;
     if ((e = scratch.get(&mask, (size_t)nsub * (size_t)(a_all.npx / GROUP_PX) * sizeof(unsigned short))) != cudaSuccess) return (int)e;
+    const bool vahadane = a_all.method == SB_METHOD_VAHADANE;
+    DictState* dstate = nullptr; DictConsts* dconsts = nullptr;
+    if (vahadane) {
+        if ((e = scratch.get(&dstate, (size_t)nsub * sizeof(DictState))) != cudaSuccess) return (int)e;
+        if ((e = scratch.get(&dconsts, (size_t)nsub * sizeof(DictConsts))) != cudaSuccess) return (int)e;
+    }
+    static DeviceOnce once_v;
+    if ((e = ensure_dyn_smem(once_v, vahadane_plan_conc_kernel, (int)TILE_SHARED_BYTES)) != cudaSuccess) return (int)e;
     static DeviceOnce once_p, once_a, once_c;
-    const int tsm = (int)sizeof(TileShared);
+    const int tsm = (int)TILE_SHARED_BYTES;
     if ((e = ensure_dyn_smem(once_p, plan_angle_kernel, tsm)) != cudaSuccess) return (int)e;
     if ((e = ensure_dyn_smem(once_a, select_angle_kernel, tsm)) != cudaSuccess) return (int)e;
     if ((e = ensure_dyn_smem(once_c, select_conc_kernel, tsm)) != cudaSuccess) return (int)e;
@@ -980,10 +1428,28 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
         const RingGeom g{a.in, nullptr, a.B, a.npx};
         TileKernelArgs k{a, state, ac, cc, lists, fb, fb + nsub};
         int rc;
-        { NvtxRange r("stream: moments"); if ((rc = launch_ring_reduce<MomentOp>(g, p, num_sms, st)) != 0) return rc; }
-        { NvtxRange r("stream: plan angle"); plan_angle_kernel<<<a.B, NT, tsm, st>>>(k); }
-        { NvtxRange r("stream: angle brackets"); if ((rc = launch_ring_reduce<AngleOp>(g, p, num_sms, st)) != 0) return rc; }
-        { NvtxRange r("stream: select angle"); select_angle_kernel<<<a.B, NT, tsm, st>>>(k); }
+        int n_launch = 0;
+        if (vahadane) {
+            p.dstate = dstate; p.dconsts = dconsts;
+            const DictKernelArgs d{k, dstate, dconsts, mask};
+            const int unit_chunks = unit_groups(a.npx / GROUP_PX);       // chunk = NT groups: a unit of for_each_unit is this many chunks
+            const int n_full = a.dl_iters + (a.dl_sample_iters > 0 ? 4 : 0);
+            { NvtxRange r("stream: tissue mask"); if ((rc = launch_ring_reduce<MaskOp>(g, p, num_sms, st)) != 0) return rc; }
+            { NvtxRange r("stream: dictionary, sample passes"); dl_sample_kernel<<<a.B, DLS_NT, 0, st>>>(d); }
+            for (int it = 0; it < n_full; ++it) {
+                NvtxRange r("stream: dictionary, full pass");
+                if ((rc = launch_ring_reduce<DictOp>(g, p, num_sms, st, unit_chunks)) != 0) return rc;
+                dl_update_kernel<<<a.B, DL_UPD_THREADS, 0, st>>>(d);
+            }
+            n_launch = 2 + 2 * n_full;
+            if (a.mode >= PIPE_FIT) { NvtxRange r("stream: plan concentration"); vahadane_plan_conc_kernel<<<a.B, NT, tsm, st>>>(k); ++n_launch; }
+        } else {
+            { NvtxRange r("stream: moments"); if ((rc = launch_ring_reduce<MomentOp>(g, p, num_sms, st)) != 0) return rc; }
+            { NvtxRange r("stream: plan angle"); plan_angle_kernel<<<a.B, NT, tsm, st>>>(k); }
+            { NvtxRange r("stream: angle brackets"); if ((rc = launch_ring_reduce<AngleOp>(g, p, num_sms, st)) != 0) return rc; }
+            { NvtxRange r("stream: select angle"); select_angle_kernel<<<a.B, NT, tsm, st>>>(k); }
+            n_launch = 4;
+        }
         if (a.mode >= PIPE_FIT) {
             { NvtxRange r("stream: concentration brackets"); if ((rc = launch_ring_reduce<ConcOp>(g, p, num_sms, st)) != 0) return rc; }
             { NvtxRange r("stream: select concentration"); select_conc_kernel<<<a.B, NT, tsm, st>>>(k); }
@@ -994,7 +1460,7 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
         f.cluster_size = 1;
         f.tile_list = fb; f.tile_count = fb + nsub;
         { NvtxRange r("stream: fused fallback"); if ((rc = launch_tile_pipeline(f, num_sms, st)) != 0) return rc; }
-        scratch.h->launches += a.mode >= PIPE_FIT ? 7 : 5;
+        scratch.h->launches += n_launch + (a.mode >= PIPE_FIT ? 3 : 1);
     }
     return 0;
 }
