@@ -81,6 +81,13 @@ int  sb_version(void);
 /* number of kernel launches issued through this handle since creation (bench.py's gpu_launches) */
 long long sb_launch_count(const sb_handle* h);
 
+/* Diagnostics of the streaming statistics passes (csrc/sb_stream.cu): counters[0] = tiles that left the streaming passes
+ * for the fused per-tile kernel since the last reset, counters[1..7] = by reason (too small / too little tissue, sample too
+ * small (angle, concentration), bracket at the edge of the key range, bracket missed or list overflowed (angle,
+ * concentration), non-unit stain vectors).  Results are the same bits either way; the counters only say which path
+ * produced them.  Synchronises with the device.  counters: HOST unsigned[8]. */
+int sb_stream_fallbacks(sb_handle* h, unsigned* counters, int reset);
+
 /* Caller-owned scratch (SURVEY section 8-b "ownership").  sb_workspace_bytes: upper bound of the per-call scratch any
  * entry point takes for a [B,H,W,3] batch.  sb_set_workspace lends `bytes` of DEVICE memory to the handle (NULL, 0
  * takes it back); calls whose scratch fits use it instead of the stream-ordered pool.  The lender must keep it alive
@@ -174,6 +181,21 @@ int sb_stain_augment(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int 
  * :146-158, get_mean_std :174-186).  means/stds: double [B,3] of the brightness-standardised tile in LAB. */
 int sb_reinhard_stats(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double* means, double* stds,
                       void* stream);
+
+/* The exported pieces of the Reinhard path, each as its own entry point:
+ *   sb_standardize_brightness  standardize_brightness -- stain_utils.py:188-194: uint8(clip(I * 255 / percentile(I, 90), 0, 255)) per tile.
+ *   sb_lab_mean_std            get_mean_std -- stain_utils.py:174-186: mean / population std of lab_split's three planes (no
+ *                              brightness standardisation); means, stds: double [B,3].
+ *   sb_lab_split               lab_split -- stain_utils.py:146-158: 8-bit RGB -> LAB, I1 = float32(L) / 2.55, I2 = a - 128,
+ *                              I3 = b - 128; three device float planes of n_pixels each.
+ *   sb_lab_merge               merge_back -- stain_utils.py:160-172: uint8(clip((I1 * 2.55, I2 + 128, I3 + 128), 0, 255)) -> LAB2RGB;
+ *                              planes are device float (double when is_f64) and are NOT modified (the reference scales its
+ *                              arguments in place; the Python mirror reproduces that on the caller's arrays). */
+int sb_standardize_brightness(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, void* stream);
+int sb_lab_mean_std(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double* means, double* stds, void* stream);
+int sb_lab_split(sb_handle* h, const uint8_t* rgb, size_t n_pixels, float* I1, float* I2, float* I3, void* stream);
+int sb_lab_merge(sb_handle* h, const void* I1, const void* I2, const void* I3, int is_f64, size_t n_pixels, uint8_t* rgb,
+                 void* stream);
 
 /* ReinhardStainNormalizer.transform -- normalizer.py:70-94.  target_means/target_stds: device double[3]. */
 int sb_reinhard_transform(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W,

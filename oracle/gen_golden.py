@@ -5,7 +5,7 @@ Run:  python -m oracle.gen_golden            (from the repo root; needs /root/re
 
 Provenance of each group of keys:
   pure reference (numpy + OpenCV only, nothing shimmed):
-      mask/*  macenko_M/*  reinhard/*  lumstd/*  od/*  errors/*
+      mask/*  macenko_M/*  reinhard/*  lumstd/*  od/*  errors/*  labutil/*
   reference code + shimmed spams.lasso (closed form, see oracle/stain_oracle.py header):
       macenko_norm/*  stain_aug/*
   reference code + shimmed spams.trainDL (deterministic full-batch restatement, 50 iterations):
@@ -62,6 +62,18 @@ def main(out_path):
         G[f"reinhard/{name}/out"] = r.transform(src)
         G[f"reinhard/{name}/out_masked"] = r.transform(src, mask_background=True)
         G[f"lumstd/{name}"] = su.LuminosityStandardizer.standardize(src)
+        if name in ("s_64", "odd_67x53"):
+            # the exported pieces of the Reinhard path (stain_utils.py:146-194)
+            G[f"labutil/{name}/bright"] = su.standardize_brightness(src)
+            I1, I2, I3 = su.lab_split(src)
+            G[f"labutil/{name}/I1"], G[f"labutil/{name}/I2"], G[f"labutil/{name}/I3"] = I1.copy(), I2.copy(), I3.copy()
+            m, sd = su.get_mean_std(src)
+            G[f"labutil/{name}/means"] = np.array(m).reshape(3)
+            G[f"labutil/{name}/stds"] = np.array(sd).reshape(3)
+            # merge_back of transformed planes, float32 and float64 (it scales its arguments in place: pass copies)
+            J = [(I1 * 0.9 + 3.0), (I2 * 1.1 - 2.0), (I3 * 0.8 + 1.5)]
+            G[f"labutil/{name}/merge_f32"] = su.merge_back(*[x.astype(np.float32).copy() for x in J])
+            G[f"labutil/{name}/merge_f64"] = su.merge_back(*[x.astype(np.float64).copy() for x in J])
         # ---- reference + lasso shim
         n = ExtractiveStainNormalizer("macenko")
         n.fit(tgt)

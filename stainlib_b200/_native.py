@@ -26,7 +26,8 @@ EXPORTS = [
     "sb_concentrations", "sb_recombine", "sb_stain_augment", "sb_reinhard_stats", "sb_reinhard_transform",
     "sb_luminosity_standardize", "sb_hed_augment", "sb_grayscale_augment",
     "sb_slide_grid", "sb_slide_moments", "sb_slide_angle_hist", "sb_slide_conc_hist", "sb_slide_dl_sums", "sb_decode_jpeg",
-    "sb_workspace_bytes", "sb_set_workspace", "sb_rgb_to_od", "sb_od_to_rgb", "sb_hed_augment_f32",
+    "sb_workspace_bytes", "sb_set_workspace", "sb_stream_fallbacks", "sb_standardize_brightness", "sb_lab_mean_std",
+    "sb_lab_split", "sb_lab_merge", "sb_rgb_to_od", "sb_od_to_rgb", "sb_hed_augment_f32",
 ]
 
 
@@ -93,6 +94,11 @@ def load_library():
         lib.sb_workspace_bytes.argtypes = [ci, ci, ci]
         lib.sb_workspace_bytes.restype = ctypes.c_size_t
         lib.sb_set_workspace.argtypes = [vp, vp, ctypes.c_size_t]
+        lib.sb_stream_fallbacks.argtypes = [vp, ctypes.POINTER(ctypes.c_uint), ci]
+        lib.sb_standardize_brightness.argtypes = [vp, vp, vp, ci, ci, ci, vp]
+        lib.sb_lab_mean_std.argtypes = [vp, vp, ci, ci, ci, vp, vp, vp]
+        lib.sb_lab_split.argtypes = [vp, vp, ctypes.c_size_t, vp, vp, vp, vp]
+        lib.sb_lab_merge.argtypes = [vp, vp, vp, vp, ci, ctypes.c_size_t, vp, vp]
         lib.sb_rgb_to_od.argtypes = [vp, vp, ctypes.c_size_t, vp, ci, vp]
         lib.sb_od_to_rgb.argtypes = [vp, vp, ci, ctypes.c_size_t, vp, vp, vp]
         lib.sb_grayscale_augment.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp]
@@ -160,6 +166,14 @@ def set_workspace(tensor, device=None):
     assert tensor.is_cuda and tensor.dtype == torch.uint8 and tensor.is_contiguous()
     check(load_library().sb_set_workspace(h, ctypes.c_void_p(tensor.data_ptr()), tensor.numel()))
     _workspaces[idx] = tensor
+
+
+def stream_fallbacks(device=None, reset=False):
+    """[total, by reason 1..7] tiles that left the streaming statistics passes for the fused kernel (diagnostics)."""
+    h, _ = get_handle(device)
+    out = (ctypes.c_uint * 8)()
+    check(load_library().sb_stream_fallbacks(h, out, int(bool(reset))))
+    return [int(x) for x in out]
 
 
 def workspace_bytes(B, H, W):

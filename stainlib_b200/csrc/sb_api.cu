@@ -278,6 +278,7 @@ int sb_tissue_mask(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double
     sb::PointArgs a{};
     a.in = rgb; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb, mask, a.npx) && (a.npx % 16 == 0);
     a.tab = h->tab; a.ybound = mask_ybound_f(luminosity_threshold); a.mask_out = mask; a.status = status;
+    for (int c = 0; c < 3; ++c) a.ycoef[c] = (float)SB_RGB2LAB_COEFFS[3 + c];
     cudaError_t e = (cudaError_t)sb::launch_mask(a, h->num_sms, st);     // presets status to EMPTY_MASK on the stream first
     if (e != cudaSuccess) return cuda_fail(e, "mask launch");
     h->launches += status ? 2 : 1;
@@ -406,7 +407,9 @@ int sb_normalize_host(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int
     sb::NvtxRange nvtx("sb_normalize_host");
     const size_t tile_bytes = (size_t)H * W * 3;
     if (chunk_tiles <= 0) {
-        chunk_tiles = (int)(((size_t)12 << 20) / tile_bytes);   // 12 MB chunks: short fill/drain, still link-rate copies (tools/pcie_probe.py)
+        // 48 MB chunks: link-rate copies, and enough tiles per launch (64 of 512x512) that the ~10-35 launches of the
+        // streaming statistics passes stay far below the chunk's copy time (a 12 MB chunk left Vahadane launch-bound)
+        chunk_tiles = (int)(((size_t)48 << 20) / tile_bytes);
         if (chunk_tiles < 1) chunk_tiles = 1;
     }
     if (chunk_tiles > B) chunk_tiles = B;
@@ -528,6 +531,15 @@ int sb_stain_augment(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int 
     cudaError_t e = (cudaError_t)sb::launch_stain_augment(a, scratch);
     if (e != cudaSuccess) return cuda_fail(e, "stain_augment launch");
     h->launches += 1;
+    return SB_OK;
+}
+
+int sb_stream_fallbacks(sb_handle* h, unsigned* counters, int reset) {
+    if (!h || !counters) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    cudaError_t e = (cudaError_t)sb::stream_fallback_counters(counters, reset != 0);      // synchronises with the device
+    if (e != cudaSuccess) return cuda_fail(e, "fallback counters");
     return SB_OK;
 }
 

@@ -19,7 +19,7 @@
 
 namespace sb {
 
-enum LabMode { REINHARD_STATS = 0, REINHARD_TRANSFORM = 1, LUM_STANDARDIZE = 2 };
+enum LabMode { REINHARD_STATS = 0, REINHARD_TRANSFORM = 1, LUM_STANDARDIZE = 2, BRIGHTNESS_STANDARDIZE = 3 };
 
 struct LabArgs {
     const uint8_t* in;
@@ -34,6 +34,7 @@ struct LabArgs {
     int lmax;               // tissue <=> L <= lmax (L of the standardised image)
     double percentile;      // LUM_STANDARDIZE
     int32_t* status;
+    int skip_brightness;    // REINHARD_STATS without standardize_brightness first: get_mean_std (stain_utils.py:174-186)
 };
 
 struct __align__(16) LabShared {
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(NT, 2) lab_tile_kernel(LabArgs a) {
         for (int i = threadIdx.x; i < 768; i += NT) (&sh->hist[0][0])[i] = 0;
         if (threadIdx.x == 0) sh->any_tissue = 0;
         __syncthreads();
-        if (reinhard) {
+        if (reinhard && !a.skip_brightness) {
             // ---- pass 1: histogram of all 3N channel bytes -> 90th percentile -> brightness table (stain_utils.py:188-194)
             for (int g = threadIdx.x; g < G; g += NT) {
                 uint32_t w[12]; int nvalid;
@@ -146,6 +147,21 @@ __global__ void __launch_bounds__(NT, 2) lab_tile_kernel(LabArgs a) {
                 sh->hist[0][threadIdx.x] = 0;
             }
             __syncthreads();
+            if (a.mode == BRIGHTNESS_STANDARDIZE) {
+                // standardize_brightness alone (stain_utils.py:188-194): every byte through the table, nothing else
+                uint8_t* __restrict__ tb = a.out + (size_t)tile * npx * 3;
+                for (int g = threadIdx.x; g < G; g += NT) {
+                    uint32_t w[12], o[12]; int nvalid;
+                    load_group<true>(tin, npx, g, aligned, w, nvalid);
+#pragma unroll
+                    for (int k = 0; k < 12; ++k)
+                        o[k] = (uint32_t)sh->smap[w[k] & 255u] | ((uint32_t)sh->smap[(w[k] >> 8) & 255u] << 8) |
+                               ((uint32_t)sh->smap[(w[k] >> 16) & 255u] << 16) | ((uint32_t)sh->smap[w[k] >> 24] << 24);
+                    store_group(tb, npx, g, aligned, o);
+                }
+                __syncthreads();
+                continue;
+            }
         } else if (tile == (int)blockIdx.x) {
             if (threadIdx.x < 256) sh->gam2[threadIdx.x] = sh->gamma[threadIdx.x];
             __syncthreads();
@@ -248,6 +264,60 @@ __global__ void __launch_bounds__(NT, 2) lab_tile_kernel(LabArgs a) {
             a.status[tile] = 0;
         }
         __syncthreads();
+    }
+}
+
+// ---- lab_split / merge_back (stain_utils.py:146-172) as stand-alone per-pixel kernels: the exported pieces of the Reinhard
+// path.  The integer sRGB <-> CIELAB arithmetic is lab_forward / lab_inverse above with the plain linearisation table.
+struct LabPointTables {
+    unsigned short gamma[256];
+    unsigned short cbrt[3072];
+    int yf[512];
+    unsigned char invg[4096];
+};
+__device__ __forceinline__ void lab_point_load(LabPointTables* t, const Tables& tab) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) t->gamma[i] = tab.gamma[i];
+    for (int i = threadIdx.x; i < 3072; i += blockDim.x) t->cbrt[i] = tab.cbrt[i];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) t->yf[i] = tab.lab2yf[i];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) t->invg[i] = tab.invgamma[i];
+    __syncthreads();
+}
+// I1 = float32(L) / 2.55, I2 = a - 128, I3 = b - 128 (float32 arithmetic, as numpy does on the float32 planes).
+__global__ void __launch_bounds__(256) lab_split_kernel(Tables tab, const uint8_t* __restrict__ rgb, size_t npx, float* __restrict__ I1,
+                                                        float* __restrict__ I2, float* __restrict__ I3) {
+    __shared__ LabPointTables t;
+    lab_point_load(&t, tab);
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += (size_t)gridDim.x * blockDim.x) {
+        const int R = t.gamma[rgb[3 * p]], G = t.gamma[rgb[3 * p + 1]], Bl = t.gamma[rgb[3 * p + 2]];
+        const int fX = t.cbrt[(R * 1777 + G * 1541 + Bl * 778 + 2048) >> 12];
+        const int fY = t.cbrt[(R * 871 + G * 2929 + Bl * 296 + 2048) >> 12];
+        const int fZ = t.cbrt[(R * 73 + G * 448 + Bl * 3575 + 2048) >> 12];
+        const int L = (SB_LAB_LSCALE * fY + SB_LAB_LSHIFT + 16384) >> 15;
+        const int A = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
+        const int Bc = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
+        I1[p] = __fdiv_rn((float)L, 2.55f);
+        I2[p] = (float)A - 128.0f;
+        I3[p] = (float)Bc - 128.0f;
+    }
+}
+// uint8(clip((I1 * 2.55, I2 + 128, I3 + 128), 0, 255)) -> LAB2RGB, in the arithmetic of the planes' own dtype.
+template <typename T>
+__global__ void __launch_bounds__(256) lab_merge_kernel(Tables tab, const T* __restrict__ I1, const T* __restrict__ I2, const T* __restrict__ I3,
+                                                        size_t npx, uint8_t* __restrict__ rgb) {
+    __shared__ LabPointTables t;
+    lab_point_load(&t, tab);
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += (size_t)gridDim.x * blockDim.x) {
+        const int L = trunc_clip_u8((double)(I1[p] * (T)2.55)), A = trunc_clip_u8((double)(I2[p] + (T)128.0)), Bc = trunc_clip_u8((double)(I3[p] + (T)128.0));
+        const int y = t.yf[2 * L], ify = t.yf[2 * L + 1];
+        const int adiv = ((5 * A * 53687 + 128) >> 13) - 128 * 16384 / 500;
+        const int bdiv = ((Bc * 41943 + 16) >> 9) - 128 * 16384 / 200 + 1;
+        const int x = ab_to_xz(ify + adiv), z = ab_to_xz(ify - bdiv);
+        const int ro = (12615 * x - 6296 * y - 2223 * z + 8192) >> 14;
+        const int go = (-3773 * x + 7684 * y + 185 * z + 8192) >> 14;
+        const int bo = (217 * x - 836 * y + 4715 * z + 8192) >> 14;
+        rgb[3 * p] = t.invg[min(max(ro, 0), 4095)];
+        rgb[3 * p + 1] = t.invg[min(max(go, 0), 4095)];
+        rgb[3 * p + 2] = t.invg[min(max(bo, 0), 4095)];
     }
 }
 
@@ -697,6 +767,55 @@ int sb_reinhard_transform(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out,
     a.tmeans = target_means; a.tstds = target_stds; a.mask_background = mask_background; a.lmax = lab_lmax(luminosity_threshold);
     a.status = status;
     return launch_lab(h, a, (cudaStream_t)stream);
+}
+
+int sb_standardize_brightness(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, void* stream) {
+    if (bad_img(h, rgb_in, B, H, W) || !rgb_out) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_standardize_brightness");
+    sb::LabArgs a{};
+    a.in = rgb_in; a.out = rgb_out; a.B = B; a.npx = H * W; a.aligned = aligned16(rgb_in, rgb_out, a.npx); a.mode = sb::BRIGHTNESS_STANDARDIZE;
+    return launch_lab(h, a, (cudaStream_t)stream);
+}
+
+int sb_lab_mean_std(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double* means, double* stds, void* stream) {
+    if (bad_img(h, rgb, B, H, W) || !means || !stds) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_lab_mean_std");
+    sb::LabArgs a{};
+    a.in = rgb; a.B = B; a.npx = H * W; a.aligned = aligned16(rgb, rgb, a.npx); a.mode = sb::REINHARD_STATS; a.skip_brightness = 1;
+    a.means_out = means; a.stds_out = stds;
+    return launch_lab(h, a, (cudaStream_t)stream);
+}
+
+int sb_lab_split(sb_handle* h, const uint8_t* rgb, size_t n_pixels, float* I1, float* I2, float* I3, void* stream) {
+    if (!h || !rgb || !I1 || !I2 || !I3 || n_pixels == 0) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_lab_split");
+    size_t blocks = (n_pixels + 255) / 256;
+    if (blocks > (size_t)h->num_sms * 8) blocks = (size_t)h->num_sms * 8;
+    sb::lab_split_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(h->tab, rgb, n_pixels, I1, I2, I3);
+    if (cudaGetLastError() != cudaSuccess) return SB_ERR_CUDA;
+    h->launches += 1;
+    return SB_OK;
+}
+
+int sb_lab_merge(sb_handle* h, const void* I1, const void* I2, const void* I3, int is_f64, size_t n_pixels, uint8_t* rgb, void* stream) {
+    if (!h || !rgb || !I1 || !I2 || !I3 || n_pixels == 0) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    sb::NvtxRange nvtx("sb_lab_merge");
+    size_t blocks = (n_pixels + 255) / 256;
+    if (blocks > (size_t)h->num_sms * 8) blocks = (size_t)h->num_sms * 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_f64) sb::lab_merge_kernel<double><<<(int)blocks, 256, 0, st>>>(h->tab, (const double*)I1, (const double*)I2, (const double*)I3, n_pixels, rgb);
+    else sb::lab_merge_kernel<float><<<(int)blocks, 256, 0, st>>>(h->tab, (const float*)I1, (const float*)I2, (const float*)I3, n_pixels, rgb);
+    if (cudaGetLastError() != cudaSuccess) return SB_ERR_CUDA;
+    h->launches += 1;
+    return SB_OK;
 }
 
 int sb_luminosity_standardize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, int H, int W, double percentile, void* stream) {

@@ -130,6 +130,7 @@ int launch_tile_pipeline(const PipeArgs& a, int num_sms, cudaStream_t stream);
 bool stream_pipeline_eligible(const PipeArgs& a);
 size_t stream_scratch_bytes(int B, int npx);
 int launch_stream_pipeline(const PipeArgs& a, Scratch& scratch);
+int stream_fallback_counters(unsigned out[8], bool reset);
 
 // ---- slide-level fit passes (sb_pipeline.cu): 0 moments, 1/2 angle histograms (level 1/2), 3/4 concentration histograms
 struct SlideArgs {
@@ -166,6 +167,7 @@ struct PointArgs {
     int32_t* status;
 };
 int launch_mask(const PointArgs& a, int num_sms, cudaStream_t stream);
+int launch_mask_stream(const PointArgs& a, int num_sms, cudaStream_t stream);      // sb_stream.cu: the mask as a pass on the TMA ring
 int launch_recombine(const PointArgs& a, Scratch& scratch, bool use_tma);
 int launch_recombine_normalize(const PointArgs& a, Scratch& scratch, bool use_tma, const double* M_src,
                                const double* maxC_src, const double* Mt, const double* maxCt, int32_t* status);

@@ -292,7 +292,8 @@ struct KeyList {
     void* base;
     unsigned start;     // bracket start (offset origin of the narrow form)
     bool wide;
-    __device__ __forceinline__ unsigned cap() const { return wide ? LIST_BYTES / 4 : LIST_BYTES / 2; }
+    unsigned bytes = LIST_BYTES;     // size of the buffer at base (16 KB in the fused kernel, 32 KB in the per-tile kernels of the streaming path)
+    __device__ __forceinline__ unsigned cap() const { return wide ? bytes / 4 : bytes / 2; }
     __device__ __forceinline__ void put(unsigned idx, unsigned key) const {
         if (wide) static_cast<unsigned*>(base)[idx] = key; else static_cast<unsigned short*>(base)[idx] = (unsigned short)(key - start);
     }
@@ -315,12 +316,15 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned x) {
 // overflows the lists.  Small samples (256^2 tiles) do not miss at 3 sigma + 8 and only pay for wider brackets (+6 %),
 // and beyond ~80 ranks the brackets of big tiles approach the list capacity: hence the two regimes and the cap.
 // sigmas >= 0 (SB_BRACKET_SIGMAS / SB_BRACKET_PAD, sweeps only) overrides the rule with sigmas * sigma + pad.
-__device__ inline void plan_bracket(unsigned n, unsigned n_s, unsigned lo, unsigned& ra, unsigned& rb, float sigmas, float pad) {
+// cap: largest half-width the key lists can take (80 in the fused kernel, whose lists hold 4096 full keys; the per-tile
+// kernels of the streaming path, with 8192, pass stream_bracket_cap(n) -- wide enough for 5 sigma on megapixel tiles too).
+__device__ inline void plan_bracket(unsigned n, unsigned n_s, unsigned lo, unsigned& ra, unsigned& rb, float sigmas, float pad, double cap = 80.0,
+                                    double wide_sigmas = 5.0) {
     const double q = (double)lo / (double)n;
     const double pos = q * (double)n_s;
     const double sd = sqrt((double)n_s * q * (1.0 - q));
-    const double m_narrow = 3.0 * sd + 8.0, m_wide = 5.0 * sd + 16.0;
-    double m = n_s < 6000u ? m_narrow : fmin(m_wide, fmax(m_narrow, 80.0));
+    const double m_narrow = 3.0 * sd + 8.0, m_wide = wide_sigmas * sd + 16.0;
+    double m = n_s < 6000u ? m_narrow : fmin(m_wide, fmax(m_narrow, cap));
     if (sigmas >= 0.f) m = (double)sigmas * sd + (double)pad;
     const double a = floor(pos - m), b = ceil(pos + m) + 1.0;
     ra = a < 0.0 ? 0u : (unsigned)a;

@@ -167,6 +167,8 @@ __global__ void fill_i32_kernel(int32_t* p, int n, int32_t v) {
 int launch_mask(const PointArgs& a, int num_sms, cudaStream_t stream) {
     // preset every tile to EMPTY_MASK; a CTA that sees tissue clears the bit (stream-ordered: no host synchronisation)
     if (a.status) fill_i32_kernel<<<(a.B + 255) / 256, 256, 0, stream>>>(a.status, a.B, SB_STATUS_EMPTY_MASK);
+    // 16-byte aligned tiles of whole 16-pixel groups: streaming pass on the TMA ring; register-staged kernel otherwise
+    if (a.aligned && (a.npx % GROUP_PX) == 0 && ((size_t)a.npx * 3) % 16 == 0 && a.ycoef[0] != 0.f) return launch_mask_stream(a, num_sms, stream);
     mask_kernel<<<point_grid(a, num_sms, 8), PT, 0, stream>>>(a);
     return (int)cudaGetLastError();
 }

@@ -30,7 +30,8 @@
 
 namespace sb {
 
-constexpr int SLIST_CAP = 8192;                     // entries of a per-tile key list in global memory (full 23-bit keys)
+constexpr int SLIST_CAP_MAX = 16384;                // entries of a per-tile key list in global memory (full 23-bit keys): 8192 for tiles up
+__host__ __device__ inline int slist_cap(int npx) { return npx > (1 << 20) ? SLIST_CAP_MAX : SLIST_CAP_MAX / 2; }   // to a megapixel, 16384 beyond
 constexpr int RQ_CAP = 64;                          // entries per warp queue: drained below 32 after every push round
 constexpr int RR_GT = 512;                          // compute threads of a ring-reduce CTA (one 16-pixel group each per chunk)
 constexpr int RR_STAGES = 6;
@@ -358,13 +359,13 @@ __device__ __forceinline__ void rq_drain_rest(WarpScratch& ws, P&& proc) {
 }
 // Key-list staging buffer j (0 / 1) of the warp: append the keys of the lanes with pred; 32 staged keys go to the tile's
 // global list with one atomic reservation.  n is warp-uniform.
-__device__ __forceinline__ void stage_flush32(unsigned* buf, unsigned& n, unsigned* glen, unsigned* glist) {
+__device__ __forceinline__ void stage_flush32(unsigned* buf, unsigned& n, unsigned* glen, unsigned* glist, unsigned cap) {
     __syncwarp();
     unsigned basei = 0;
     if ((threadIdx.x & 31) == 0) basei = atomicAdd(glen, 32u);
     basei = __shfl_sync(0xffffffffu, basei, 0);
     const unsigned idx = basei + (threadIdx.x & 31u);
-    if (idx < (unsigned)SLIST_CAP) glist[idx] = buf[threadIdx.x & 31u];
+    if (idx < cap) glist[idx] = buf[threadIdx.x & 31u];
     const unsigned rest = n - 32u;                       // < 32
     const unsigned carry = (threadIdx.x & 31u) < rest ? buf[32u + (threadIdx.x & 31u)] : 0u;
     __syncwarp();
@@ -372,22 +373,22 @@ __device__ __forceinline__ void stage_flush32(unsigned* buf, unsigned& n, unsign
     n = rest;
     __syncwarp();
 }
-__device__ __forceinline__ void stage_append(unsigned* buf, unsigned& n, bool pred, unsigned key, unsigned* glen, unsigned* glist) {
+__device__ __forceinline__ void stage_append(unsigned* buf, unsigned& n, bool pred, unsigned key, unsigned* glen, unsigned* glist, unsigned cap) {
     const unsigned m = __ballot_sync(0xffffffffu, pred);
     if (m) {
         if (pred) buf[n + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = key;
         n += __popc(m);
-        if (n >= 32u) stage_flush32(buf, n, glen, glist);
+        if (n >= 32u) stage_flush32(buf, n, glen, glist, cap);
     }
 }
-__device__ __forceinline__ void stage_flush_rest(unsigned* buf, unsigned& n, unsigned* glen, unsigned* glist) {
+__device__ __forceinline__ void stage_flush_rest(unsigned* buf, unsigned& n, unsigned* glen, unsigned* glist, unsigned cap) {
     if (n > 0u) {
         __syncwarp();
         unsigned basei = 0;
         if ((threadIdx.x & 31) == 0) basei = atomicAdd(glen, n);
         basei = __shfl_sync(0xffffffffu, basei, 0);
         const unsigned idx = basei + (threadIdx.x & 31u);
-        if ((threadIdx.x & 31u) < n && idx < (unsigned)SLIST_CAP) glist[idx] = buf[threadIdx.x & 31u];
+        if ((threadIdx.x & 31u) < n && idx < cap) glist[idx] = buf[threadIdx.x & 31u];
         n = 0u;
         __syncwarp();
     }
@@ -398,7 +399,8 @@ struct StreamParams {
     TileState* state;
     const AngleConsts* aconsts;
     const ConcConsts* cconsts;
-    unsigned* lists;              // [B][2][SLIST_CAP]
+    unsigned* lists;              // [B][2][list_cap]
+    int list_cap;
     struct DictState* dstate;     // Vahadane: per-tile dictionary, sums of the current pass, Anderson history
     const struct DictConsts* dconsts;
     unsigned short* mask;         // [B][groups]: 16 tissue bits per 16-pixel group, written by pass 1, read by pass 3
@@ -502,9 +504,9 @@ struct AngleOp {
         if (has && key < k.ka0) ++acc.below0;
         if (has && key < k.ka1) ++acc.below1;
         unsigned* len = p.state[tile].len;
-        unsigned* list0 = p.lists + (size_t)tile * 2 * SLIST_CAP;
-        stage_append(ws.w + RQ_CAP, ws.n0, has && key >= k.ka0 && key < k.kb0, key, &len[0], list0);
-        stage_append(ws.w + 2 * RQ_CAP, ws.n1, has && key >= k.ka1 && key < k.kb1, key, &len[1], list0 + SLIST_CAP);
+        unsigned* list0 = p.lists + (size_t)tile * 2 * p.list_cap;
+        stage_append(ws.w + RQ_CAP, ws.n0, has && key >= k.ka0 && key < k.kb0, key, &len[0], list0, (unsigned)p.list_cap);
+        stage_append(ws.w + 2 * RQ_CAP, ws.n1, has && key >= k.ka1 && key < k.kb1, key, &len[1], list0 + p.list_cap, (unsigned)p.list_cap);
     }
     __device__ static bool tile_active(const Params& p, int tile) { return p.aconsts[tile].mode == 0; }
     __device__ static void process(const Consts& k, const Params& p, const OdAbs tab, const unsigned char* buf, bool active, unsigned px0,
@@ -530,9 +532,9 @@ struct AngleOp {
     __device__ static void finish_run(const Consts& k, const Params& p, const OdAbs tab, WarpScratch& ws, Acc& acc, int tile) {
         if (k.mode == 0) {
             rq_drain_rest(ws, [&](bool has, uint32_t rgb) { exact(k, p, tab, ws, acc, tile, has, rgb); });
-            unsigned* list0 = p.lists + (size_t)tile * 2 * SLIST_CAP;
-            stage_flush_rest(ws.w + RQ_CAP, ws.n0, &p.state[tile].len[0], list0);
-            stage_flush_rest(ws.w + 2 * RQ_CAP, ws.n1, &p.state[tile].len[1], list0 + SLIST_CAP);
+            unsigned* list0 = p.lists + (size_t)tile * 2 * p.list_cap;
+            stage_flush_rest(ws.w + RQ_CAP, ws.n0, &p.state[tile].len[0], list0, (unsigned)p.list_cap);
+            stage_flush_rest(ws.w + 2 * RQ_CAP, ws.n1, &p.state[tile].len[1], list0 + p.list_cap, (unsigned)p.list_cap);
             const unsigned b0 = warp_sum_u(acc.below0), b1 = warp_sum_u(acc.below1);
             if ((threadIdx.x & 31) == 0) {
                 if (b0) atomicAdd(&p.state[tile].below[0], b0);
@@ -594,9 +596,9 @@ struct ConcOp {
         if (s0) { if (neg_as_one(x0.x) != 0.f) --acc.corr0; if (k0 < k.ka0) ++acc.corr0; }
         if (s1) { if (neg_as_one(x1.x) != 0.f) --acc.corr1; if (k1 < k.ka1) ++acc.corr1; }
         unsigned* len = p.state[tile].clen;
-        unsigned* list0 = p.lists + (size_t)tile * 2 * SLIST_CAP;
-        stage_append(ws.w + RQ_CAP, ws.n0, s0 && k0 >= k.ka0 && k0 < k.kb0, k0, &len[0], list0);
-        stage_append(ws.w + 2 * RQ_CAP, ws.n1, s1 && k1 >= k.ka1 && k1 < k.kb1, k1, &len[1], list0 + SLIST_CAP);
+        unsigned* list0 = p.lists + (size_t)tile * 2 * p.list_cap;
+        stage_append(ws.w + RQ_CAP, ws.n0, s0 && k0 >= k.ka0 && k0 < k.kb0, k0, &len[0], list0, (unsigned)p.list_cap);
+        stage_append(ws.w + 2 * RQ_CAP, ws.n1, s1 && k1 >= k.ka1 && k1 < k.kb1, k1, &len[1], list0 + p.list_cap, (unsigned)p.list_cap);
     }
     template <int LM>
     __device__ static __forceinline__ void body(const Consts& k, const Params& p, const OdAbs tab, const unsigned char* buf, bool active,
@@ -636,9 +638,9 @@ struct ConcOp {
         if (k.mode == 0) {
             if (k.lm == LASSO_UNIT_POS) rq_drain_rest(ws, [&](bool has, uint32_t rgb) { exact<LASSO_UNIT_POS>(k, p, tab, ws, acc, tile, has, rgb); });
             else rq_drain_rest(ws, [&](bool has, uint32_t rgb) { exact<LASSO_UNIT_NEG>(k, p, tab, ws, acc, tile, has, rgb); });
-            unsigned* list0 = p.lists + (size_t)tile * 2 * SLIST_CAP;
-            stage_flush_rest(ws.w + RQ_CAP, ws.n0, &p.state[tile].clen[0], list0);
-            stage_flush_rest(ws.w + 2 * RQ_CAP, ws.n1, &p.state[tile].clen[1], list0 + SLIST_CAP);
+            unsigned* list0 = p.lists + (size_t)tile * 2 * p.list_cap;
+            stage_flush_rest(ws.w + RQ_CAP, ws.n0, &p.state[tile].clen[0], list0, (unsigned)p.list_cap);
+            stage_flush_rest(ws.w + 2 * RQ_CAP, ws.n1, &p.state[tile].clen[1], list0 + p.list_cap, (unsigned)p.list_cap);
             // (the float counts are exact integers: at most 16 per chunk and thread, far below 2^24 per run)
             int t0 = (int)acc.n0 + acc.corr0, t1 = (int)acc.n1 + acc.corr1;
 #pragma unroll
@@ -693,6 +695,56 @@ struct MaskOp {
             if (sm) atomicAdd(&p.state[tile].mom[0], (unsigned long long)sm);
         }
         acc_init(acc);
+    }
+};
+
+// get_tissue_mask (stain_utils.py:32-48) as a streaming pass: 3 B/px in through the ring, 1 B/px out (16 bytes per thread,
+// coalesced); a tile that shows tissue clears the EMPTY_MASK bit its status word was preset to.
+struct MaskOutParams {
+    const unsigned short* gamma;
+    float ycoef[3], ybound;
+    uint8_t* mask_out;            // [B][npx], 1 = tissue
+    int32_t* status;              // [B] or null
+    int npx;
+};
+struct MaskOutOp {
+    using Consts = Empty;
+    using Params = MaskOutParams;
+    struct Acc { unsigned any; };
+    static constexpr int kLaneShift = 2;
+    __device__ static void fill_table(unsigned char* tab, const Params& p, int tid, int n) {
+        for (int i = tid; i < 256 * 32; i += n)
+            *reinterpret_cast<float*>(tab + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = (float)p.gamma[i >> 5];
+    }
+    __device__ static Consts load_consts(const Params&, int) { return Empty{}; }
+    __device__ static bool tile_active(const Params&, int) { return true; }
+    __device__ static void acc_init(Acc& a) { a.any = 0; }
+    __device__ static void process(const Consts&, const Params& p, const OdAbs tab, const unsigned char* buf, bool active, unsigned px0, WarpScratch&,
+                                   Acc& acc, int tile, bool) {
+        if (!active) return;
+        uint32_t w[12];
+        load_group_smem(buf, true, w);
+        const float2 cr = dup(p.ycoef[0]), cg = dup(p.ycoef[1]), cb = dup(p.ycoef[2]);
+        const float bound = p.ybound;
+        unsigned mbits = 0;
+        for_each_pair_od_abs(tab, w, [&](int i, float2 g0, float2 g1, float2 g2) {
+            const float2 y = __ffma2_rn(g2, cb, __ffma2_rn(g1, cg, __fmul2_rn(g0, cr)));
+            mbits |= set_lt(y.x, bound) & (1u << i);
+            mbits |= set_lt(y.y, bound) & (2u << i);
+        });
+        acc.any |= mbits;
+        // four bits -> four 0/1 bytes: the multiply puts bit j of the nibble at bit 8 j (no two products collide)
+        uint4 v;
+        v.x = ((mbits & 15u) * 0x00204081u) & 0x01010101u;
+        v.y = (((mbits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+        v.z = (((mbits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+        v.w = (((mbits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+        stg_stream(reinterpret_cast<uint4*>(p.mask_out + (size_t)tile * p.npx + px0) + threadIdx.x, v);
+    }
+    __device__ static void finish_run(const Consts&, const Params& p, const OdAbs, WarpScratch&, Acc& acc, int tile) {
+        const unsigned any = __ballot_sync(0xffffffffu, acc.any != 0u);
+        if ((threadIdx.x & 31) == 0 && any && p.status) atomicAnd(&p.status[tile], ~SB_STATUS_EMPTY_MASK);
+        acc.any = 0;
     }
 };
 
@@ -765,6 +817,7 @@ struct TileKernelArgs {
     AngleConsts* aconsts;
     ConcConsts* cconsts;
     unsigned* lists;
+    int list_cap;                 // entries per key list (slist_cap(npx)); the kernels' second shared list sits at TILE_LIST1_OFFSET
     int* fb_list;                 // tiles for the fused kernel
     int* fb_count;
 };
@@ -772,13 +825,54 @@ struct TileShared {
     float2 tab[256];
     PipeShared ps;                // allocated without its fused-kernel-only tail (see PipeShared)
 };
-constexpr size_t TILE_SHARED_BYTES = offsetof(TileShared, ps) + offsetof(PipeShared, aa);
+// Layout of the per-tile kernels' dynamic shared memory: TileShared up to PipeShared::aa, then the two key lists of
+// list_cap full keys each (twice / four times the fused kernel's): 2 x 32 KB for tiles up to a megapixel -- list 0 then
+// simply is the 32 KB histogram buffer --, 2 x 64 KB behind the structure for bigger tiles.
+constexpr size_t TILE_LIST_OFFSET = (offsetof(TileShared, ps) + offsetof(PipeShared, aa) + 15) & ~(size_t)15;
+__host__ __device__ inline size_t tile_shared_bytes(int list_cap) {
+    return TILE_LIST_OFFSET + (size_t)list_cap * sizeof(unsigned) * (list_cap * sizeof(unsigned) > 2 * L1_BINS * sizeof(unsigned) ? 2 : 1);
+}
+struct TileLists { void* l0; void* l1; unsigned bytes; };
+__device__ __forceinline__ TileLists tile_lists(unsigned char* smem_raw, PipeShared* sh, int list_cap) {
+    const unsigned bytes = (unsigned)list_cap * (unsigned)sizeof(unsigned);
+    if (bytes <= 2 * L1_BINS * sizeof(unsigned)) return TileLists{sh->hist, smem_raw + TILE_LIST_OFFSET, bytes};
+    return TileLists{smem_raw + TILE_LIST_OFFSET, smem_raw + TILE_LIST_OFFSET + bytes, bytes};
+}
 
+// Half-width cap of a sampled bracket (in sample ranks) such that the bracket -- (2 m + 1) sample ranks of 16 pixels plus
+// up to two level-1 bins (n / 4096 keys each) of rounding -- stays below ~7000 of the 8192 list entries.
+__device__ inline double stream_bracket_cap(unsigned n, int list_cap) {
+    const double m = 0.8 * (double)list_cap / 32.0 - 0.5;      // (2 m + 1) sample ranks of 16 pixels fill 80 % of the list
+    return m > 80.0 ? m : 80.0;
+}
+constexpr double STREAM_WIDE_SIGMAS = 6.5;      // the lists of the streaming path afford wider brackets than the fused kernel's 5 sigma
+// Bracket edges INSIDE the level-1 bins that hold the bracket's sample ranks: the keys of a bin are taken as uniformly spread
+// over it (rank `rem` of `cnt` sample keys in bin `bin`), with 1/16 of a bin of padding.  Snapping the edges to whole bins,
+// as the fused kernel does, costs up to two bins of extra keys in the list -- thousands on a megapixel tile, whose tissue
+// angles crowd into a few hundred of the 4096 bins.  The bracket only has to CONTAIN the target rank (validated exactly
+// after the pass) and fit the list.
+__device__ inline unsigned bracket_edge_lo(unsigned bin, unsigned rem, unsigned cnt) {
+    const unsigned base = bin << L2_BITS, off = cnt ? (unsigned)(((unsigned long long)rem << L2_BITS) / cnt) : 0u;
+    const unsigned pad = 1u << (L2_BITS - 4);
+    return base + off > pad ? base + off - pad : 0u;
+}
+__device__ inline unsigned bracket_edge_hi(unsigned bin, unsigned rem, unsigned cnt) {
+    const unsigned base = bin << L2_BITS, off = cnt ? (unsigned)((((unsigned long long)rem + 1u) << L2_BITS) / cnt) + 1u : (1u << L2_BITS);
+    const unsigned e = base + off + (1u << (L2_BITS - 4));
+    return e < (1u << KEY_BITS) ? e : (1u << KEY_BITS);
+}
 __device__ __forceinline__ void fill_small_table(float2* tab, const Tables& t) {
     for (int i = threadIdx.x; i < 256; i += NT) tab[i] = make_float2(t.od[i], (float)t.gamma[i]);
 }
+// Why tiles left the streaming path, counted per process and device (diagnostics: sb_stream_fallbacks):
+//   1 tile too small / too little tissue   2 angle sample too small   3 concentration sample too small
+//   4 concentration bracket touches zero or the top of the key range   5 angle bracket missed its rank or its list overflowed
+//   6 non-unit stain vectors   7 concentration bracket missed / overflowed
+__device__ unsigned g_fallback_reasons[8];
 // Thread 0: the tile leaves the streaming path.
-__device__ inline void tile_to_fallback(const TileKernelArgs& k, int tile) {
+__device__ inline void tile_to_fallback(const TileKernelArgs& k, int tile, int reason) {
+    atomicAdd(&g_fallback_reasons[reason & 7], 1u);
+    atomicAdd(&g_fallback_reasons[0], 1u);
     k.state[tile].path = PATH_FALLBACK;
     k.aconsts[tile].mode = 1;
     k.cconsts[tile].mode = 1;
@@ -846,7 +940,7 @@ __global__ void __launch_bounds__(NT) plan_angle_kernel(TileKernelArgs k) {
         st.n_tissue = (unsigned)n;
         sh->s_cnt = 0; sh->s_ok = 0;
         if (flags) tile_flagged(k, tile, flags);
-        else if ((unsigned)n < 16384u || npx < 32768) { tile_to_fallback(k, tile); sh->flags = -1; }
+        else if ((unsigned)n < 16384u || npx < 32768) { tile_to_fallback(k, tile, 1); sh->flags = -1; }
     }
     zero_hist(sh);
     if (sh->flags != 0) return;
@@ -868,12 +962,12 @@ __global__ void __launch_bounds__(NT) plan_angle_kernel(TileKernelArgs k) {
     if (threadIdx.x == 0) {
         const unsigned n_s = sh->s_cnt;
         if (n_s >= 1024u) {
-            plan_bracket(n_tissue, n_s, p_lo[0], sh->q_rank[0], sh->q_rank[1], a.bracket_sigmas, a.bracket_pad);
-            plan_bracket(n_tissue, n_s, p_lo[1], sh->q_rank[2], sh->q_rank[3], a.bracket_sigmas, a.bracket_pad);
+            plan_bracket(n_tissue, n_s, p_lo[0], sh->q_rank[0], sh->q_rank[1], a.bracket_sigmas, a.bracket_pad, stream_bracket_cap(n_tissue, k.list_cap), STREAM_WIDE_SIGMAS);
+            plan_bracket(n_tissue, n_s, p_lo[1], sh->q_rank[2], sh->q_rank[3], a.bracket_sigmas, a.bracket_pad, stream_bracket_cap(n_tissue, k.list_cap), STREAM_WIDE_SIGMAS);
             for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
             sh->s_ok = 1;
         } else {
-            tile_to_fallback(k, tile);
+            tile_to_fallback(k, tile, 2);
         }
     }
     __syncthreads();
@@ -882,8 +976,8 @@ __global__ void __launch_bounds__(NT) plan_angle_kernel(TileKernelArgs k) {
     if (threadIdx.x == 0) {
         unsigned ka[2], kb[2];
         for (int j = 0; j < 2; ++j) {
-            ka[j] = sh->q_bin[2 * j] << L2_BITS;
-            kb[j] = (sh->q_bin[2 * j + 1] + 1u) << L2_BITS;
+            ka[j] = bracket_edge_lo(sh->q_bin[2 * j], sh->q_rem[2 * j], sh->hist[sh->q_bin[2 * j]]);
+            kb[j] = bracket_edge_hi(sh->q_bin[2 * j + 1], sh->q_rem[2 * j + 1], sh->hist[sh->q_bin[2 * j + 1]]);
         }
         // a pixel in the half-plane x > 0 whose diamond coordinate lies safely between the low and the high bracket (64 key
         // units of slack) is "above bracket 0, below bracket 1" without computing its key (as in the fused kernel)
@@ -935,12 +1029,12 @@ __device__ __forceinline__ void plan_conc_block(const TileKernelArgs& k, int til
     if (threadIdx.x == 0) {
         const unsigned n_s = sh->s_cnt;
         if (n_s >= 1024u) {
-            plan_bracket((unsigned)npx, n_s, c_lo, sh->q_rank[0], sh->q_rank[1], a.bracket_sigmas, a.bracket_pad);
+            plan_bracket((unsigned)npx, n_s, c_lo, sh->q_rank[0], sh->q_rank[1], a.bracket_sigmas, a.bracket_pad, stream_bracket_cap((unsigned)npx, k.list_cap), STREAM_WIDE_SIGMAS);
             sh->q_rank[2] = sh->q_rank[0]; sh->q_rank[3] = sh->q_rank[1];
             for (int q = 0; q < 4; ++q) { sh->q_bin[q] = 0; sh->q_rem[q] = 0; }
             sh->s_ok = 1;
         } else {
-            tile_to_fallback(k, tile);
+            tile_to_fallback(k, tile, 3);
         }
     }
     __syncthreads();
@@ -954,8 +1048,9 @@ __device__ __forceinline__ void plan_conc_block(const TileKernelArgs& k, int til
         float mid[2], half[2];
         bool ok = true;
         for (int j = 0; j < 2; ++j) {
-            ka[j] = sh->q_bin[2 * j] << L2_BITS;
-            kb[j] = (sh->q_bin[2 * j + 1] + 1u) << L2_BITS;
+            const unsigned* hj = sh->hist + j * L1_BINS;
+            ka[j] = bracket_edge_lo(sh->q_bin[2 * j], sh->q_rem[2 * j], hj[sh->q_bin[2 * j]]);
+            kb[j] = bracket_edge_hi(sh->q_bin[2 * j + 1], sh->q_rem[2 * j + 1], hj[sh->q_bin[2 * j + 1]]);
             // a bracket that touches zero (a stain absent from >= 99 % of the tile) or the top of the key range: robust path
             ok = ok && ka[j] >= 64u && kb[j] + 64u < (1u << KEY_BITS);
             // concentrations outside [lo, hi] (64 key units of slack around the bracket) need no exact key
@@ -965,7 +1060,7 @@ __device__ __forceinline__ void plan_conc_block(const TileKernelArgs& k, int til
             half[j] = float_above(fmax(hi - (double)mid[j], (double)mid[j] - lo) * (1.0 + 1e-6));
             ok = ok && lo > 0.0;
         }
-        if (!ok) tile_to_fallback(k, tile);
+        if (!ok) tile_to_fallback(k, tile, 4);
         else {
             c.mid0 = mid[0]; c.half0 = half[0]; c.mid1 = mid[1]; c.half1 = half[1];
             c.ka0 = ka[0]; c.kb0 = kb[0]; c.ka1 = ka[1]; c.kb1 = kb[1];
@@ -993,23 +1088,24 @@ __global__ void __launch_bounds__(NT) select_angle_kernel(TileKernelArgs k) {
     unsigned p_lo[2], p_hi[2];
     { double fr; percentile_index(n_tissue, 100.0 - a.ang_pct, p_lo[0], p_hi[0], fr); percentile_index(n_tissue, a.ang_pct, p_lo[1], p_hi[1], fr); }
     const unsigned ka0 = st.brk[0], kb0 = st.brk[1], ka1 = st.brk[2], kb1 = st.brk[3];
-    const KeyList list0{sh->hist, ka0, kb0 - ka0 > LIST_SPAN}, list1{sh->hist + L1_BINS, ka1, kb1 - ka1 > LIST_SPAN};
+    const TileLists tl = tile_lists(smem_raw, sh, k.list_cap);
+    const KeyList list0{tl.l0, ka0, kb0 - ka0 > LIST_SPAN, tl.bytes}, list1{tl.l1, ka1, kb1 - ka1 > LIST_SPAN, tl.bytes};
     fill_small_table(ts->tab, a.tab);
     if (threadIdx.x == 0) {
         bool ok = true;
         for (int j = 0; j < 2; ++j) {
             sh->l_len[j] = st.len[j]; sh->l_below[j] = st.below[j];
-            ok = ok && st.len[j] <= (j ? list1 : list0).cap() && st.below[j] <= p_lo[j] && p_hi[j] < st.below[j] + st.len[j];
+            ok = ok && st.len[j] <= min((j ? list1 : list0).cap(), (unsigned)k.list_cap) && st.below[j] <= p_lo[j] && p_hi[j] < st.below[j] + st.len[j];
         }
         sh->s_ok = ok ? 1 : 0;
         sh->flags = 0;
-        if (!ok) tile_to_fallback(k, tile);
+        if (!ok) tile_to_fallback(k, tile, 5);
     }
     __syncthreads();
     if (!sh->s_ok) return;
-    const unsigned* gl = k.lists + (size_t)tile * 2 * SLIST_CAP;
+    const unsigned* gl = k.lists + (size_t)tile * 2 * k.list_cap;
     load_list(list0, gl, sh->l_len[0]);
-    load_list(list1, gl + SLIST_CAP, sh->l_len[1]);
+    load_list(list1, gl + k.list_cap, sh->l_len[1]);
     __syncthreads();
     {
         const unsigned r_lo[2] = {p_lo[0] - sh->l_below[0], p_lo[1] - sh->l_below[1]};
@@ -1051,7 +1147,7 @@ __global__ void __launch_bounds__(NT) select_angle_kernel(TileKernelArgs k) {
             else {
                 make_lasso_consts(sh->Msrc, a.lasso_lambda, sh->lk);
                 const int lm = lasso_mode_of(sh->lk.rg00, sh->lk.rg11, sh->lk.g01);
-                if (lm == LASSO_GENERAL) { tile_to_fallback(k, tile); sh->flags = -1; }      // non-unit rows: robust path
+                if (lm == LASSO_GENERAL) { tile_to_fallback(k, tile, 6); sh->flags = -1; }      // non-unit rows: robust path
             }
         }
         sh->s_cnt = 0; sh->s_ok = 0;
@@ -1075,21 +1171,22 @@ __global__ void __launch_bounds__(NT) select_conc_kernel(TileKernelArgs k) {
     double fr;
     percentile_index((unsigned)npx, a.conc_pct, c_lo, c_hi, fr);
     const unsigned ka0 = st.cbrk[0], kb0 = st.cbrk[1], ka1 = st.cbrk[2], kb1 = st.cbrk[3];
-    const KeyList list0{sh->hist, ka0, kb0 - ka0 > LIST_SPAN}, list1{sh->hist + L1_BINS, ka1, kb1 - ka1 > LIST_SPAN};
+    const TileLists tl = tile_lists(smem_raw, sh, k.list_cap);
+    const KeyList list0{tl.l0, ka0, kb0 - ka0 > LIST_SPAN, tl.bytes}, list1{tl.l1, ka1, kb1 - ka1 > LIST_SPAN, tl.bytes};
     if (threadIdx.x == 0) {
         bool ok = true;
         for (int j = 0; j < 2; ++j) {
             sh->l_len[j] = st.clen[j]; sh->l_below[j] = st.cbelow[j];
-            ok = ok && st.clen[j] <= (j ? list1 : list0).cap() && st.cbelow[j] <= c_lo && c_hi < st.cbelow[j] + st.clen[j];
+            ok = ok && st.clen[j] <= min((j ? list1 : list0).cap(), (unsigned)k.list_cap) && st.cbelow[j] <= c_lo && c_hi < st.cbelow[j] + st.clen[j];
         }
         sh->s_ok = ok ? 1 : 0;
-        if (!ok) tile_to_fallback(k, tile);
+        if (!ok) tile_to_fallback(k, tile, 7);
     }
     __syncthreads();
     if (!sh->s_ok) return;
-    const unsigned* gl = k.lists + (size_t)tile * 2 * SLIST_CAP;
+    const unsigned* gl = k.lists + (size_t)tile * 2 * k.list_cap;
     load_list(list0, gl, sh->l_len[0]);
-    load_list(list1, gl + SLIST_CAP, sh->l_len[1]);
+    load_list(list1, gl + k.list_cap, sh->l_len[1]);
     __syncthreads();
     {
         const unsigned r_lo[2] = {c_lo - sh->l_below[0], c_lo - sh->l_below[1]};
@@ -1333,6 +1430,7 @@ __global__ void __launch_bounds__(DL_UPD_THREADS) dl_update_kernel(DictKernelArg
             d.dconsts[tile] = c;
         }
     }
+    __syncwarp();
     done = __shfl_sync(0xffffffffu, done, 0);
     if (done) return;
     {
@@ -1355,7 +1453,7 @@ __global__ void __launch_bounds__(NT) vahadane_plan_conc_kernel(TileKernelArgs k
         sh->flags = 0;
         for (int q = 0; q < 6; ++q) sh->Msrc[q] = st.Msrc[q];
         make_lasso_consts(sh->Msrc, k.a.lasso_lambda, sh->lk);
-        if (lasso_mode_of(sh->lk.rg00, sh->lk.rg11, sh->lk.g01) == LASSO_GENERAL) { tile_to_fallback(k, tile); sh->flags = -1; }
+        if (lasso_mode_of(sh->lk.rg00, sh->lk.rg11, sh->lk.g01) == LASSO_GENERAL) { tile_to_fallback(k, tile, 6); sh->flags = -1; }
         sh->s_cnt = 0; sh->s_ok = 0;
     }
     __syncthreads();
@@ -1365,6 +1463,23 @@ __global__ void __launch_bounds__(NT) vahadane_plan_conc_kernel(TileKernelArgs k
 
 // ------------------------------------------------------------------------------------------------ host side
 constexpr int STREAM_SUB_BATCH = 4096;              // tiles per round of passes: bounds the key-list scratch at 256 MB
+
+// status must have been preset to SB_STATUS_EMPTY_MASK on the stream (launch_mask does it).
+int launch_mask_stream(const PointArgs& a, int num_sms, cudaStream_t stream) {
+    MaskOutParams p{};
+    p.gamma = a.tab.gamma; p.ycoef[0] = a.ycoef[0]; p.ycoef[1] = a.ycoef[1]; p.ycoef[2] = a.ycoef[2]; p.ybound = a.ybound;
+    p.mask_out = a.mask_out; p.status = a.status; p.npx = a.npx;
+    return launch_ring_reduce<MaskOutOp>(RingGeom{a.in, nullptr, a.B, a.npx}, p, num_sms, stream);
+}
+
+int stream_fallback_counters(unsigned out[8], bool reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_fallback_reasons, 8 * sizeof(unsigned));
+    if (e == cudaSuccess && reset) {
+        const unsigned zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        e = cudaMemcpyToSymbol(g_fallback_reasons, zero, sizeof(zero));
+    }
+    return (int)e;
+}
 
 bool stream_pipeline_eligible(const PipeArgs& a) {
     return (a.method == SB_METHOD_MACENKO || a.method == SB_METHOD_VAHADANE) && a.aligned && a.npx >= 32768 && (a.npx % GROUP_PX) == 0 &&
@@ -1376,12 +1491,13 @@ static int stream_sub_batch(int B, int npx) {
     long long n = (1LL << 30) / (npx > 0 ? npx : 1);
     if (n > STREAM_SUB_BATCH) n = STREAM_SUB_BATCH;
     if (n < 1) n = 1;
+    // (beyond a megapixel the lists double: at most 2^30 / npx < 1024 tiles of them, 128 MB)
     return (int)(B < n ? B : n);
 }
 size_t stream_scratch_bytes(int B, int npx) {
     const size_t n = (size_t)stream_sub_batch(B, npx);
     return up256(n * sizeof(TileState)) + up256(n * sizeof(AngleConsts)) + up256(n * sizeof(ConcConsts)) +
-           up256(n * 2 * SLIST_CAP * sizeof(unsigned)) + up256((n + 1) * sizeof(int)) + up256(n * (size_t)(npx / GROUP_PX) * sizeof(unsigned short)) +
+           up256(n * 2 * (size_t)slist_cap(npx) * sizeof(unsigned)) + up256((n + 1) * sizeof(int)) + up256(n * (size_t)(npx / GROUP_PX) * sizeof(unsigned short)) +
            up256(n * sizeof(DictState)) + up256(n * sizeof(DictConsts));
 }
 
@@ -1395,7 +1511,8 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
     if ((e = scratch.get(&state, (size_t)nsub * sizeof(TileState))) != cudaSuccess) return (int)e;
     if ((e = scratch.get(&ac, (size_t)nsub * sizeof(AngleConsts))) != cudaSuccess) return (int)e;
     if ((e = scratch.get(&cc, (size_t)nsub * sizeof(ConcConsts))) != cudaSuccess) return (int)e;
-    if ((e = scratch.get(&lists, (size_t)nsub * 2 * SLIST_CAP * sizeof(unsigned))) != cudaSuccess) return (int)e;
+    const int list_cap = slist_cap(a_all.npx);
+    if ((e = scratch.get(&lists, (size_t)nsub * 2 * list_cap * sizeof(unsigned))) != cudaSuccess) return (int)e;
     if ((e = scratch.get(&fb, (size_t)(nsub + 1) * sizeof(int))) != cudaSuccess) return (int)e;
     if ((e = scratch.get(&mask, (size_t)nsub * (size_t)(a_all.npx / GROUP_PX) * sizeof(unsigned short))) != cudaSuccess) return (int)e;
     const bool vahadane = a_all.method == SB_METHOD_VAHADANE;
@@ -1405,9 +1522,9 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
         if ((e = scratch.get(&dconsts, (size_t)nsub * sizeof(DictConsts))) != cudaSuccess) return (int)e;
     }
     static DeviceOnce once_v;
-    if ((e = ensure_dyn_smem(once_v, vahadane_plan_conc_kernel, (int)TILE_SHARED_BYTES)) != cudaSuccess) return (int)e;
+    if ((e = ensure_dyn_smem(once_v, vahadane_plan_conc_kernel, (int)tile_shared_bytes(SLIST_CAP_MAX))) != cudaSuccess) return (int)e;
     static DeviceOnce once_p, once_a, once_c;
-    const int tsm = (int)TILE_SHARED_BYTES;
+    const int tsm = (int)tile_shared_bytes(SLIST_CAP_MAX), tsm_run = (int)tile_shared_bytes(list_cap);
     if ((e = ensure_dyn_smem(once_p, plan_angle_kernel, tsm)) != cudaSuccess) return (int)e;
     if ((e = ensure_dyn_smem(once_a, select_angle_kernel, tsm)) != cudaSuccess) return (int)e;
     if ((e = ensure_dyn_smem(once_c, select_conc_kernel, tsm)) != cudaSuccess) return (int)e;
@@ -1423,10 +1540,10 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
         if ((e = cudaMemsetAsync(fb + nsub, 0, sizeof(int), st)) != cudaSuccess) return (int)e;
         StreamParams p{};
         p.state = state; p.aconsts = ac; p.cconsts = cc; p.lists = lists; p.od = a.tab.od; p.gamma = a.tab.gamma;
-        p.mask = mask; p.groups = a.npx / GROUP_PX;
+        p.mask = mask; p.groups = a.npx / GROUP_PX; p.list_cap = list_cap;
         p.ycoef[0] = a.ycoef[0]; p.ycoef[1] = a.ycoef[1]; p.ycoef[2] = a.ycoef[2]; p.ybound = a.ybound;
         const RingGeom g{a.in, nullptr, a.B, a.npx};
-        TileKernelArgs k{a, state, ac, cc, lists, fb, fb + nsub};
+        TileKernelArgs k{a, state, ac, cc, lists, list_cap, fb, fb + nsub};
         int rc;
         int n_launch = 0;
         if (vahadane) {
@@ -1442,17 +1559,17 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
                 dl_update_kernel<<<a.B, DL_UPD_THREADS, 0, st>>>(d);
             }
             n_launch = 2 + 2 * n_full;
-            if (a.mode >= PIPE_FIT) { NvtxRange r("stream: plan concentration"); vahadane_plan_conc_kernel<<<a.B, NT, tsm, st>>>(k); ++n_launch; }
+            if (a.mode >= PIPE_FIT) { NvtxRange r("stream: plan concentration"); vahadane_plan_conc_kernel<<<a.B, NT, tsm_run, st>>>(k); ++n_launch; }
         } else {
             { NvtxRange r("stream: moments"); if ((rc = launch_ring_reduce<MomentOp>(g, p, num_sms, st)) != 0) return rc; }
-            { NvtxRange r("stream: plan angle"); plan_angle_kernel<<<a.B, NT, tsm, st>>>(k); }
+            { NvtxRange r("stream: plan angle"); plan_angle_kernel<<<a.B, NT, tsm_run, st>>>(k); }
             { NvtxRange r("stream: angle brackets"); if ((rc = launch_ring_reduce<AngleOp>(g, p, num_sms, st)) != 0) return rc; }
-            { NvtxRange r("stream: select angle"); select_angle_kernel<<<a.B, NT, tsm, st>>>(k); }
+            { NvtxRange r("stream: select angle"); select_angle_kernel<<<a.B, NT, tsm_run, st>>>(k); }
             n_launch = 4;
         }
         if (a.mode >= PIPE_FIT) {
             { NvtxRange r("stream: concentration brackets"); if ((rc = launch_ring_reduce<ConcOp>(g, p, num_sms, st)) != 0) return rc; }
-            { NvtxRange r("stream: select concentration"); select_conc_kernel<<<a.B, NT, tsm, st>>>(k); }
+            { NvtxRange r("stream: select concentration"); select_conc_kernel<<<a.B, NT, tsm_run, st>>>(k); }
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
         // tiles the streaming passes did not serve: the fused kernel, driven by the device-side list (no host sync)

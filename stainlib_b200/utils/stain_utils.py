@@ -68,14 +68,14 @@ class LuminosityThresholdTissueLocator(ABCTissueLocator):
     def get_tissue_mask(I, luminosity_threshold=0.8):
         assert is_uint8_image(I), "Image should be RGB uint8."
         b = nv.Batch(I)
-        mask = b.dev_tensor((b.B, b.H, b.W), torch.uint8)
+        mask = b.dev_tensor((b.B, b.H, b.W), torch.bool)       # the kernel writes 0 / 1 bytes: a bool tensor, no conversion pass
         status = b.dev_tensor((b.B,), torch.int32)
         nv.check(nv.load_library().sb_tissue_mask(b.handle, nv.ptr(b.dev), b.B, b.H, b.W, float(luminosity_threshold),
                                                   nv.ptr(mask), nv.ptr(status), nv.stream_ptr(b.idx)))
         st = status.cpu()
         LuminosityThresholdTissueLocator.last_status = st
         raise_for_status(st, b.single)
-        return b.give_back(mask.bool())
+        return b.give_back(mask)
 
 
 class LuminosityStandardizer(object):
@@ -177,3 +177,59 @@ def convert_OD_to_RGB(OD):
                                                 nv.stream_ptr(idx)))
     assert int(neg.item()) == 0, "Negative optical density."
     return _from_cuda(out, kind)
+
+
+def standardize_brightness(I):
+    """stain_utils.py:188-194: uint8(clip(I * 255 / percentile(I, 90), 0, 255)) per tile (exact 256-bin histogram
+    percentile on the GPU)."""
+    assert is_uint8_image(I), "Image should be RGB uint8."
+    b = nv.Batch(I)
+    out = b.new_like()
+    nv.check(nv.load_library().sb_standardize_brightness(b.handle, nv.ptr(b.dev), nv.ptr(out), b.B, b.H, b.W, nv.stream_ptr(b.idx)))
+    return b.give_back(out)
+
+
+def lab_split(I):
+    """stain_utils.py:146-158: 8-bit RGB -> LAB (OpenCV's integer path, bit-exact), split into three float32 planes
+    I1 = L / 2.55, I2 = a - 128, I3 = b - 128.  One image -> three [H,W] arrays; a batch -> three [B,H,W] tensors."""
+    assert is_uint8_image(I), "Image should be RGB uint8."
+    b = nv.Batch(I)
+    planes = [b.dev_tensor((b.B, b.H, b.W), torch.float32) for _ in range(3)]
+    nv.check(nv.load_library().sb_lab_split(b.handle, nv.ptr(b.dev), b.B * b.H * b.W, nv.ptr(planes[0]), nv.ptr(planes[1]),
+                                            nv.ptr(planes[2]), nv.stream_ptr(b.idx)))
+    return tuple(b.give_back(p) for p in planes)
+
+
+def merge_back(I1, I2, I3):
+    """stain_utils.py:160-172: LAB planes -> RGB uint8.  Like the reference, numpy planes are scaled IN PLACE
+    (I1 *= 2.55, I2 += 128, I3 += 128) as a side effect."""
+    is_np = isinstance(I1, np.ndarray)
+    t = [torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x for x in (I1, I2, I3)]
+    _, idx = nv.get_handle(t[0].device if t[0].is_cuda else None)
+    f64 = t[0].dtype == torch.float64
+    dt = torch.float64 if f64 else torch.float32
+    d = [x.to(device=f"cuda:{idx}", dtype=dt).contiguous() for x in t]
+    out = torch.empty(tuple(d[0].shape) + (3,), dtype=torch.uint8, device=d[0].device)
+    h, _ = nv.get_handle(idx)
+    nv.check(nv.load_library().sb_lab_merge(h, nv.ptr(d[0]), nv.ptr(d[1]), nv.ptr(d[2]), int(f64), d[0].numel(), nv.ptr(out),
+                                            nv.stream_ptr(idx)))
+    if is_np:
+        I1 *= 2.55
+        I2 += 128.0
+        I3 += 128.0
+        return out.cpu().numpy()
+    return out if t[0].is_cuda else out.cpu()
+
+
+def get_mean_std(I):
+    """stain_utils.py:174-186: per-channel mean and population standard deviation of lab_split(I), as the reference's
+    tuples of (1,1) float64 arrays (cv.meanStdDev's output); a batch returns two [B,3] tensors."""
+    assert is_uint8_image(I), "Image should be RGB uint8."
+    b = nv.Batch(I)
+    means = b.dev_tensor((b.B, 3), torch.float64)
+    stds = b.dev_tensor((b.B, 3), torch.float64)
+    nv.check(nv.load_library().sb_lab_mean_std(b.handle, nv.ptr(b.dev), b.B, b.H, b.W, nv.ptr(means), nv.ptr(stds), nv.stream_ptr(b.idx)))
+    if b.single:
+        m, sd = means[0].cpu().numpy(), stds[0].cpu().numpy()
+        return tuple(np.array([[m[k]]]) for k in range(3)), tuple(np.array([[sd[k]]]) for k in range(3))
+    return (means, stds) if b.kind == "cuda" else (means.cpu(), stds.cpu())

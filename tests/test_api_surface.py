@@ -33,7 +33,9 @@ def test_import_paths_and_top_level_exports(stainlib):
     from stainlib.normalization.normalizer import ExtractiveStainNormalizer, ReinhardStainNormalizer
     from stainlib.augmentation.augmenter import StainAugmentor, HedLightColorAugmenter, GrayscaleAugmentor       # noqa: F401
     from stainlib.utils.stain_utils import (LuminosityThresholdTissueLocator, LuminosityStandardizer, get_concentrations,   # noqa: F401
-                                            convert_RGB_to_OD, convert_OD_to_RGB, normalize_matrix_rows, is_uint8_image)
+                                            convert_RGB_to_OD, convert_OD_to_RGB, normalize_matrix_rows, is_uint8_image,
+                                            standardize_brightness, lab_split, merge_back, get_mean_std, get_sign, is_image,
+                                            ABCStainExtractor, ABCTissueLocator)      # everything normalizer.py / augmenter.py import
     from stainlib.utils.excepts import TissueMaskException, InvalidRangeError                                     # noqa: F401
     assert stainlib.MacenkoStainExtractor is MacenkoStainExtractor and stainlib.ExtractiveStainNormalizer is ExtractiveStainNormalizer
     # north_star spellings

@@ -267,3 +267,32 @@ def test_two_devices_one_process(sb):
     assert torch.equal(r.transform(batch.to("cuda:1")).cpu(), r.transform(batch.to("cuda:0")).cpu())
     h = sb.HedLightColorAugmenter()
     assert torch.equal(h.transform(batch.to("cuda:1")).cpu(), h.transform(batch.to("cuda:0")).cpu())
+
+
+@pytest.mark.parametrize("name", ["s_64", "odd_67x53"])
+def test_lab_utilities_vs_reference(sb, golden, name):
+    """standardize_brightness / lab_split / get_mean_std / merge_back (stain_utils.py:146-194), each through its own CUDA
+    entry point, against the reference's own outputs: bit-exact (integer LAB, float32 / float64 arithmetic as numpy's)."""
+    from stainlib_b200.utils.stain_utils import get_mean_std, lab_split, merge_back, standardize_brightness
+    src = golden[f"in/{name}/src"]
+    assert np.array_equal(standardize_brightness(src), golden[f"labutil/{name}/bright"])
+    I1, I2, I3 = lab_split(src)
+    for got, key in ((I1, "I1"), (I2, "I2"), (I3, "I3")):
+        assert got.dtype == np.float32 and np.array_equal(got, golden[f"labutil/{name}/{key}"])
+    m, sd = get_mean_std(src)
+    np.testing.assert_allclose(np.array(m).reshape(3), golden[f"labutil/{name}/means"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(np.array(sd).reshape(3), golden[f"labutil/{name}/stds"], rtol=1e-12, atol=1e-12)
+    assert m[0].shape == (1, 1) and sd[2].shape == (1, 1)
+    J = [(I1 * 0.9 + 3.0), (I2 * 1.1 - 2.0), (I3 * 0.8 + 1.5)]
+    for dt, key in ((np.float32, "merge_f32"), (np.float64, "merge_f64")):
+        planes = [x.astype(dt).copy() for x in J]
+        keep = planes[0].copy()
+        assert np.array_equal(merge_back(*planes), golden[f"labutil/{name}/{key}"])
+        assert np.array_equal(planes[0], keep * dt(2.55) if dt is np.float32 else keep * 2.55)      # scaled in place like the reference
+    # batched tensors
+    batch = torch.from_numpy(np.stack([src, src[::-1].copy()])).cuda()
+    P = lab_split(batch)
+    assert P[0].shape == batch.shape[:3] and np.array_equal(P[0][0].cpu().numpy(), golden[f"labutil/{name}/I1"])
+    mb, sb_ = get_mean_std(batch)
+    np.testing.assert_allclose(mb[0].cpu().numpy(), golden[f"labutil/{name}/means"], rtol=1e-12)
+    assert torch.equal(merge_back(*P)[1].cpu(), torch.from_numpy(so.merge_back(*[p[1].cpu().numpy().copy() for p in P])))

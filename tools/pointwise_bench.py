@@ -52,7 +52,7 @@ rows = [
     ("GrayscaleAugmentor.pop (gray ring)", 6.0, lambda: gray.pop()),
     ("ReinhardStainNormalizer.transform (lab_tile_kernel)", 6.0, lambda: rein.transform(x)),
     ("LuminosityStandardizer.standardize (lab_tile_kernel)", 6.0, lambda: LuminosityStandardizer.standardize(x)),
-    ("get_tissue_mask (mask_kernel)", 4.0, lambda: LuminosityThresholdTissueLocator.get_tissue_mask(x)),
+    ("get_tissue_mask (mask ring pass)", 4.0, lambda: LuminosityThresholdTissueLocator.get_tissue_mask(x)),
     ("MacenkoStainExtractor.get_stain_matrix (tile_pipeline_kernel, extract)", 3.0, lambda: sb.MacenkoStainExtractor.get_stain_matrix(x)),
     ("ExtractiveStainNormalizer('macenko').transform", 6.0, lambda: mac.transform(x)),
 ]
