@@ -88,6 +88,13 @@ long long sb_launch_count(const sb_handle* h);
  * produced them.  Synchronises with the device.  counters: HOST unsigned[8]. */
 int sb_stream_fallbacks(sb_handle* h, unsigned* counters, int reset);
 
+/* Per-pass timing of the streaming statistics (what bench.py's roofline records are made of): with timing enabled, the
+ * next sb_extract / sb_fit / sb_normalize records a CUDA event in front of every launch of its statistics passes on the
+ * caller's stream; sb_get_pass_timing waits for them and returns the number of passes of the LAST call, their
+ * durations (ms) and their names ('\n'-separated).  Off by default: no events, no synchronisation. */
+int sb_set_pass_timing(sb_handle* h, int enable);
+int sb_get_pass_timing(sb_handle* h, int max_passes, float* ms, char* names, int names_bytes);
+
 /* Caller-owned scratch (SURVEY section 8-b "ownership").  sb_workspace_bytes: upper bound of the per-call scratch any
  * entry point takes for a [B,H,W,3] batch.  sb_set_workspace lends `bytes` of DEVICE memory to the handle (NULL, 0
  * takes it back); calls whose scratch fits use it instead of the stream-ordered pool.  The lender must keep it alive

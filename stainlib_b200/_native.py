@@ -27,7 +27,7 @@ EXPORTS = [
     "sb_luminosity_standardize", "sb_hed_augment", "sb_grayscale_augment",
     "sb_slide_grid", "sb_slide_moments", "sb_slide_angle_hist", "sb_slide_conc_hist", "sb_slide_dl_sums", "sb_decode_jpeg",
     "sb_workspace_bytes", "sb_set_workspace", "sb_stream_fallbacks", "sb_standardize_brightness", "sb_lab_mean_std",
-    "sb_lab_split", "sb_lab_merge", "sb_rgb_to_od", "sb_od_to_rgb", "sb_hed_augment_f32",
+    "sb_lab_split", "sb_lab_merge", "sb_set_pass_timing", "sb_get_pass_timing", "sb_rgb_to_od", "sb_od_to_rgb", "sb_hed_augment_f32",
 ]
 
 
@@ -95,6 +95,8 @@ def load_library():
         lib.sb_workspace_bytes.restype = ctypes.c_size_t
         lib.sb_set_workspace.argtypes = [vp, vp, ctypes.c_size_t]
         lib.sb_stream_fallbacks.argtypes = [vp, ctypes.POINTER(ctypes.c_uint), ci]
+        lib.sb_set_pass_timing.argtypes = [vp, ci]
+        lib.sb_get_pass_timing.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float), ctypes.c_char_p, ci]
         lib.sb_standardize_brightness.argtypes = [vp, vp, vp, ci, ci, ci, vp]
         lib.sb_lab_mean_std.argtypes = [vp, vp, ci, ci, ci, vp, vp, vp]
         lib.sb_lab_split.argtypes = [vp, vp, ctypes.c_size_t, vp, vp, vp, vp]
@@ -174,6 +176,22 @@ def stream_fallbacks(device=None, reset=False):
     out = (ctypes.c_uint * 8)()
     check(load_library().sb_stream_fallbacks(h, out, int(bool(reset))))
     return [int(x) for x in out]
+
+
+def set_pass_timing(enable, device=None):
+    h, _ = get_handle(device)
+    check(load_library().sb_set_pass_timing(h, int(bool(enable))))
+
+
+def get_pass_timing(device=None):
+    """[(name, ms), ...] of the statistics passes of the last extract / fit / transform (needs set_pass_timing(True))."""
+    h, _ = get_handle(device)
+    ms = (ctypes.c_float * 48)()
+    names = ctypes.create_string_buffer(4096)
+    n = load_library().sb_get_pass_timing(h, 48, ms, names, 4096)
+    if n < 0:
+        check(n)
+    return list(zip(names.value.decode().split("\n")[:n], [float(ms[i]) for i in range(n)]))
 
 
 def workspace_bytes(B, H, W):

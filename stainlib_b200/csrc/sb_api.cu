@@ -261,6 +261,7 @@ int sb_destroy(sb_handle* h) {
     if (h->d_target) cudaFree(h->d_target);
     if (h->d_status) cudaFree(h->d_status);
     if (h->table_mem) cudaFree(h->table_mem);
+    for (int i = 0; i < sb_handle::MAX_PASS_EVENTS; ++i) if (h->pass_ev[i]) cudaEventDestroy(h->pass_ev[i]);
     }
     delete h;
     return SB_OK;
@@ -532,6 +533,34 @@ int sb_stain_augment(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int 
     if (e != cudaSuccess) return cuda_fail(e, "stain_augment launch");
     h->launches += 1;
     return SB_OK;
+}
+
+int sb_set_pass_timing(sb_handle* h, int enable) {
+    if (!h) return SB_ERR_ARG;
+    h->pass_timing = enable != 0;
+    h->n_pass_ev = 0;
+    return SB_OK;
+}
+
+int sb_get_pass_timing(sb_handle* h, int max_passes, float* ms, char* names, int names_bytes) {
+    if (!h || !ms || max_passes <= 0) return SB_ERR_ARG;
+    sb::DeviceGuard guard(h);
+    if (!guard.ok) return SB_ERR_CUDA;
+    int n = 0;
+    std::string all;
+    for (int i = 0; i + 1 < h->n_pass_ev && n < max_passes; ++i) {
+        if (cudaEventSynchronize(h->pass_ev[i + 1]) != cudaSuccess) return SB_ERR_CUDA;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, h->pass_ev[i], h->pass_ev[i + 1]) != cudaSuccess) return SB_ERR_CUDA;
+        ms[n++] = t;
+        all += h->pass_name[i];
+        all += '\n';
+    }
+    if (names && names_bytes > 0) {
+        std::strncpy(names, all.c_str(), (size_t)names_bytes - 1);
+        names[names_bytes - 1] = 0;
+    }
+    return n;
 }
 
 int sb_stream_fallbacks(sb_handle* h, unsigned* counters, int reset) {

@@ -26,6 +26,12 @@ struct sb_handle {
     unsigned char* user_ws = nullptr;
     size_t user_ws_bytes = 0, user_ws_off = 0;
     int scratch_depth = 0;
+    // optional per-pass timing of the streaming statistics (sb_set_pass_timing): CUDA events on the launching stream
+    static constexpr int MAX_PASS_EVENTS = 48;
+    bool pass_timing = false;
+    cudaEvent_t pass_ev[MAX_PASS_EVENTS] = {};
+    const char* pass_name[MAX_PASS_EVENTS] = {};
+    int n_pass_ev = 0;
 };
 
 // ---- host-side helpers shared by the translation units that hold entry points / launchers

@@ -138,6 +138,15 @@ __device__ __forceinline__ void for_each_px_odg_small(const float2* tab, const u
     }
 }
 
+// bits |= bit when x > thr (x < thr): one compare into a predicate and one predicated OR -- set.gt + and + or costs a third
+// instruction on the ALU pipe, which bounds these kernels.
+__device__ __forceinline__ void or_if_gt(unsigned& bits, float x, float thr, unsigned bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(bits) : "f"(x), "f"(thr), "r"(bit));
+}
+__device__ __forceinline__ void or_if_lt(unsigned& bits, float x, float thr, unsigned bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(bits) : "f"(x), "f"(thr), "r"(bit));
+}
+
 struct WarpScratch {
     unsigned* w;                  // [0, 64) rare-pixel queue, [64, 128) staged keys of list 0, [128, 192) of list 1
     unsigned qlen, n0, n1;        // warp-uniform fill counts
@@ -523,8 +532,8 @@ struct AngleOp {
         for_each_pair_od_abs(tab, w, [&](int i, float2 o0, float2 o1, float2 o2) {
             const float2 h1 = __ffma2_rn(o2, a2, __ffma2_rn(o1, a1, __fmul2_rn(o0, a0)));
             const float2 h2 = __ffma2_rn(o2, b2, __ffma2_rn(o1, b1, __fmul2_rn(o0, b0)));
-            fastbits |= set_gt(fminf(h1.x, h2.x), margin) & (1u << i);
-            fastbits |= set_gt(fminf(h1.y, h2.y), margin) & (2u << i);
+            or_if_gt(fastbits, fminf(h1.x, h2.x), margin, 1u << i);
+            or_if_gt(fastbits, fminf(h1.y, h2.y), margin, 2u << i);
         });
         acc.below1 += __popc(mbits & fastbits);
         rq_push_flagged(ws, mbits & ~fastbits, buf + (threadIdx.x & ~31u) * 48u, [&](bool has, uint32_t rgb) { exact(k, p, tab, ws, acc, tile, has, rgb); });
@@ -679,8 +688,8 @@ struct MaskOp {
         // Y = 871 g[R] + 2929 g[G] + 296 g[B]: integers below 2^24, exact in fp32 in any order -- two pixels per FFMA2
         for_each_pair_od_abs(tab, w, [&](int i, float2 g0, float2 g1, float2 g2) {
             const float2 y = __ffma2_rn(g2, cb, __ffma2_rn(g1, cg, __fmul2_rn(g0, cr)));
-            mbits |= set_lt(y.x, bound) & (1u << i);
-            mbits |= set_lt(y.y, bound) & (2u << i);
+            or_if_lt(mbits, y.x, bound, 1u << i);
+            or_if_lt(mbits, y.y, bound, 2u << i);
         });
         const int g = (int)(px0 >> 4) + (int)threadIdx.x;
         p.mask[(unsigned)tile * (unsigned)p.groups + (unsigned)g] = (unsigned short)mbits;
@@ -729,8 +738,8 @@ struct MaskOutOp {
         unsigned mbits = 0;
         for_each_pair_od_abs(tab, w, [&](int i, float2 g0, float2 g1, float2 g2) {
             const float2 y = __ffma2_rn(g2, cb, __ffma2_rn(g1, cg, __fmul2_rn(g0, cr)));
-            mbits |= set_lt(y.x, bound) & (1u << i);
-            mbits |= set_lt(y.y, bound) & (2u << i);
+            or_if_lt(mbits, y.x, bound, 1u << i);
+            or_if_lt(mbits, y.y, bound, 2u << i);
         });
         acc.any |= mbits;
         // four bits -> four 0/1 bytes: the multiply puts bit j of the nibble at bit 8 j (no two products collide)
@@ -1501,8 +1510,23 @@ size_t stream_scratch_bytes(int B, int npx) {
            up256(n * sizeof(DictState)) + up256(n * sizeof(DictConsts));
 }
 
+// Optional timing of the passes (sb_set_pass_timing): an event in front of every launch and one behind the last, on the
+// launching stream; sb_get_pass_timing reads the differences.  Off by default: nothing is recorded.
+struct PassTimer {
+    sb_handle* h;
+    cudaStream_t st;
+    void mark(const char* name) {
+        if (!h->pass_timing || h->n_pass_ev >= sb_handle::MAX_PASS_EVENTS) return;
+        if (!h->pass_ev[h->n_pass_ev] && cudaEventCreate(&h->pass_ev[h->n_pass_ev]) != cudaSuccess) return;
+        cudaEventRecord(h->pass_ev[h->n_pass_ev], st);
+        h->pass_name[h->n_pass_ev++] = name;
+    }
+};
+
 int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
     cudaStream_t st = scratch.st;
+    PassTimer pt{scratch.h, st};
+    scratch.h->n_pass_ev = 0;
     const int num_sms = scratch.h->num_sms;
     const int nsub = stream_sub_batch(a_all.B, a_all.npx);
     TileState* state = nullptr; AngleConsts* ac = nullptr; ConcConsts* cc = nullptr; unsigned* lists = nullptr; int* fb = nullptr;
@@ -1551,24 +1575,35 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
             const DictKernelArgs d{k, dstate, dconsts, mask};
             const int unit_chunks = unit_groups(a.npx / GROUP_PX);       // chunk = NT groups: a unit of for_each_unit is this many chunks
             const int n_full = a.dl_iters + (a.dl_sample_iters > 0 ? 4 : 0);
+            pt.mark("ring_reduce<MaskOp>: tissue mask");
             { NvtxRange r("stream: tissue mask"); if ((rc = launch_ring_reduce<MaskOp>(g, p, num_sms, st)) != 0) return rc; }
+            pt.mark("dl_sample_kernel: dictionary warm start on the 1-in-16 sample");
             { NvtxRange r("stream: dictionary, sample passes"); dl_sample_kernel<<<a.B, DLS_NT, 0, st>>>(d); }
             for (int it = 0; it < n_full; ++it) {
                 NvtxRange r("stream: dictionary, full pass");
+                pt.mark("ring_reduce<DictOp>: full dictionary pass");
                 if ((rc = launch_ring_reduce<DictOp>(g, p, num_sms, st, unit_chunks)) != 0) return rc;
+                pt.mark("dl_update_kernel");
                 dl_update_kernel<<<a.B, DL_UPD_THREADS, 0, st>>>(d);
             }
             n_launch = 2 + 2 * n_full;
-            if (a.mode >= PIPE_FIT) { NvtxRange r("stream: plan concentration"); vahadane_plan_conc_kernel<<<a.B, NT, tsm_run, st>>>(k); ++n_launch; }
+            if (a.mode >= PIPE_FIT) pt.mark("vahadane_plan_conc_kernel");
+            if (a.mode >= PIPE_FIT) { NvtxRange r("stream: plan concentration"); vahadane_plan_conc_kernel<<<a.B, NT, TILE_LIST_OFFSET, st>>>(k); ++n_launch; }
         } else {
+            pt.mark("ring_reduce<MomentOp>: mask + moments");
             { NvtxRange r("stream: moments"); if ((rc = launch_ring_reduce<MomentOp>(g, p, num_sms, st)) != 0) return rc; }
-            { NvtxRange r("stream: plan angle"); plan_angle_kernel<<<a.B, NT, tsm_run, st>>>(k); }
+            pt.mark("plan_angle_kernel");
+            { NvtxRange r("stream: plan angle"); plan_angle_kernel<<<a.B, NT, TILE_LIST_OFFSET, st>>>(k); }
+            pt.mark("ring_reduce<AngleOp>: angle brackets");
             { NvtxRange r("stream: angle brackets"); if ((rc = launch_ring_reduce<AngleOp>(g, p, num_sms, st)) != 0) return rc; }
+            pt.mark("select_angle_kernel");
             { NvtxRange r("stream: select angle"); select_angle_kernel<<<a.B, NT, tsm_run, st>>>(k); }
             n_launch = 4;
         }
         if (a.mode >= PIPE_FIT) {
+            pt.mark("ring_reduce<ConcOp>: concentration brackets");
             { NvtxRange r("stream: concentration brackets"); if ((rc = launch_ring_reduce<ConcOp>(g, p, num_sms, st)) != 0) return rc; }
+            pt.mark("select_conc_kernel");
             { NvtxRange r("stream: select concentration"); select_conc_kernel<<<a.B, NT, tsm_run, st>>>(k); }
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
@@ -1576,7 +1611,9 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
         PipeArgs f = a;
         f.cluster_size = 1;
         f.tile_list = fb; f.tile_count = fb + nsub;
+        pt.mark("tile_pipeline_kernel: fallback tiles");
         { NvtxRange r("stream: fused fallback"); if ((rc = launch_tile_pipeline(f, num_sms, st)) != 0) return rc; }
+        pt.mark("end");
         scratch.h->launches += n_launch + (a.mode >= PIPE_FIT ? 3 : 1);
     }
     return 0;

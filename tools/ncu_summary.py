@@ -32,14 +32,18 @@ def main():
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
     for rep in sys.argv[4:]:
-        hdr, units, launches = raw(rep)
-        vals = launches[0]
+      hdr, units, launches = raw(rep)
+      seen = set()
+      for li, vals in enumerate(launches):
         full = vals[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").strip()
         kname = full.split("<")[0]
-        m = re.search(r"ring_pointwise_kernel<(?:sb::)?(\w+)", full)
-        if m:                                           # the ring template: keep the Op in the name
-            kname = f"ring_pointwise_kernel<{m.group(1)}>"
-        base = os.path.join(ROOT, "profiles", f"{tag}_{kname}".replace("<", "_").replace(">", ""))
+        m = re.search(r"(ring_pointwise_kernel|ring_reduce_kernel)<(?:sb::)?(\w+)", full)
+        if m:                                           # the ring templates: keep the Op in the name
+            kname = f"{m.group(1)}<{m.group(2)}>"
+        if kname in seen:                               # first profiled launch of every kernel in the report
+            continue
+        seen.add(kname)
+        base = os.path.join(ROOT, "profiles", f"{tag}_{workload}_{kname}".replace("<", "_").replace(">", ""))
         with open(base + "_ncu.csv", "w") as f:
             f.write(f"# ncu --set full --clock-control none, {workload}, first profiled launch; from {os.path.basename(rep)}\n")
             f.write(f"Kernel Name,,{vals[hdr.index('Kernel Name')]}\n")
@@ -63,7 +67,7 @@ def main():
         so = os.path.join(ROOT, "stainlib_b200", "libstainb200.so")
         sha = hashlib.sha256(open(so, "rb").read()).hexdigest()[:16] if os.path.exists(so) else None
         traffic.setdefault(workload, {})[kname] = {"dram_bytes": int(rd + wr), "so_sha16": sha, "report": os.path.basename(rep)}
-        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f":::{li + 1}"], capture_output=True, text=True).stdout
         mix = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_opmix.py"), str(npx), "30"], input=src, capture_output=True, text=True).stdout
         with open(base + "_opmix.txt", "w") as f:
             f.write(f"# executed thread-instructions per pixel, {workload}, {os.path.basename(rep)}\n" + mix)
