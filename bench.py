@@ -571,7 +571,8 @@ def run_extractive(ctx, name, steps, warmup, headline):
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": round(gbs(dom_ms, dom_bpp), 1), "peak": peak, "unit": "GB/s",
                      "frac": round(gbs(dom_ms, dom_bpp) / peak, 4), "peak_source": peak_src, "algorithmic_bytes_per_px": dom_bpp,
                      "launch_ms": round(dom_ms, 4), "launches_per_step": len(by_kernel.get(dom_name, [1])),
-                     "share_of_step": round(tot_ms / med_step_ms, 3), "traffic": ncu_traffic(name, dom_name)},
+                     "share_of_step": round(tot_ms / med_step_ms, 3),
+                     "traffic": ncu_traffic(name, dom_name.replace("ring_reduce<", "ring_reduce_kernel<"))},
         # every statistics pass of the step (read-only, 3 B/px for the ring passes; per-tile kernels have no roofline)
         "roofline_passes": [{"pass": k, "ms": round(ms, 4),
                              **({"frac": round(gbs(ms, 3.0) / peak, 4)} if k.startswith("ring_reduce") and "#" not in k else {})} for k, ms in passes],

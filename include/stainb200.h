@@ -140,8 +140,9 @@ int sb_normalize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, i
  * target slide), possibly sharded over ranks.  Each pass produces statistics that ADD across launches and ranks; the
  * caller all-reduces them and does the small serial steps (covariance + eigenvectors, rank selection in the
  * histograms, stain matrix) on the host between passes -- stainlib_b200/normalization/slide_fit.py is that host side.
- *   sb_slide_moments     masked OD moments: partials double [sb_slide_grid()][10] = (sum od[3], sum od x od[6] (00,01,02,
- *                        11,12,22), n) per CTA; add the rows.
+ *   sb_slide_moments     masked OD moments: partials int64 [sb_slide_grid()][10] = (sum od[3], sum od x od[6] (00,01,02,
+ *                        11,12,22), n) per CTA, the nine sums in FIXED POINT (scale 2^32; n is a plain count): add the rows,
+ *                        all-reduce them as integers, divide by 2^32 -- the totals then do not depend on the sharding.
  *   sb_slide_angle_hist  level 1: hist[4096] += counts of the top 12 bits of the 23-bit angle key of every tissue pixel,
  *                        V (HOST double[6]) = the two leading eigenvectors (rows); level 2: hist[q*2048 + low 11 bits]
  *                        += for keys whose level-1 bin is bins[q] (HOST unsigned[4]).
@@ -152,14 +153,15 @@ int sb_normalize(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out, int B, i
  * values as in csrc/sb_device.cuh (angle_from_key, conc_from_key). */
 int sb_slide_grid(sb_handle* h, int B, int H, int W);
 int sb_slide_moments(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold,
-                     double* partials, void* stream);
+                     long long* partials, void* stream);
 int sb_slide_angle_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold,
                         const double* V, int level, const unsigned* bins, unsigned long long* hist, void* stream);
 /*   sb_slide_dl_sums     one Vahadane dictionary pass: sparse codes of the tissue pixels (sample != 0: of the 1-in-16 sample
- *                        groups of every tile) under the dictionary D (HOST double[6], rows = atoms); partials double
- *                        [sb_slide_grid()][10] = (sum a a^T (00,01,11), sum x a_0 [3], sum x a_1 [3], pixel count). */
+ *                        groups of every tile) under the dictionary D (HOST double[6], rows = atoms); partials int64
+ *                        [sb_slide_grid()][10] = (sum a a^T (00,01,11), sum x a_0 [3], sum x a_1 [3], pixel count), the nine
+ *                        sums in fixed point, scale 2^30. */
 int sb_slide_dl_sums(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold, const double* D,
-                     double dl_lambda, int sample, double* partials, void* stream);
+                     double dl_lambda, int sample, long long* partials, void* stream);
 int sb_slide_conc_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, const double* M, double lasso_lambda,
                        int level, const unsigned* bins, unsigned long long* hist, void* stream);
 

@@ -330,7 +330,7 @@ int sb_slide_grid(sb_handle* h, int B, int H, int W) {
 }
 
 int sb_slide_moments(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold,
-                     double* partials, void* stream) {
+                     long long* partials, void* stream) {
     sb::SlideArgs a;
     int rc = slide_args(h, rgb, B, H, W, luminosity_threshold, a);
     if (rc) return rc;
@@ -364,7 +364,7 @@ int sb_slide_angle_hist(sb_handle* h, const uint8_t* rgb, int B, int H, int W, d
 }
 
 int sb_slide_dl_sums(sb_handle* h, const uint8_t* rgb, int B, int H, int W, double luminosity_threshold, const double* D,
-                     double dl_lambda, int sample, double* partials, void* stream) {
+                     double dl_lambda, int sample, long long* partials, void* stream) {
     sb::SlideArgs a;
     int rc = slide_args(h, rgb, B, H, W, luminosity_threshold, a);
     if (rc) return rc;

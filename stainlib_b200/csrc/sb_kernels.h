@@ -147,7 +147,7 @@ struct SlideArgs {
     float V[6];                 // projection plane (passes 1, 2): rows = the two leading eigenvectors
     LassoK lk;                  // passes 3, 4
     unsigned bins[4];           // level-1 bins refined by passes 2 and 4
-    double* sums;               // pass 0: [grid][10] per-CTA partials (n last)
+    long long* sums;            // passes 0, 5, 6: [grid][10] per-CTA partials, fixed point (2^32 moments, 2^30 dictionary sums); count last
     unsigned long long* hist;   // passes 1-4: [8192] counters, accumulated (+=)
 };
 int slide_grid(const SlideArgs& a, int num_sms);

@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(SLIDE_NT, 2) slide_pass_kernel(SlideArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* od_rep = smem_raw;
     unsigned* hist = reinterpret_cast<unsigned*>(smem_raw + OD_REP_BYTES);          // 8192 counters
-    __shared__ double red[SLIDE_NT / 32][10];
+    __shared__ long long red[SLIDE_NT / 32][10];
     const uint32_t lane_off = (threadIdx.x & 31) << 3;
     const YCoef yc{a.ycoef[0], a.ycoef[1], a.ycoef[2], a.ybound};
     for (int i = threadIdx.x; i < 256 * 32; i += SLIDE_NT)
@@ -740,9 +740,11 @@ __global__ void __launch_bounds__(SLIDE_NT, 2) slide_pass_kernel(SlideArgs a) {
     const float v00 = a.V[0], v01 = a.V[1], v02 = a.V[2], v10 = a.V[3], v11 = a.V[4], v12 = a.V[5];
     const LassoK lk = a.lk;
     const unsigned b0 = a.bins[0], b1 = a.bins[1], b2 = a.bins[2], b3 = a.bins[3];
-    double acc[9];
+    // fixed-point partial sums (the group sums of pass A / the group sums of a dictionary pass): the caller adds the rows of
+    // all CTAs, launches and ranks as INTEGERS, so the totals do not depend on how the slide was sharded
+    long long acc[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+    for (int i = 0; i < 9; ++i) acc[i] = 0;
     unsigned long long cnt = 0;
     for (long long item = blockIdx.x; item < total; item += gridDim.x) {
         const int tile = (int)(item / cpt);
@@ -765,7 +767,7 @@ __global__ void __launch_bounds__(SLIDE_NT, 2) slide_pass_kernel(SlideArgs a) {
                 });
                 cnt += c;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
+                for (int i = 0; i < 9; ++i) acc[i] += to_fix(f[i], FIX_MOMENT);
             } else if (PASS == 5 || PASS == 6) {
                 // Vahadane dictionary pass: sparse codes of the tissue pixels (PASS 6: of the 1-in-16 sample groups of
                 // every tile) under the dictionary in lk; sums of a a^T (3) and x a^T (6), and the pixel count
@@ -786,7 +788,7 @@ __global__ void __launch_bounds__(SLIDE_NT, 2) slide_pass_kernel(SlideArgs a) {
                 });
                 cnt += c;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) acc[i] += (double)f[i];
+                for (int i = 0; i < 9; ++i) acc[i] += to_fix(f[i], FIX_DL);
             } else if (PASS == 1 || PASS == 2) {
                 for_each_px_odg(od_rep, lane_off, w, [&](int i, float2 r, float2 gg, float2 b) {
                     const float px = fmaf(b.x, v02, fmaf(gg.x, v01, r.x * v00));
@@ -834,8 +836,8 @@ __global__ void __launch_bounds__(SLIDE_NT, 2) slide_pass_kernel(SlideArgs a) {
         // per-CTA partial sums, added on the host in CTA order (fixed order for a fixed grid)
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) acc[i] = warp_sum(acc[i]);
-        const double c = warp_sum((double)cnt);
+        for (int i = 0; i < 9; ++i) acc[i] = warp_sum_ll(acc[i]);
+        const long long c = warp_sum_ll((long long)cnt);
         if (lane == 0) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) red[warp][i] = acc[i];
@@ -843,7 +845,7 @@ __global__ void __launch_bounds__(SLIDE_NT, 2) slide_pass_kernel(SlideArgs a) {
         }
         __syncthreads();
         if (threadIdx.x < 10) {
-            double t = 0.0;
+            long long t = 0;
             for (int wv = 0; wv < SLIDE_NT / 32; ++wv) t += red[wv][threadIdx.x];
             a.sums[(size_t)blockIdx.x * 10 + threadIdx.x] = t;
         }

@@ -70,6 +70,21 @@ def _all_reduce(t, group):
     return t
 
 
+FIX_MOMENT, FIX_DL = float(1 << 32), float(1 << 30)     # csrc/sb_pipe_common.cuh
+
+
+def _reduce_sums(t, group, scale):
+    """All-reduce of a sums vector whose first nine entries are sums and the rest counts.  The device passes return it as
+    int64 with the sums in fixed point: integer addition is exact and order-free, so sharded == unsharded to the last
+    bit; float64 vectors (the CPU stand-ins of the tests) are reduced as they are."""
+    a = _all_reduce(t, group).cpu().numpy()
+    if a.dtype == np.int64:
+        out = a.astype(np.float64)
+        out[:9] /= scale
+        return out
+    return a
+
+
 def _locate(hist, rank):
     """Bin of a cumulative histogram that holds 0-based ``rank`` and the rank inside that bin."""
     cum = np.cumsum(hist)
@@ -95,22 +110,24 @@ class SlidePasses(object):
         return 0 if self.tiles is None else int(self.tiles.shape[0] * self.tiles.shape[1] * self.tiles.shape[2])
 
     def moments(self):
-        out = torch.zeros(10, dtype=torch.float64, device=self.dev)
+        """int64 [10]: fixed-point (2^32) sums of od (3) and od x od (6) over the tissue pixels, and their count."""
+        out = torch.zeros(10, dtype=torch.int64, device=self.dev)
         if self.tiles is not None:
             T, H, W = self._shape()
             grid = self.lib.sb_slide_grid(self.h, T, H, W)
-            part = torch.zeros(grid, 10, dtype=torch.float64, device=self.dev)
+            part = torch.zeros(grid, 10, dtype=torch.int64, device=self.dev)
             nv.check(self.lib.sb_slide_moments(self.h, nv.ptr(self.tiles), T, H, W, self.thr, nv.ptr(part), nv.stream_ptr(self.idx)))
             out = part.sum(dim=0)
         return out
 
     def dl_sums(self, D, lam, sample):
-        """One dictionary pass under D (2x3, rows = atoms): float64 [10] = (A00, A01, A11, B[:,0] (3), B[:,1] (3), count)."""
-        out = torch.zeros(10, dtype=torch.float64, device=self.dev)
+        """One dictionary pass under D (2x3, rows = atoms): int64 [10] = fixed-point (2^30) A00, A01, A11, B[:,0] (3),
+        B[:,1] (3), and the pixel count."""
+        out = torch.zeros(10, dtype=torch.int64, device=self.dev)
         if self.tiles is not None:
             T, H, W = self._shape()
             grid = self.lib.sb_slide_grid(self.h, T, H, W)
-            part = torch.zeros(grid, 10, dtype=torch.float64, device=self.dev)
+            part = torch.zeros(grid, 10, dtype=torch.int64, device=self.dev)
             Dc = (ctypes.c_double * 6)(*[float(x) for x in np.asarray(D).reshape(6)])
             nv.check(self.lib.sb_slide_dl_sums(self.h, nv.ptr(self.tiles), T, H, W, self.thr, Dc, float(lam), int(bool(sample)),
                                                nv.ptr(part), nv.stream_ptr(self.idx)))
@@ -143,9 +160,10 @@ def macenko_slide_fit(tiles, luminosity_threshold=0.8, angular_percentile=99.0, 
     Every rank returns the same numbers.  Raises TissueMaskException when the whole slide has no tissue.
     ``passes``: object with the interface of SlidePasses (the CPU tests of this host logic inject one)."""
     sp = passes if passes is not None else SlidePasses(tiles, luminosity_threshold, lasso_lambda, device)
-    n_px = torch.tensor([sp.n_pixels()], dtype=torch.float64, device=sp.dev)
     # ---- pass 0: moments -> covariance (ddof = 1) -> the two leading eigenvectors, signs as macenko_stain_extractor.py:24-27
-    t = _all_reduce(torch.cat([sp.moments(), n_px]), group).cpu().numpy()
+    mom = sp.moments()
+    n_px = torch.tensor([sp.n_pixels()], dtype=mom.dtype, device=sp.dev)
+    t = _reduce_sums(torch.cat([mom.to(sp.dev), n_px]), group, FIX_MOMENT)
     n, n_all = t[9], int(round(t[10]))
     if n < 1.0:
         raise TissueMaskException("Empty tissue mask computed")
@@ -273,7 +291,7 @@ def vahadane_slide_fit(tiles, luminosity_threshold=0.8, dl_lambda=0.1, dl_iters=
         k += 1
         aa.carry()
         for it in range(n_it):
-            t = _all_reduce(sp.dl_sums(D, dl_lambda, sample), group).cpu().numpy()
+            t = _reduce_sums(sp.dl_sums(D, dl_lambda, sample), group, FIX_DL)
             if sample and it == 0 and t[9] < 1024.0:              # sample too small: four more full passes instead
                 phases[k] = (False, dl_iters + 4)
                 aa = _Anderson(dl_anderson)
