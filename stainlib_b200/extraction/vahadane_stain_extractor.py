@@ -17,14 +17,14 @@ class VahadaneStainExtractor(ABCStainExtractor):
     anderson = 4
 
     @staticmethod
-    def get_stain_matrix(I, luminosity_threshold=0.8, regularizer=0.1, n_iter=None, n_sample_iter=None, anderson=None):
+    def get_stain_matrix(I, luminosity_threshold=0.8, regularizer=0.1, n_iter=None, n_sample_iter=None, anderson=None, cluster_size=None):
         assert is_uint8_image(I), "Image should be RGB uint8."
         cls = VahadaneStainExtractor
         p = nv.default_params(nv.SB_METHOD_VAHADANE, luminosity_threshold=float(luminosity_threshold),
                               dl_lambda=float(regularizer),
                               dl_iters=int(cls.n_iter if n_iter is None else n_iter),
                               dl_sample_iters=int(cls.n_sample_iter if n_sample_iter is None else n_sample_iter),
-                              dl_anderson=int(cls.anderson if anderson is None else anderson))
+                              dl_anderson=int(cls.anderson if anderson is None else anderson), cluster_size=cluster_size)
         M, st = _extract(I, p)
         VahadaneStainExtractor.last_status = st
         return M

@@ -206,3 +206,57 @@ def test_large_tile_mask_recompute_path(sb):
     np.testing.assert_allclose(sb.MacenkoStainExtractor.get_stain_matrix(src), so.macenko_stain_matrix(src), rtol=0, atol=M_ATOL)
     mx, frac = lsb_stats(n.transform(src), o.transform(src), wrap=True)
     assert mx <= 1 and frac >= 0.999, (mx, frac)
+
+
+def _edge_batch_256():
+    """256x256 tiles (large enough for the streaming passes) that exercise every exit of the streaming path: normal tiles,
+    an all-white tile (EMPTY_MASK), one tissue pixel (FEW_TISSUE), a tile with too little tissue for the sampled brackets
+    (-> fused fallback), a dark tile, saturated bands, a near-single-stain tile."""
+    from stainlib_b200.synth import edge_case_tiles
+    e = edge_case_tiles(256, 256)
+    sparse = np.full((256, 256, 3), 255, np.uint8)
+    sparse[:64, :128] = synth_tile(77, 64, 128)                      # ~6000 tissue pixels: below the 16,384 of the sampled path
+    return np.stack([synth_tile(70, 256), e["all_white"], e["one_tissue_pixel"], sparse, e["dark"], e["saturated_bands"],
+                     e["near_single_stain"], synth_tile(71, 256)])
+
+
+@pytest.mark.parametrize("method", ["macenko", "vahadane"])
+def test_streaming_path_equals_fused_path_on_edge_tiles(sb, method):
+    """The streaming passes (automatic choice for aligned tiles of >= 32,768 pixels) and the fused per-tile kernel
+    (cluster_size=1) must give the same bytes, stain matrices and status words, tile by tile, including flagged tiles and
+    tiles the streaming path hands back to the fused kernel."""
+    from stainlib_b200 import _native as nv
+    tiles = torch.from_numpy(_edge_batch_256()).cuda()
+    tgt = synth_tile(1, 256, kind="target")
+    a = sb.ExtractiveStainNormalizer(method)
+    b = sb.ExtractiveStainNormalizer(method, cluster_size=1)
+    a.fit(tgt)
+    b.fit(tgt)
+    assert np.array_equal(a.stain_matrix_target, b.stain_matrix_target) and np.array_equal(a.maxC_target, b.maxC_target)
+    nv.stream_fallbacks(reset=True)
+    out_a, out_b = a.transform(tiles), b.transform(tiles)
+    assert torch.equal(a.last_status, b.last_status)
+    st = a.last_status.cpu().numpy()
+    # (one tissue pixel: np.cov is NaN for Macenko -> FEW_TISSUE; the dictionary learner accepts it and the 99th percentile
+    #  of its concentrations is zero -> ZERO_MAXC, output zeros like the reference's division by zero)
+    assert st[0] == 0 and st[1] & 1 and st[2] != 0 and st[7] == 0
+    assert (st[2] & 2) if method == "macenko" else (st[2] & 4)
+    assert torch.equal(out_a, out_b)
+    assert torch.equal(out_a[1], tiles[1])                                              # flagged tiles pass through
+    if method == "macenko":
+        assert torch.equal(out_a[2], tiles[2])
+    assert nv.stream_fallbacks()[0] >= 1                                              # the sparse tile took the fused kernel
+    ext = sb.MacenkoStainExtractor if method == "macenko" else sb.VahadaneStainExtractor
+    Ma, Mb = ext.get_stain_matrix(tiles), ext.get_stain_matrix(tiles, cluster_size=1)
+    assert torch.equal(torch.nan_to_num(Ma, nan=-7.0), torch.nan_to_num(Mb, nan=-7.0))
+    assert bool(torch.isnan(Ma[1]).all()) and not bool(torch.isnan(Ma[0]).any())
+
+
+def test_streaming_path_parameters(sb):
+    """Non-default parameters through the streaming passes against the oracle: angular percentile, luminosity threshold."""
+    src, tgt = synth_tile(81, 256), synth_tile(1, 256, kind="target")
+    M = sb.MacenkoStainExtractor.get_stain_matrix(src, luminosity_threshold=0.7, angular_percentile=95)
+    np.testing.assert_allclose(M, so.macenko_stain_matrix(src, luminosity_threshold=0.7, angular_percentile=95), atol=M_ATOL)
+    batch = torch.from_numpy(np.stack([src, synth_tile(82, 256)])).cuda()
+    Mb = sb.MacenkoStainExtractor.get_stain_matrix(batch, luminosity_threshold=0.7, angular_percentile=95)
+    np.testing.assert_allclose(Mb[0].cpu().numpy(), M, atol=0)

@@ -130,3 +130,14 @@ def test_vahadane_host_device_and_shards_bytes_equal(sb):
         vs.fit(tgt)
         assert np.array_equal(vs.stain_matrix_target, v.stain_matrix_target), S
         assert torch.equal(vs.transform(batch.cuda()).cpu(), ref), S
+
+
+def test_vahadane_streaming_plain_iteration(sb):
+    """The plain (un-accelerated, no warm start) 30-pass iteration through the streaming passes (256x256 tile) against the
+    CPU full-batch restatement and against the fused kernel."""
+    I = synth_tile(9, 256)
+    M = sb.VahadaneStainExtractor.get_stain_matrix(I, n_iter=30, n_sample_iter=0, anderson=0)
+    M_f = sb.VahadaneStainExtractor.get_stain_matrix(I, n_iter=30, n_sample_iter=0, anderson=0, cluster_size=1)
+    assert np.array_equal(M, M_f)
+    M_o = so.vahadane_stain_matrix(I, solver="fullbatch", n_iter=30)
+    np.testing.assert_allclose(M, M_o, rtol=0, atol=1e-4)
