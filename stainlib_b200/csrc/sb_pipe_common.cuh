@@ -25,7 +25,10 @@ struct __align__(16) PipeShared {
     unsigned okey[4];                // the four selected 23-bit keys (either selection path writes them)
     // sampled-bracket selection
     unsigned lhist[2][256];
-    unsigned l_len[2], l_below[2], l_bin[2], l_rem[2], l_cnt[2], l_min[2], s_cnt;
+    // 16-byte aligned: the compiler fetches l_len/l_below with one LDS.128, which must not straddle lhist's last word
+    // (a block zeroing lhist while a slower thread still loads its ranks is how compute-sanitizer racecheck saw it)
+    alignas(16) unsigned l_len[2];
+    unsigned l_below[2], l_bin[2], l_rem[2], l_cnt[2], l_min[2], s_cnt;
     double ang[4], cs[4];            // the four selected angles; cos/sin of the two interpolated ones
     unsigned brk_a[2], brk_b[2];
     float fast_lo[2], fast_hi[2];    // conservative float thresholds that let most pixels skip the exact key
