@@ -1298,6 +1298,9 @@ __global__ void __launch_bounds__(DLS_NT, 8) dl_sample_kernel(DictKernelArgs d) 
         k.aconsts[tile].mode = 1;
         k.cconsts[tile].mode = 1;
         if (n_tissue < 1u) { sh->flags = SB_STATUS_EMPTY_MASK; tile_flagged(k, tile, SB_STATUS_EMPTY_MASK); }
+        // a sample too thin for the warm start (< 1024 tissue pixels): the tile's 4 extra full passes are not worth four
+        // launches for the whole batch -- the fused kernel runs it
+        else if (a.dl_sample_iters > 0 && !((double)st.mom[0] >= 1024.0)) { sh->flags = -1; tile_to_fallback(k, tile, 1); }
         const double r0[3] = {0.65, 0.70, 0.29}, r1[3] = {0.07, 0.99, 0.11};
         const double n0 = sqrt(r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]), n1 = sqrt(r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
         for (int q = 0; q < 3; ++q) { sh->D[q] = r0[q] / n0; sh->D[3 + q] = r1[q] / n1; }
@@ -1392,7 +1395,7 @@ __global__ void __launch_bounds__(DLS_NT, 8) dl_sample_kernel(DictKernelArgs d) 
         for (int q = 0; q < 10; ++q) ds.sums[q] = 0ull;
         ds.aa = sh->aa;
         ds.it = 0;
-        ds.n_it = a.dl_iters + ((a.dl_sample_iters > 0 && !use_sample) ? 4 : 0);
+        ds.n_it = a.dl_iters;
         if (ds.n_it <= 0) dl_tile_done(d, tile, sh->D);
         else {
             DictConsts c;
@@ -1574,7 +1577,7 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
             p.dstate = dstate; p.dconsts = dconsts;
             const DictKernelArgs d{k, dstate, dconsts, mask};
             const int unit_chunks = unit_groups(a.npx / GROUP_PX);       // chunk = NT groups: a unit of for_each_unit is this many chunks
-            const int n_full = a.dl_iters + (a.dl_sample_iters > 0 ? 4 : 0);
+            const int n_full = a.dl_iters;       // (tiles without a usable sample, which get 4 more, are fallback tiles)
             pt.mark("ring_reduce<MaskOp>: tissue mask");
             { NvtxRange r("stream: tissue mask"); if ((rc = launch_ring_reduce<MaskOp>(g, p, num_sms, st)) != 0) return rc; }
             pt.mark("dl_sample_kernel: dictionary warm start on the 1-in-16 sample");
