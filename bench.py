@@ -543,6 +543,10 @@ def run_extractive(ctx, name, steps, warmup, headline):
     peak, peak_src = measured_peak()
     med_step_ms = float(np.median(per_step_ms))
     gbs = lambda ms, bpp: npx_rank * bpp / (ms * 1e-3) / 1e9
+    # the statistics passes run in rounds of at most 4096 tiles / 2^30 pixels (sb_stream.cu: stream_sub_batch): one launch of a
+    # pass covers one round, not the whole batch
+    round_tiles = min(B, 4096, max(1, (1 << 30) // (H * W)))
+    gbs_pass = lambda ms, bpp: round_tiles * H * W * bpp / (ms * 1e-3) / 1e9
     # The step is a sequence of kernels; its DOMINANT kernel is the one with the largest total time per step.  Candidates: the
     # read-only streaming passes of the statistics (3 algorithmic B/px each; the Vahadane dictionary pass runs several times
     # per step: its first launch, with every tile still iterating, is the one whose bytes are known) and K4 (6 B/px).
@@ -554,6 +558,7 @@ def run_extractive(ctx, name, steps, warmup, headline):
         by_kernel.setdefault(short(k), []).append(ms)
     cands = [(sum(v), kname, v[0], 3.0) for kname, v in by_kernel.items()] + [(k4_ms, "ring_pointwise_kernel<K4Op>", k4_ms, BYTES_PER_PX)]
     tot_ms, dom_name, dom_ms, dom_bpp = max(cands) if cands else (stats_ms, "tile_pipeline_kernel", stats_ms, 3.0)
+    gbs_dom = gbs if dom_name.startswith("ring_pointwise") or not cands else gbs_pass     # K4 is one launch over the whole batch
     fb = nv.stream_fallbacks(ctx.local, reset=True)
     rec = {
         "metric": metric_name(method), "value": round(value, 1), "unit": "Mpx/s", "n_gpus": ctx.world,
@@ -568,14 +573,15 @@ def run_extractive(ctx, name, steps, warmup, headline):
         "e2e": e2e,
         "gpu_launches": int(launches),
         # dominant kernel of the step (largest total time per step), timed by CUDA events in front of / behind its launch
-        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": round(gbs(dom_ms, dom_bpp), 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(gbs(dom_ms, dom_bpp) / peak, 4), "peak_source": peak_src, "algorithmic_bytes_per_px": dom_bpp,
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": round(gbs_dom(dom_ms, dom_bpp), 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(gbs_dom(dom_ms, dom_bpp) / peak, 4), "peak_source": peak_src, "algorithmic_bytes_per_px": dom_bpp,
                      "launch_ms": round(dom_ms, 4), "launches_per_step": len(by_kernel.get(dom_name, [1])),
+                     "tiles_per_launch": round_tiles if gbs_dom is gbs_pass else B,
                      "share_of_step": round(tot_ms / med_step_ms, 3),
                      "traffic": ncu_traffic(name, dom_name.replace("ring_reduce<", "ring_reduce_kernel<"))},
         # every statistics pass of the step (read-only, 3 B/px for the ring passes; per-tile kernels have no roofline)
         "roofline_passes": [{"pass": k, "ms": round(ms, 4),
-                             **({"frac": round(gbs(ms, 3.0) / peak, 4)} if k.startswith("ring_reduce") and "#" not in k else {})} for k, ms in passes],
+                             **({"frac": round(gbs_pass(ms, 3.0) / peak, 4)} if k.startswith("ring_reduce") and "#" not in k else {})} for k, ms in passes],
         "roofline_stats": {"kernel": "all statistics passes of a step (sb_fit)", "launch_ms": round(stats_ms, 4), "frac_at_3_B_per_px": round(gbs(stats_ms, 3.0) / peak, 4),
                            "share_of_step": round(stats_ms / med_step_ms, 3)},
         "roofline_k4": {"bound": "hbm", "kernel": "ring_pointwise_kernel<K4Op> (fused OD+recombine on the TMA ring)",

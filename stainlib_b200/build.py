@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstainb200.so")
-SOURCES = ["sb_api.cu", "sb_pipeline.cu", "sb_stream.cu", "sb_pointwise.cu", "sb_colour.cu", "sb_recombine.cu", "sb_io.cu"]
+SOURCES = ["sb_api.cu", "sb_pipeline.cu", "sb_stream.cu", "sb_pointwise.cu", "sb_colour.cu", "sb_reinhard.cu", "sb_recombine.cu", "sb_io.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -15,6 +15,7 @@
 //   gray_kernel       GrayscaleAugmentor.pop       augmenter.py:390-401
 #include "sb_kernels.h"
 #include "sb_ring.cuh"
+#include "sb_lab.cuh"
 #include "sb_tables.inc"
 
 namespace sb {
@@ -64,13 +65,6 @@ __device__ __forceinline__ void lab_forward(const LabShared* sh, int r, int g, i
     // no saturation needed: over all 2^24 colours L is in [0,255], a in [42,226], b in [20,223] (tests/test_oracle_lab.py)
 }
 
-__device__ __forceinline__ int ab_to_xz(int t) {
-    // inverse companding in fixed point, C truncating division.  t <= 20545, so the cubic branch stays below 2^31 and,
-    // being positive, divides by shifting; the linear branch (very dark colours, possibly negative t) is rare
-    if (t > 3390) return (int)((((unsigned)(t * t) >> 14) * (unsigned)t) >> 14);
-    return (t * 108) / 841 - 290;
-}
-
 __device__ __forceinline__ void lab_inverse(const LabShared* sh, int L, int A, int Bc, int& r, int& g, int& b) {
     const int y = sh->yf[2 * L], ify = sh->yf[2 * L + 1];
     const int adiv = ((5 * A * 53687 + 128) >> 13) - 128 * 16384 / 500;
@@ -82,32 +76,6 @@ __device__ __forceinline__ void lab_inverse(const LabShared* sh, int L, int A, i
     r = sh->invg[min(max(ro, 0), 4095)];
     g = sh->invg[min(max(go, 0), 4095)];
     b = sh->invg[min(max(bo, 0), 4095)];
-}
-
-// numpy.percentile (linear) of uint8-valued data given its exact histogram (n values), evaluated by one thread.
-__device__ inline double hist_percentile(const unsigned* h, unsigned long long n, double pct) {
-    const double vi = (double)(n - 1) * (pct / 100.0);
-    unsigned long long lo = (unsigned long long)floor(vi);
-    if (lo > n - 1) lo = n - 1;
-    const unsigned long long hi = lo + 1 < n ? lo + 1 : n - 1;
-    const double frac = vi - (double)lo;
-    unsigned long long c = 0;
-    int vlo = 255, vhi = 255;
-    bool flo = false, fhi = false;
-    for (int v = 0; v < 256; ++v) {
-        c += h[v];
-        if (!flo && c > lo) { vlo = v; flo = true; }
-        if (!fhi && c > hi) { vhi = v; fhi = true; }
-    }
-    return lerp_np((double)vlo, (double)vhi, frac);
-}
-
-__device__ inline unsigned char trunc_clip_u8(double x) {
-    // np.clip(x, 0, 255).astype(np.uint8); NaN -> 0
-    if (!(x == x)) return 0;
-    if (x <= 0.0) return 0;
-    if (x >= 255.0) return 255;
-    return (unsigned char)(int)x;
 }
 
 __global__ void __launch_bounds__(NT, 2) lab_tile_kernel(LabArgs a) {
@@ -715,8 +683,17 @@ int lab_lmax(double thr) {
         if ((double)L / 255.0 < thr) best = L;
     return best;
 }
+// Diagnostic switch (A/B timing, path-equality tests): SB_REINHARD_TILE_KERNEL=1 keeps aligned tiles on lab_tile_kernel.
+bool ring_disabled() {
+    const char* e = getenv("SB_REINHARD_TILE_KERNEL");
+    return e && e[0] == '1';
+}
 int launch_lab(sb_handle* hh, sb::LabArgs& a, cudaStream_t st) {
     sb_handle* h = hh;
+    // 16-byte aligned tiles: the streaming passes of sb_reinhard.cu (same bytes; lab_tile_kernel keeps the rest)
+    if (a.mode != sb::BRIGHTNESS_STANDARDIZE && a.aligned && sb::reinhard_ring_eligible(a.in, a.out ? a.out : a.in, a.npx) && !ring_disabled())
+        return sb::launch_reinhard_ring(h, a.in, a.out, a.B, a.npx, a.mode, a.skip_brightness, a.tmeans, a.tstds, a.means_out, a.stds_out,
+                                        a.mask_background, a.lmax, a.percentile, a.status, st);
     a.tab = h->tab;
     static sb::DeviceOnce once;
     if (sb::ensure_dyn_smem(once, sb::lab_tile_kernel, (int)sizeof(sb::LabShared)) != cudaSuccess) return SB_ERR_CUDA;

@@ -153,6 +153,12 @@ struct SlideArgs {
 int slide_grid(const SlideArgs& a, int num_sms);
 int launch_slide_pass(const SlideArgs& a, int pass, int grid, cudaStream_t stream);
 
+// ---- Reinhard / luminosity standardiser as streaming passes on the TMA ring (sb_reinhard.cu); mode = LabMode 0..2 of sb_colour.cu
+bool reinhard_ring_eligible(const void* in, const void* out, int npx);
+int launch_reinhard_ring(sb_handle* h, const uint8_t* in, uint8_t* out, int B, int npx, int mode, int skip_brightness, const double* tmeans,
+                         const double* tstds, double* means_out, double* stds_out, int mask_background, int lmax, double percentile,
+                         int32_t* status, cudaStream_t st);
+
 // ---- pointwise kernels (sb_pointwise.cu)
 struct PointArgs {
     const uint8_t* in;
