@@ -487,7 +487,9 @@ int sb_concentrations(sb_handle* h, const uint8_t* rgb, int B, int H, int W, con
     sb::PointArgs a{};
     a.in = rgb; a.B = B; a.npx = H * W; a.aligned = is_aligned(rgb, rgb, a.npx);
     a.tab = h->tab; a.M = M; a.lasso_lambda = lasso_lambda; a.conc_out = C;
-    cudaError_t e = (cudaError_t)sb::launch_concentrations(a, h->num_sms, (cudaStream_t)stream);
+    // 16-byte aligned tiles: a pass on the TMA ring with coalesced stores; register-staged kernel otherwise (same bits)
+    cudaError_t e = (cudaError_t)(sb::concentrations_stream_eligible(a) ? sb::launch_concentrations_stream(a, h->num_sms, (cudaStream_t)stream)
+                                                                       : sb::launch_concentrations(a, h->num_sms, (cudaStream_t)stream));
     if (e != cudaSuccess) return cuda_fail(e, "concentrations launch");
     h->launches += 1;
     return SB_OK;

@@ -102,6 +102,19 @@ struct Scratch {
     Scratch& operator=(const Scratch&) = delete;
 };
 
+// Optional timing of the passes (sb_set_pass_timing): an event in front of every launch and one behind the last, on the
+// launching stream; sb_get_pass_timing reads the differences.  Off by default: nothing is recorded.
+struct PassTimer {
+    sb_handle* h;
+    cudaStream_t st;
+    void mark(const char* name) {
+        if (!h->pass_timing || h->n_pass_ev >= sb_handle::MAX_PASS_EVENTS) return;
+        if (!h->pass_ev[h->n_pass_ev] && cudaEventCreate(&h->pass_ev[h->n_pass_ev]) != cudaSuccess) return;
+        cudaEventRecord(h->pass_ev[h->n_pass_ev], st);
+        h->pass_name[h->n_pass_ev++] = name;
+    }
+};
+
 }  // namespace sb
 
 namespace sb {
@@ -185,6 +198,8 @@ int launch_recombine_normalize(const PointArgs& a, Scratch& scratch, bool use_tm
                                const double* maxC_src, const double* Mt, const double* maxCt, int32_t* status);
 int launch_stain_augment(const PointArgs& a, Scratch& scratch);
 int launch_concentrations(const PointArgs& a, int num_sms, cudaStream_t stream);
+bool concentrations_stream_eligible(const PointArgs& a);                             // sb_stream.cu: concentrations as a pass on the TMA ring
+int launch_concentrations_stream(const PointArgs& a, int num_sms, cudaStream_t stream);
 int launch_rgb_to_od(const uint8_t* in, void* out, size_t n, int f32, const double* od64, int num_sms, cudaStream_t stream);
 int launch_od_to_rgb(const void* od, uint8_t* out, size_t n, int f32, int* negative, int num_sms, cudaStream_t stream);
 

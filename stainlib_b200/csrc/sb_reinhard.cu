@@ -488,6 +488,8 @@ int launch_reinhard_ring(sb_handle* h, const uint8_t* in, uint8_t* out, int B, i
                          const double* tstds, double* means_out, double* stds_out, int mask_background, int lmax, double percentile,
                          int32_t* status, cudaStream_t st) {
     Scratch scratch(h, st);
+    PassTimer pt{h, st};
+    h->n_pass_ev = 0;
     const size_t nb = (size_t)B * 256;
     unsigned* hist = nullptr; unsigned* lhist = nullptr; float* gam2 = nullptr; unsigned long long* sums = nullptr; uint2* tl_ab = nullptr;
     cudaError_t e;
@@ -503,12 +505,15 @@ int launch_reinhard_ring(sb_handle* h, const uint8_t* in, uint8_t* out, int B, i
     int launches = 0;
     if (!skip) {
         NvtxRange r("reinhard: byte histogram");
+        pt.mark("rein_ring<ByteHistOp>: histogram of all channel bytes");
         if (launch_rein_ring<ByteHistOp>(RingGeom{in, nullptr, B, npx}, ByteHistParams{hist}, h->num_sms, st) != 0) return SB_ERR_CUDA;
         ++launches;
     }
+    pt.mark("rein_plan_kernel");
     rein_plan_kernel<<<B, 256, 0, st>>>(hist, npx, h->tab.gamma, skip, gam2);
     {
         NvtxRange r("reinhard: LAB statistics");
+        pt.mark(mode == REIN_STATS ? "rein_ring<LabStatsOp>: forward LAB + statistics (read only)" : "rein_ring<LabStatsOp>: forward LAB + statistics, LAB bytes parked");
         const LabStatsParams p{gam2, h->tab.cbrt, lhist, sums};
         const int rc = mode == REIN_STATS ? launch_rein_ring<LabStatsOp<false>>(RingGeom{in, nullptr, B, npx}, p, h->num_sms, st)
                                           : launch_rein_ring<LabStatsOp<true>>(RingGeom{in, out, B, npx}, p, h->num_sms, st);
@@ -517,10 +522,12 @@ int launch_reinhard_ring(sb_handle* h, const uint8_t* in, uint8_t* out, int B, i
     ReinStatsArgs sa{};
     sa.lhist = lhist; sa.sums = sums; sa.npx = npx; sa.mode = mode; sa.tmeans = tmeans; sa.tstds = tstds; sa.means_out = means_out; sa.stds_out = stds_out;
     sa.mask_background = mask_background; sa.lmax = lmax; sa.percentile = percentile; sa.lab2yf = h->tab.lab2yf; sa.tl_ab = tl_ab; sa.status = status;
+    pt.mark("rein_stats_kernel");
     rein_stats_kernel<<<B, 256, 0, st>>>(sa);
     launches += 3;
     if (mode != REIN_STATS) {
         NvtxRange r("reinhard: map + inverse conversion");
+        pt.mark("rein_ring<LabInvOp>: map + inverse LAB, in place");
         LabInvParams p{tl_ab, h->tab.invgamma, 0, 0};
         p.adiv_bg = ((5 * 128 * 53687 + 128) >> 13) - 128 * 16384 / 500;
         p.bdiv_bg = ((128 * 41943 + 16) >> 9) - 128 * 16384 / 200 + 1;
@@ -530,6 +537,7 @@ int launch_reinhard_ring(sb_handle* h, const uint8_t* in, uint8_t* out, int B, i
         if (rc != 0) return SB_ERR_CUDA;
         ++launches;
     }
+    pt.mark("end");
     if (cudaGetLastError() != cudaSuccess) return SB_ERR_CUDA;
     h->launches += launches;
     return SB_OK;

@@ -280,6 +280,34 @@ static int launch_ring_reduce(const RingGeom& g, const typename Op::Params& p, i
     return (int)cudaGetLastError();
 }
 
+// The per-tile kernels read the 1-in-16 sample of a tile two or three times.  Out of the tile that is one 48-byte group every
+// 768 bytes: DRAM delivers 64-byte granules, so the sample costs a fifth of the whole tile in traffic, scattered.  The first
+// ring pass has every group in shared memory anyway: the thread that holds a sample group copies it to a packed per-tile
+// buffer (1/16 of the batch, written once, read back coalesced).
+__device__ __forceinline__ void keep_sample_group(uint4* sample, int tile, int groups, int g, const uint32_t (&w)[12]) {
+    if (is_sample_group(g, groups)) {
+        uint4* dst = sample + ((size_t)tile * (size_t)(groups / SAMPLE_STRIDE) + (size_t)(g / SAMPLE_STRIDE)) * 3;
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    }
+}
+// Sample block j of a tile from the packed buffer.
+__device__ __forceinline__ void load_sample_block(const uint4* tile_sample, int j, uint32_t (&w)[12]) {
+    const uint4 a = tile_sample[3 * (size_t)j], b = tile_sample[3 * (size_t)j + 1], c = tile_sample[3 * (size_t)j + 2];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+}
+// f(w) for every sample block of the tile (all threads of the CTA).
+template <class F>
+__device__ __forceinline__ void for_each_packed_sample(const uint4* tile_sample, int n_blk, F&& f) {
+    for (int j = (int)threadIdx.x; j < n_blk; j += NT) {
+        uint32_t w[12];
+        load_sample_block(tile_sample, j, w);
+        f(w);
+    }
+}
+
 __device__ __forceinline__ void load_group_smem(const unsigned char* buf, bool active, uint32_t (&w)[12]) {
     if (active) {
         const uint4* v = reinterpret_cast<const uint4*>(buf + threadIdx.x * 48u);
@@ -414,6 +442,7 @@ struct StreamParams {
     const struct DictConsts* dconsts;
     unsigned short* mask;         // [B][groups]: 16 tissue bits per 16-pixel group, written by pass 1, read by pass 3
     int groups;                   // 16-pixel groups per tile
+    uint4* sample;                // [B][groups / SAMPLE_STRIDE][3]: the 1-in-16 sample groups of every tile, packed (written by the first pass)
     const float* od;
     const unsigned short* gamma;
     float ycoef[3], ybound;
@@ -458,6 +487,7 @@ struct MomentOp {
         if (!active) return;
         uint32_t w[12];
         load_group_smem(buf, true, w);
+        keep_sample_group(p.sample, tile, p.groups, (int)(px0 >> 4) + (int)threadIdx.x, w);      // (first: the stores drain behind the arithmetic)
         const YCoef yc{p.ycoef[0], p.ycoef[1], p.ycoef[2], p.ybound};
         float f[9];
 #pragma unroll
@@ -682,6 +712,7 @@ struct MaskOp {
         if (!active) return;
         uint32_t w[12];
         load_group_smem(buf, true, w);
+        keep_sample_group(p.sample, tile, p.groups, (int)(px0 >> 4) + (int)threadIdx.x, w);
         const float2 cr = dup(p.ycoef[0]), cg = dup(p.ycoef[1]), cb = dup(p.ycoef[2]);
         const float bound = p.ybound;
         unsigned mbits = 0;
@@ -757,6 +788,58 @@ struct MaskOutOp {
     }
 };
 
+// get_concentrations (stain_utils.py:69-78) as a streaming pass: 3 B/px in through the ring, 8 B/px out.  A thread that kept
+// "its" 16-pixel group would write 16 float2 = 128 bytes at a 128-byte stride from its neighbour lanes (32 sectors per store
+// instruction); here the lanes of a warp take CONSECUTIVE pixels of the warp's 512-pixel stretch of the chunk (three byte loads
+// from shared memory: 96 contiguous bytes per warp, broadcast within a word, no bank conflicts), so every store instruction
+// writes 256 contiguous bytes.  The arithmetic is lasso2 of the register-staged concentrations_kernel: same bits.
+struct ConcOutParams {
+    const float* od;
+    const double* M;              // [B][2][3]
+    double lasso_lambda;
+    float* conc_out;              // [B][npx][2]
+    int npx;
+};
+struct ConcOutOp {
+    using Consts = LassoK;
+    using Params = ConcOutParams;
+    struct Acc {};
+    static constexpr int kLaneShift = 2;
+    __device__ static void fill_table(unsigned char* tab, const Params& p, int tid, int n) {
+        for (int i = tid; i < 256 * 32; i += n)
+            *reinterpret_cast<float*>(tab + (i >> 5) * OD_ROW_BYTES + (i & 31) * 4) = p.od[i >> 5];
+    }
+    __device__ static Consts load_consts(const Params& p, int tile) {
+        double M[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) M[q] = p.M[(size_t)tile * 6 + q];
+        LassoK lk;
+        make_lasso_consts(M, p.lasso_lambda, lk);
+        return lk;
+    }
+    __device__ static bool tile_active(const Params&, int) { return true; }
+    __device__ static void acc_init(Acc&) {}
+    __device__ static void process(const Consts& lk, const Params& p, const OdAbs tab, const unsigned char* buf, bool, unsigned px0, WarpScratch&,
+                                   Acc&, int tile, bool) {
+        const unsigned rest = (unsigned)p.npx - px0;                              // pixels of the tile from this chunk on
+        const unsigned n_chunk = rest < (unsigned)(RR_GT * GROUP_PX) ? rest : (unsigned)(RR_GT * GROUP_PX);
+        const unsigned w0 = (threadIdx.x & ~31u) * GROUP_PX;                        // the warp's stretch of the chunk: 512 pixels
+        float2* out = reinterpret_cast<float2*>(p.conc_out) + (size_t)tile * (size_t)p.npx + px0;
+#pragma unroll 4
+        for (unsigned i = 0; i < GROUP_PX; ++i) {
+            const unsigned j = w0 + i * 32u + (threadIdx.x & 31u);
+            if (j < n_chunk) {
+                const unsigned char* b = buf + 3u * j;
+                const uint32_t r = b[0], g = b[1], bl = b[2];
+                float c0, c1;
+                lasso2(lk, od_lookup(tab, r, 0u, 0), od_lookup(tab, g, 0u, 0), od_lookup(tab, bl, 0u, 0), c0, c1);
+                asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(out + j), "f"(c0), "f"(c1) : "memory");
+            }
+        }
+    }
+    __device__ static void finish_run(const Consts&, const Params&, const OdAbs, WarpScratch&, Acc&, int) {}
+};
+
 // One full dictionary pass: sparse-code the tissue pixels under the tile's current dictionary, accumulate a a^T and x a^T.
 // The partial sums are the ones of the fused kernel, bit for bit: fp32 per thread over the groups of one UNIT (the ring
 // hands units to CTAs whole, and thread t of a chunk holds the group thread t of the fused kernel visits), reduced over
@@ -829,6 +912,7 @@ struct TileKernelArgs {
     int list_cap;                 // entries per key list (slist_cap(npx)); the kernels' second shared list sits at TILE_LIST1_OFFSET
     int* fb_list;                 // tiles for the fused kernel
     int* fb_count;
+    const uint4* sample;          // packed 1-in-16 sample of every tile (StreamParams::sample)
 };
 struct TileShared {
     float2 tab[256];
@@ -958,7 +1042,7 @@ __global__ void __launch_bounds__(NT) plan_angle_kernel(TileKernelArgs k) {
     unsigned p_lo[2], p_hi[2];
     { double fr; percentile_index(n_tissue, 100.0 - a.ang_pct, p_lo[0], p_hi[0], fr); percentile_index(n_tissue, a.ang_pct, p_lo[1], p_hi[1], fr); }
     unsigned scnt = 0;
-    for_each_sample_group(tin, npx, 0, G, true, [&](auto, const uint32_t (&w)[12], int, int) {
+    for_each_packed_sample(k.sample + (size_t)tile * (size_t)(G / SAMPLE_STRIDE) * 3, G / SAMPLE_STRIDE, [&](const uint32_t (&w)[12]) {
         for_each_px_odg_small(ts->tab, w, [&](int, float2 r, float2 g, float2 b) {
             const float px = fmaf(b.x, v02, fmaf(g.x, v01, r.x * v00));
             const float py = fmaf(b.x, v12, fmaf(g.x, v11, r.x * v10));
@@ -1023,7 +1107,7 @@ __device__ __forceinline__ void plan_conc_block(const TileKernelArgs& k, int til
     unsigned c_lo, c_hi;
     { double fr; percentile_index((unsigned)npx, a.conc_pct, c_lo, c_hi, fr); }
     unsigned scnt = 0;
-    for_each_sample_group(tin, npx, 0, G, true, [&](auto, const uint32_t (&w)[12], int, int) {
+    for_each_packed_sample(k.sample + (size_t)tile * (size_t)(G / SAMPLE_STRIDE) * 3, G / SAMPLE_STRIDE, [&](const uint32_t (&w)[12]) {
         scnt += GROUP_PX;
         for_each_px_odg_small(ts->tab, w, [&](int, float2 r, float2 g, float2 b) {
             float c0, c1;
@@ -1312,6 +1396,7 @@ __global__ void __launch_bounds__(DLS_NT, 8) dl_sample_kernel(DictKernelArgs d) 
     if (sh->flags != 0) return;
     const bool use_sample = a.dl_sample_iters > 0 && (double)st.mom[0] >= 1024.0;
     const unsigned short* mrow = d.mask + (size_t)tile * G;
+    const uint4* tile_sample = k.sample + (size_t)tile * (size_t)(G / SAMPLE_STRIDE) * 3;
     const int n_blk = G / SAMPLE_STRIDE;                 // sample blocks of the tile (npx is a multiple of 16)
     if (use_sample) {
         for (int it = 0; it < a.dl_sample_iters; ++it) {
@@ -1328,8 +1413,7 @@ __global__ void __launch_bounds__(DLS_NT, 8) dl_sample_kernel(DictKernelArgs d) 
                 if (j < n_blk) {
                     const int g = sample_group_of_block(j);
                     uint32_t w[12];
-                    int nvalid;
-                    load_group<true>(tin, npx, g, true, w, nvalid);
+                    load_sample_block(tile_sample, j, w);
                     const uint32_t mbits = mrow[g];
                     const float2* tb = sh->tab;
                     {
@@ -1484,6 +1568,13 @@ int launch_mask_stream(const PointArgs& a, int num_sms, cudaStream_t stream) {
     return launch_ring_reduce<MaskOutOp>(RingGeom{a.in, nullptr, a.B, a.npx}, p, num_sms, stream);
 }
 
+bool concentrations_stream_eligible(const PointArgs& a) { return a.aligned && a.npx % GROUP_PX == 0 && a.npx >= 4096; }
+int launch_concentrations_stream(const PointArgs& a, int num_sms, cudaStream_t stream) {
+    ConcOutParams p{};
+    p.od = a.tab.od; p.M = a.M; p.lasso_lambda = a.lasso_lambda; p.conc_out = a.conc_out; p.npx = a.npx;
+    return launch_ring_reduce<ConcOutOp>(RingGeom{a.in, nullptr, a.B, a.npx}, p, num_sms, stream);
+}
+
 int stream_fallback_counters(unsigned out[8], bool reset) {
     cudaError_t e = cudaMemcpyFromSymbol(out, g_fallback_reasons, 8 * sizeof(unsigned));
     if (e == cudaSuccess && reset) {
@@ -1510,21 +1601,8 @@ size_t stream_scratch_bytes(int B, int npx) {
     const size_t n = (size_t)stream_sub_batch(B, npx);
     return up256(n * sizeof(TileState)) + up256(n * sizeof(AngleConsts)) + up256(n * sizeof(ConcConsts)) +
            up256(n * 2 * (size_t)slist_cap(npx) * sizeof(unsigned)) + up256((n + 1) * sizeof(int)) + up256(n * (size_t)(npx / GROUP_PX) * sizeof(unsigned short)) +
-           up256(n * sizeof(DictState)) + up256(n * sizeof(DictConsts));
+           up256(n * sizeof(DictState)) + up256(n * sizeof(DictConsts)) + up256(n * (size_t)(npx / GROUP_PX / SAMPLE_STRIDE) * 48);
 }
-
-// Optional timing of the passes (sb_set_pass_timing): an event in front of every launch and one behind the last, on the
-// launching stream; sb_get_pass_timing reads the differences.  Off by default: nothing is recorded.
-struct PassTimer {
-    sb_handle* h;
-    cudaStream_t st;
-    void mark(const char* name) {
-        if (!h->pass_timing || h->n_pass_ev >= sb_handle::MAX_PASS_EVENTS) return;
-        if (!h->pass_ev[h->n_pass_ev] && cudaEventCreate(&h->pass_ev[h->n_pass_ev]) != cudaSuccess) return;
-        cudaEventRecord(h->pass_ev[h->n_pass_ev], st);
-        h->pass_name[h->n_pass_ev++] = name;
-    }
-};
 
 int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
     cudaStream_t st = scratch.st;
@@ -1542,6 +1620,8 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
     if ((e = scratch.get(&lists, (size_t)nsub * 2 * list_cap * sizeof(unsigned))) != cudaSuccess) return (int)e;
     if ((e = scratch.get(&fb, (size_t)(nsub + 1) * sizeof(int))) != cudaSuccess) return (int)e;
     if ((e = scratch.get(&mask, (size_t)nsub * (size_t)(a_all.npx / GROUP_PX) * sizeof(unsigned short))) != cudaSuccess) return (int)e;
+    uint4* sample = nullptr;
+    if ((e = scratch.get(&sample, (size_t)nsub * (size_t)(a_all.npx / GROUP_PX / SAMPLE_STRIDE) * 48)) != cudaSuccess) return (int)e;
     const bool vahadane = a_all.method == SB_METHOD_VAHADANE;
     DictState* dstate = nullptr; DictConsts* dconsts = nullptr;
     if (vahadane) {
@@ -1567,10 +1647,10 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
         if ((e = cudaMemsetAsync(fb + nsub, 0, sizeof(int), st)) != cudaSuccess) return (int)e;
         StreamParams p{};
         p.state = state; p.aconsts = ac; p.cconsts = cc; p.lists = lists; p.od = a.tab.od; p.gamma = a.tab.gamma;
-        p.mask = mask; p.groups = a.npx / GROUP_PX; p.list_cap = list_cap;
+        p.mask = mask; p.groups = a.npx / GROUP_PX; p.list_cap = list_cap; p.sample = sample;
         p.ycoef[0] = a.ycoef[0]; p.ycoef[1] = a.ycoef[1]; p.ycoef[2] = a.ycoef[2]; p.ybound = a.ybound;
         const RingGeom g{a.in, nullptr, a.B, a.npx};
-        TileKernelArgs k{a, state, ac, cc, lists, list_cap, fb, fb + nsub};
+        TileKernelArgs k{a, state, ac, cc, lists, list_cap, fb, fb + nsub, sample};
         int rc;
         int n_launch = 0;
         if (vahadane) {

@@ -296,3 +296,54 @@ def test_lab_utilities_vs_reference(sb, golden, name):
     mb, sb_ = get_mean_std(batch)
     np.testing.assert_allclose(mb[0].cpu().numpy(), golden[f"labutil/{name}/means"], rtol=1e-12)
     assert torch.equal(merge_back(*P)[1].cpu(), torch.from_numpy(so.merge_back(*[p[1].cpu().numpy().copy() for p in P])))
+
+
+def _unaligned_copy(t):
+    """The same tile batch at a data pointer that is NOT a multiple of 16: routes an operator to its register-staged kernel."""
+    flat = torch.empty(t.numel() + 16, dtype=torch.uint8, device=t.device)
+    v = flat[1:1 + t.numel()].view(t.shape)
+    v.copy_(t)
+    assert v.data_ptr() % 16 != 0 and v.is_contiguous()
+    return v
+
+
+@pytest.mark.parametrize("shape", [(5, 128, 160), (3, 512, 512), (2, 272, 1008)])
+def test_reinhard_ring_passes_equal_tile_kernel(sb, shape, monkeypatch):
+    """The streaming passes of sb_reinhard.cu (aligned tiles) and lab_tile_kernel give the same bytes and the same statistics:
+    fit, transform (both mask modes), luminosity standardiser.  The tile kernel is reached through an unaligned copy of the
+    batch and through the diagnostic switch SB_REINHARD_TILE_KERNEL."""
+    B, H, W = shape
+    x = torch.from_numpy(synth_batch(4100, B, H, W)).cuda()
+    x[0, : H // 2] = 255                               # a half-white tile
+    if B > 2:
+        x[2] = 255                                     # an all-background tile: EMPTY_MASK in mask mode
+    xu = _unaligned_copy(x)
+    tgt = synth_tile(1, 128, kind="target")
+    r = sb.ReinhardStainNormalizer()
+    r.fit(tgt)
+    outs = {}
+    for mode in ("ring", "tile"):
+        monkeypatch.setenv("SB_REINHARD_TILE_KERNEL", "1" if mode == "tile" else "0")
+        f = sb.ReinhardStainNormalizer()
+        f.fit(x[1].cpu().numpy())
+        outs[mode] = (r.transform(x), r.transform(x, mask_background=True), r.last_status.clone(),
+                      sb.LuminosityStandardizer.standardize(x, percentile=93), np.array(f.target_means).ravel(), np.array(f.target_stds).ravel())
+    monkeypatch.setenv("SB_REINHARD_TILE_KERNEL", "0")
+    for a, b in zip(outs["ring"], outs["tile"]):
+        assert (torch.equal(a, b) if isinstance(a, torch.Tensor) else np.array_equal(a, b))
+    assert torch.equal(r.transform(xu), outs["ring"][0])
+    assert torch.equal(r.transform(xu, mask_background=True), outs["ring"][1])
+    assert torch.equal(sb.LuminosityStandardizer.standardize(xu, percentile=93), outs["ring"][3])
+    if B > 2:
+        assert int(outs["ring"][2][2]) == 1 and int(outs["ring"][2][1]) == 0
+
+
+def test_concentrations_ring_pass_equals_register_kernel(sb):
+    from stainlib_b200.utils.stain_utils import get_concentrations
+    x = torch.from_numpy(synth_batch(4200, 3, 256, 320)).cuda()
+    M = sb.MacenkoStainExtractor.get_stain_matrix(x)
+    a = get_concentrations(x, M)
+    b = get_concentrations(_unaligned_copy(x), M)
+    assert torch.equal(a, b)
+    ref = so.get_concentrations(x[1].cpu().numpy(), M[1].cpu().numpy())
+    assert np.abs(a[1].cpu().numpy() - ref).max() < 2e-5

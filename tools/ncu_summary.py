@@ -37,7 +37,7 @@ def main():
       for li, vals in enumerate(launches):
         full = vals[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").strip()
         kname = full.split("<")[0]
-        m = re.search(r"(ring_pointwise_kernel|ring_reduce_kernel)<(?:sb::)?(\w+)", full)
+        m = re.search(r"(ring_pointwise_kernel|ring_reduce_kernel|rein_ring_kernel)<(?:sb::)?(\w+(?:<\d>)?)", full)
         if m:                                           # the ring templates: keep the Op in the name
             kname = f"{m.group(1)}<{m.group(2)}>"
         if kname in seen:                               # first profiled launch of every kernel in the report

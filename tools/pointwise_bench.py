@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import stainlib_b200 as sb
 from stainlib_b200.augmentation.augmenter import GrayscaleAugmentor, HedLightColorAugmenter, StainAugmentor
 from stainlib_b200.synth import synth_batch, synth_tile
-from stainlib_b200.utils.stain_utils import LuminosityStandardizer, LuminosityThresholdTissueLocator
+from stainlib_b200.utils.stain_utils import LuminosityStandardizer, LuminosityThresholdTissueLocator, get_concentrations
 
 B, H, W = 1024, 512, 512
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
@@ -44,16 +44,19 @@ mac = sb.ExtractiveStainNormalizer("macenko")
 mac.fit(synth_tile(1, H, W, kind="target"))
 aug = StainAugmentor("macenko")
 aug.fit(x)
+Msrc = sb.MacenkoStainExtractor.get_stain_matrix(x)
 gray = GrayscaleAugmentor()
 gray.fit(x)
 rows = [
     ("HedLightColorAugmenter.transform (hed ring)", 6.0, lambda: hed.transform(x, sigmas=sig, biases=bia)),
     ("StainAugmentor.pop (stain-augment ring)", 6.0, lambda: aug.pop()),
     ("GrayscaleAugmentor.pop (gray ring)", 6.0, lambda: gray.pop()),
-    ("ReinhardStainNormalizer.transform (lab_tile_kernel)", 6.0, lambda: rein.transform(x)),
-    ("LuminosityStandardizer.standardize (lab_tile_kernel)", 6.0, lambda: LuminosityStandardizer.standardize(x)),
+    ("ReinhardStainNormalizer.transform (3 ring passes)", 6.0, lambda: rein.transform(x)),
+    ("ReinhardStainNormalizer.transform mask_background (3 ring passes)", 6.0, lambda: rein.transform(x, mask_background=True)),
+    ("LuminosityStandardizer.standardize (2 ring passes)", 6.0, lambda: LuminosityStandardizer.standardize(x)),
+    ("get_concentrations (fp32 [B,N,2] out)", 11.0, lambda: get_concentrations(x, Msrc)),
     ("get_tissue_mask (mask ring pass)", 4.0, lambda: LuminosityThresholdTissueLocator.get_tissue_mask(x)),
-    ("MacenkoStainExtractor.get_stain_matrix (tile_pipeline_kernel, extract)", 3.0, lambda: sb.MacenkoStainExtractor.get_stain_matrix(x)),
+    ("MacenkoStainExtractor.get_stain_matrix (streaming passes 1-4)", 3.0, lambda: sb.MacenkoStainExtractor.get_stain_matrix(x)),
     ("ExtractiveStainNormalizer('macenko').transform", 6.0, lambda: mac.transform(x)),
 ]
 print(f"# {B} x {H}x{W} tiles, device-resident, ms per call; peak = {peak:.0f} GB/s (measured copy rate)")
