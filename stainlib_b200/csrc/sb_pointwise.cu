@@ -296,51 +296,65 @@ int launch_stain_augment(const PointArgs& a, Scratch& scratch) {
 }
 // ------------------------------------------------------------------------------------------- RGB <-> optical density
 // convert_RGB_to_OD (stain_utils.py:101-112): OD = max(-ln(max(v, 1) / 255), 1e-6) is a function of one uint8, so the
-// kernel is a 256-entry float64 table lookup: 1 B read, 8 B (or 4 B) written per value.  One thread converts 16 bytes.
+// kernel is a 256-entry float64 table lookup: 1 B read, 8 B (or 4 B) written per value.
+// One thread converts FOUR consecutive bytes (one 32-bit word in, 16 / 32 bytes out): the lanes of a warp read 128 contiguous
+// bytes and write 512 / 1024 contiguous bytes per instruction.
 template <typename T>
 __global__ void __launch_bounds__(256) rgb_to_od_kernel(const uint8_t* __restrict__ in, T* __restrict__ out, size_t n, const double* __restrict__ od64) {
     __shared__ T tab[256];
     tab[threadIdx.x] = (T)od64[threadIdx.x];
     __syncthreads();
-    const size_t nvec = n / 16;
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    const size_t nvec = n / 4;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(in) % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(T)) == 0);
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
-        uint32_t w[4];
-        if (vec_ok) { const uint4 x = ldg_stream(reinterpret_cast<const uint4*>(in) + v); w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; }
-        else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { w[i] = 0; for (int j = 0; j < 4; ++j) w[i] |= (uint32_t)in[v * 16 + i * 4 + j] << (8 * j); }
+        uint32_t w;
+        if (vec_ok) w = __ldg(reinterpret_cast<const uint32_t*>(in) + v);
+        else w = (uint32_t)in[4 * v] | ((uint32_t)in[4 * v + 1] << 8) | ((uint32_t)in[4 * v + 2] << 16) | ((uint32_t)in[4 * v + 3] << 24);
+        const T a = tab[w & 255u], b = tab[(w >> 8) & 255u], c = tab[(w >> 16) & 255u], d = tab[w >> 24];
+        if (vec_ok) {
+            if (sizeof(T) == 4) reinterpret_cast<float4*>(out)[v] = make_float4((float)a, (float)b, (float)c, (float)d);
+            else { reinterpret_cast<double2*>(out)[2 * v] = make_double2((double)a, (double)b); reinterpret_cast<double2*>(out)[2 * v + 1] = make_double2((double)c, (double)d); }
+        } else {
+            out[4 * v] = a; out[4 * v + 1] = b; out[4 * v + 2] = c; out[4 * v + 3] = d;
         }
-        T* dst = out + v * 16;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) dst[i] = tab[(w[i >> 2] >> (8 * (i & 3))) & 255u];
     }
-    // ragged tail (< 16 values)
-    if (blockIdx.x == 0 && threadIdx.x < (n & 15)) { const size_t i = nvec * 16 + threadIdx.x; out[i] = tab[in[i]]; }
+    // ragged tail (< 4 values)
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const size_t i = nvec * 4 + threadIdx.x; out[i] = tab[in[i]]; }
 }
 // convert_OD_to_RGB (stain_utils.py:114-124): uint8(255 * exp(-max(OD, 1e-6))), truncation toward zero; min_out[0] is
-// lowered below zero when any OD is negative (the reference asserts OD.min() >= 0).
+// lowered below zero when any OD is negative (the reference asserts OD.min() >= 0).  Four values per thread: one word out.
 template <typename T>
 __global__ void __launch_bounds__(256) od_to_rgb_kernel(const T* __restrict__ od, uint8_t* __restrict__ out, size_t n, int* __restrict__ negative) {
     int neg = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const double x = (double)od[i];
+    const size_t nvec = n / 4;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 4 == 0) && (reinterpret_cast<uintptr_t>(od) % (4 * sizeof(T)) == 0);
+    auto conv = [&](T xv) -> uint32_t {
+        const double x = (double)xv;
         neg |= (x < 0.0);
-        const double v = 255.0 * exp(-fmax(x, 1e-6));
-        out[i] = (uint8_t)(int)v;
+        return (uint32_t)(uint8_t)(int)(255.0 * exp(-fmax(x, 1e-6)));
+    };
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+        T x[4];
+        if (vec_ok && sizeof(T) == 4) { const float4 q = reinterpret_cast<const float4*>(od)[v]; x[0] = (T)q.x; x[1] = (T)q.y; x[2] = (T)q.z; x[3] = (T)q.w; }
+        else if (vec_ok) { const double2 q0 = reinterpret_cast<const double2*>(od)[2 * v], q1 = reinterpret_cast<const double2*>(od)[2 * v + 1]; x[0] = (T)q0.x; x[1] = (T)q0.y; x[2] = (T)q1.x; x[3] = (T)q1.y; }
+        else { x[0] = od[4 * v]; x[1] = od[4 * v + 1]; x[2] = od[4 * v + 2]; x[3] = od[4 * v + 3]; }
+        const uint32_t w = conv(x[0]) | (conv(x[1]) << 8) | (conv(x[2]) << 16) | (conv(x[3]) << 24);
+        if (vec_ok) reinterpret_cast<uint32_t*>(out)[v] = w;
+        else { out[4 * v] = (uint8_t)w; out[4 * v + 1] = (uint8_t)(w >> 8); out[4 * v + 2] = (uint8_t)(w >> 16); out[4 * v + 3] = (uint8_t)(w >> 24); }
     }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const size_t i = nvec * 4 + threadIdx.x; out[i] = (uint8_t)conv(od[i]); }
     if (neg && negative) atomicOr(negative, 1);
 }
 int launch_rgb_to_od(const uint8_t* in, void* out, size_t n, int f32, const double* od64, int num_sms, cudaStream_t stream) {
-    size_t blocks = (n / 16 + 255) / 256;
+    size_t blocks = (n / 4 + 255) / 256;
     if (blocks < 1) blocks = 1;
-    if (blocks > (size_t)num_sms * 8) blocks = (size_t)num_sms * 8;
+    if (blocks > (size_t)num_sms * 16) blocks = (size_t)num_sms * 16;
     if (f32) rgb_to_od_kernel<float><<<(int)blocks, 256, 0, stream>>>(in, static_cast<float*>(out), n, od64);
     else rgb_to_od_kernel<double><<<(int)blocks, 256, 0, stream>>>(in, static_cast<double*>(out), n, od64);
     return (int)cudaGetLastError();
 }
 int launch_od_to_rgb(const void* od, uint8_t* out, size_t n, int f32, int* negative, int num_sms, cudaStream_t stream) {
-    size_t blocks = (n + 255) / 256;
+    size_t blocks = (n / 4 + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > (size_t)num_sms * 16) blocks = (size_t)num_sms * 16;
     if (f32) od_to_rgb_kernel<float><<<(int)blocks, 256, 0, stream>>>(static_cast<const float*>(od), out, n, negative);
