@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(RN_GT + 32, 1) rein_ring_kernel(RingGeom g, ty
                     const int s = i % NST;
                     int tile; size_t off; uint32_t bytes;
                     chunk_geom(c_begin + i, tile, off, bytes);
-                    mbar_wait(&done[s], (uint32_t)((i / NST) & 1));               // stage s holds the finished output of chunk i
+                    mbar_wait_relaxed(&done[s], (uint32_t)((i / NST) & 1));       // stage s holds the finished output of chunk i
                     bulk_store(g.out + (size_t)tile * tile_bytes + off, stage_ptr(s), bytes);
                     if (i >= 1 && i - 1 + NST < n_local) {                          // refill the stage of chunk i-1 once its store has read it
                         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(RN_GT + 32, 1) rein_ring_kernel(RingGeom g, ty
             } else {
                 for (int n = 0; n < n_local; ++n) {
                     const int s = n % NST;
-                    if (n >= NST) mbar_wait(&done[s], (uint32_t)(((n / NST) - 1) & 1));   // the slot's previous chunk has been consumed
+                    if (n >= NST) mbar_wait_relaxed(&done[s], (uint32_t)(((n / NST) - 1) & 1));   // the slot's previous chunk has been consumed
                     int tile; size_t off; uint32_t bytes;
                     chunk_geom(c_begin + n, tile, off, bytes);
                     mbar_expect_tx(&full[s], bytes);
@@ -479,7 +479,8 @@ __global__ void __launch_bounds__(256) rein_stats_kernel(ReinStatsArgs a) {
 
 // ------------------------------------------------------------------------------------------------ host side
 bool reinhard_ring_eligible(const void* in, const void* out, int npx) {
-    return (((uintptr_t)in | (uintptr_t)out) % 16 == 0) && npx % GROUP_PX == 0 && npx >= 4096;
+    // (small tiles: the per-tile table refill -- 16 stores per thread and tile -- stops being negligible against one chunk of work)
+    return (((uintptr_t)in | (uintptr_t)out) % 16 == 0) && npx % GROUP_PX == 0 && npx >= 16384;
 }
 
 // mode: ReinMode.  REIN_STATS: brightness (unless skip_brightness) + means/stds.  REIN_TRANSFORM: full transform into out.

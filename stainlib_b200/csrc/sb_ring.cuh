@@ -41,6 +41,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// The producer lane is AHEAD of the compute warps for the whole kernel, i.e. it is always waiting for a stage to be handed back:
+// a bare try_wait loop keeps issuing (try_wait / yield / branch every few cycles) on the scheduler it shares with four compute
+// warps, and the stages are released at the pace of the slowest warp.  The producer therefore sleeps between polls: a stage
+// freed 0.1 us late is harmless with several chunks in flight.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(100);
+    }
+}
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -107,7 +122,7 @@ __global__ void __launch_bounds__(GT + 32, 1) ring_pointwise_kernel(RingGeom g, 
                 const int s = i % NSTAGE;
                 int tile; size_t off; uint32_t bytes;
                 chunk_geom(c_begin + i, tile, off, bytes);
-                mbar_wait(&done[s], (uint32_t)((i / NSTAGE) & 1));          // stage s holds the finished output of chunk i
+                mbar_wait_relaxed(&done[s], (uint32_t)((i / NSTAGE) & 1));  // stage s holds the finished output of chunk i
                 bulk_store(g.out + (size_t)tile * tile_bytes + off, stage_ptr(s), bytes);
                 // refill the stage of chunk i-1 once its store has finished reading shared memory
                 if (i >= 1 && i - 1 + NSTAGE < n_local) {

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(RR_GT + 32, 1) ring_reduce_kernel(RingGeom g, 
                 if (!Op::tile_active(p, tile)) continue;
                 for (int j = 0; j < run; ++j, ++n) {
                     const int s = n % RR_STAGES;
-                    if (n >= RR_STAGES) mbar_wait(&done[s], (uint32_t)(((n / RR_STAGES) - 1) & 1));     // the slot's previous chunk has been consumed
+                    if (n >= RR_STAGES) mbar_wait_relaxed(&done[s], (uint32_t)(((n / RR_STAGES) - 1) & 1));     // the slot's previous chunk has been consumed
                     const size_t off = (size_t)(first_in_tile + j) * RR_CHUNK;
                     const size_t rem = tile_bytes - off;
                     const uint32_t bytes = (uint32_t)(rem < (size_t)RR_CHUNK ? rem : (size_t)RR_CHUNK);

@@ -9,8 +9,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import stainlib_b200 as sb                                    # noqa: E402
 from stainlib_b200.synth import synth_tile, synth_batch, edge_case_tiles   # noqa: E402
-from stainlib_b200.utils.stain_utils import (LuminosityThresholdTissueLocator, convert_RGB_to_OD, lab_split, merge_back,   # noqa: E402
-                                             get_mean_std, standardize_brightness)
+from stainlib_b200.utils.stain_utils import (LuminosityThresholdTissueLocator, convert_RGB_to_OD, convert_OD_to_RGB, lab_split,   # noqa: E402
+                                             merge_back, get_mean_std, standardize_brightness, get_concentrations)
 
 tgt = synth_tile(1, 256, kind="target")
 e = edge_case_tiles(256, 256)
@@ -34,6 +34,16 @@ get_mean_std(tiles)
 standardize_brightness(tiles)
 r = sb.ReinhardStainNormalizer()
 r.fit(tgt)
-r.transform(tiles)
+r.transform(tiles)                                            # streaming ring passes (sb_reinhard.cu): several tiles per CTA
+r.transform(tiles, mask_background=True)
+sb.LuminosityStandardizer.standardize(tiles)
+big = torch.from_numpy(np.stack([synth_tile(72, 528, 400), synth_tile(73, 528, 400)])).cuda()     # partial last chunk, several CTAs per tile
+r.transform(big)
+os.environ["SB_REINHARD_TILE_KERNEL"] = "1"
+r.transform(tiles)                                            # lab_tile_kernel
+os.environ["SB_REINHARD_TILE_KERNEL"] = "0"
+M = sb.MacenkoStainExtractor.get_stain_matrix(tiles[[0, 2]])
+get_concentrations(tiles[[0, 2]], M)                          # ring pass with coalesced stores
+convert_OD_to_RGB(convert_RGB_to_OD(tiles[0]))
 torch.cuda.synchronize()
 print("sanitize smoke ok", int(m.sum()))
