@@ -431,6 +431,18 @@ __device__ __forceinline__ void stage_flush_rest(unsigned* buf, unsigned& n, uns
     }
 }
 
+// The tissue bits of a group live in global memory (2 bytes per group, written by the first pass).  A load issued when the chunk
+// is taken up is needed a few instructions later and every warp of the CTA waits out the L2 latency at once; so a thread asks
+// for the bits of ITS group of the NEXT chunk one chunk ahead (same tile, 512 groups on) and finds them in a register when it
+// gets there.  First chunk of a run: plain load.
+struct MaskPrefetch { unsigned idx, val; };
+__device__ __forceinline__ unsigned mask_bits_prefetched(const unsigned short* __restrict__ mask, MaskPrefetch& pf, unsigned tile, unsigned groups, unsigned g) {
+    const unsigned idx = tile * groups + g;
+    const unsigned bits = pf.idx == idx ? pf.val : (unsigned)mask[idx];
+    if (g + (unsigned)RR_GT < groups) { pf.val = mask[idx + RR_GT]; pf.idx = idx + RR_GT; } else pf.idx = 0xFFFFFFFFu;
+    return bits;
+}
+
 // ------------------------------------------------------------------------------------------------ pass 1: moments
 struct StreamParams {
     TileState* state;
@@ -847,7 +859,7 @@ struct ConcOutOp {
 struct DictOp {
     using Consts = DictConsts;
     using Params = StreamParams;
-    struct Acc { float2 f[9]; long long s[9]; };
+    struct Acc { float2 f[9]; long long s[9]; MaskPrefetch pf; };
     static constexpr int kLaneShift = 2;
     __device__ static void fill_table(unsigned char* tab, const Params& p, int tid, int n) {
         for (int i = tid; i < 256 * 32; i += n)
@@ -858,6 +870,7 @@ struct DictOp {
     __device__ static void acc_init(Acc& a) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) { a.f[i] = make_float2(0.f, 0.f); a.s[i] = 0; }
+        a.pf.idx = 0xFFFFFFFFu; a.pf.val = 0u;
     }
     template <int LM>
     __device__ static __forceinline__ void add_unit(const LassoK& lk, const OdAbs tab, const uint32_t (&w)[12], uint32_t mbits, float2 (&f)[9]) {
@@ -875,7 +888,7 @@ struct DictOp {
     __device__ static void process(const Consts& k, const Params& p, const OdAbs tab, const unsigned char* buf, bool active, unsigned px0, WarpScratch&,
                                    Acc& acc, int tile, bool unit_end) {
         if (active) {
-            const uint32_t mbits = p.mask[(unsigned)tile * (unsigned)p.groups + (px0 >> 4) + threadIdx.x];
+            const uint32_t mbits = mask_bits_prefetched(p.mask, acc.pf, (unsigned)tile, (unsigned)p.groups, (px0 >> 4) + threadIdx.x);
             uint32_t w[12];
             load_group_smem(buf, true, w);
             if (k.lm == LASSO_UNIT_POS) add_unit<LASSO_UNIT_POS>(k.lk, tab, w, mbits, acc.f);
