@@ -307,7 +307,7 @@ def _unaligned_copy(t):
     return v
 
 
-@pytest.mark.parametrize("shape", [(5, 128, 160), (3, 512, 512), (2, 272, 1008)])
+@pytest.mark.parametrize("shape", [(5, 128, 160), (3, 512, 512), (2, 272, 1008), (4, 128, 128), (300, 128, 144), (1, 1040, 1024)])
 def test_reinhard_ring_passes_equal_tile_kernel(sb, shape, monkeypatch):
     """The streaming passes of sb_reinhard.cu (aligned tiles) and lab_tile_kernel give the same bytes and the same statistics:
     fit, transform (both mask modes), luminosity standardiser.  The tile kernel is reached through an unaligned copy of the
