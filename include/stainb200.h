@@ -214,7 +214,9 @@ int sb_reinhard_transform(sb_handle* h, const uint8_t* rgb_in, uint8_t* rgb_out,
 /* Host feeding (replaces the PIL loading of the reference's callers,
  * stainlib_normalization.ipynb:61-74): batched nvJPEG decode of B baseline JPEGs, all H x W, from HOST memory into the
  * DEVICE batch rgb_out uint8 [B,H,W,3] (interleaved RGB), stream-ordered on `stream`.  jpeg[i] / nbytes[i]: the i-th
- * compressed tile.  SB_ERR_ARG for a corrupt / unsupported stream or a tile that is not H x W. */
+ * compressed tile.  SB_ERR_ARG for a corrupt / unsupported stream or a tile that is not H x W.  Backend: nvJPEG's GPU-assisted
+ * Huffman decoder (library default as the fallback); the environment variable SB_NVJPEG_BACKEND = default | hybrid | gpu_hybrid |
+ * hardware overrides it, SB_ERR_UNSUPPORTED when the requested backend does not exist on the device. */
 int sb_decode_jpeg(sb_handle* h, const uint8_t* const* jpeg, const size_t* nbytes, int B, int H, int W, uint8_t* rgb_out,
                    void* stream);
 

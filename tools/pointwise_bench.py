@@ -12,7 +12,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import stainlib_b200 as sb
 from stainlib_b200.augmentation.augmenter import GrayscaleAugmentor, HedLightColorAugmenter, StainAugmentor
 from stainlib_b200.synth import synth_batch, synth_tile
-from stainlib_b200.utils.stain_utils import LuminosityStandardizer, LuminosityThresholdTissueLocator, get_concentrations
+from stainlib_b200.utils.stain_utils import (LuminosityStandardizer, LuminosityThresholdTissueLocator, get_concentrations, get_mean_std,
+                                             standardize_brightness, lab_split, merge_back, convert_RGB_to_OD, convert_OD_to_RGB)
+from stainlib_b200 import _native as nv
 
 B, H, W = 1024, 512, 512
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
@@ -45,6 +47,16 @@ mac.fit(synth_tile(1, H, W, kind="target"))
 aug = StainAugmentor("macenko")
 aug.fit(x)
 Msrc = sb.MacenkoStainExtractor.get_stain_matrix(x)
+planes = lab_split(x)
+od32 = convert_RGB_to_OD(x, dtype=torch.float32)
+_m, _s = torch.empty(B, 3, dtype=torch.float64, device="cuda"), torch.empty(B, 3, dtype=torch.float64, device="cuda")
+
+
+def rein_stats(t):
+    h, idx = nv.get_handle(0)
+    nv.check(nv.load_library().sb_reinhard_stats(h, nv.ptr(t), B, H, W, nv.ptr(_m), nv.ptr(_s), nv.stream_ptr(idx)))
+
+
 gray = GrayscaleAugmentor()
 gray.fit(x)
 rows = [
@@ -55,6 +67,14 @@ rows = [
     ("ReinhardStainNormalizer.transform mask_background (3 ring passes)", 6.0, lambda: rein.transform(x, mask_background=True)),
     ("LuminosityStandardizer.standardize (2 ring passes)", 6.0, lambda: LuminosityStandardizer.standardize(x)),
     ("get_concentrations (fp32 [B,N,2] out)", 11.0, lambda: get_concentrations(x, Msrc)),
+    ("get_mean_std (byte-free: forward LAB + statistics pass)", 3.0, lambda: get_mean_std(x)),
+    ("ReinhardStainNormalizer.fit statistics over the batch (sb_reinhard_stats: 2 ring passes)", 3.0, lambda: rein_stats(x)),
+    ("standardize_brightness (lab_tile_kernel)", 6.0, lambda: standardize_brightness(x)),
+    ("lab_split (3 float planes out)", 15.0, lambda: lab_split(x)),
+    ("merge_back (3 float planes in)", 15.0, lambda: merge_back(*planes)),
+    ("convert_RGB_to_OD float32", 15.0, lambda: convert_RGB_to_OD(x, dtype=torch.float32)),
+    ("convert_RGB_to_OD float64", 27.0, lambda: convert_RGB_to_OD(x[:512])),
+    ("convert_OD_to_RGB float32", 15.0, lambda: convert_OD_to_RGB(od32)),
     ("get_tissue_mask (mask ring pass)", 4.0, lambda: LuminosityThresholdTissueLocator.get_tissue_mask(x)),
     ("MacenkoStainExtractor.get_stain_matrix (streaming passes 1-4)", 3.0, lambda: sb.MacenkoStainExtractor.get_stain_matrix(x)),
     ("ExtractiveStainNormalizer('macenko').transform", 6.0, lambda: mac.transform(x)),
@@ -63,6 +83,7 @@ print(f"# {B} x {H}x{W} tiles, device-resident, ms per call; peak = {peak:.0f} G
 for name, bpp, fn in rows:
     try:
         ms = timed(fn)
-        print(f"{name:75s} {ms:8.3f} ms  {npx / ms / 1e6:8.1f} Gpx/s  {npx * bpp / ms / 1e6 / peak:6.3f} of peak @ {bpp:.0f} B/px")
+        n_px = npx // 2 if "float64" in name else npx
+        print(f"{name:90s} {ms:8.3f} ms  {n_px / ms / 1e6:8.1f} Gpx/s  {n_px * bpp / ms / 1e6 / peak:6.3f} of peak @ {bpp:.0f} B/px")
     except Exception as e:                                     # keep going: this is a survey
-        print(f"{name:75s} failed: {type(e).__name__}: {e}")
+        print(f"{name:90s} failed: {type(e).__name__}: {e}")
