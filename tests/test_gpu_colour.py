@@ -325,7 +325,7 @@ def test_reinhard_ring_passes_equal_tile_kernel(sb, shape, monkeypatch):
     for mode in ("ring", "tile"):
         monkeypatch.setenv("SB_REINHARD_TILE_KERNEL", "1" if mode == "tile" else "0")
         f = sb.ReinhardStainNormalizer()
-        f.fit(x[1].cpu().numpy())
+        f.fit(x[B - 1].cpu().numpy())
         outs[mode] = (r.transform(x), r.transform(x, mask_background=True), r.last_status.clone(),
                       sb.LuminosityStandardizer.standardize(x, percentile=93), np.array(f.target_means).ravel(), np.array(f.target_stds).ravel())
     monkeypatch.setenv("SB_REINHARD_TILE_KERNEL", "0")
