@@ -347,3 +347,20 @@ def test_concentrations_ring_pass_equals_register_kernel(sb):
     assert torch.equal(a, b)
     ref = so.get_concentrations(x[1].cpu().numpy(), M[1].cpu().numpy())
     assert np.abs(a[1].cpu().numpy() - ref).max() < 2e-5
+
+
+def test_reinhard_tile_bytes_do_not_depend_on_the_batch(sb):
+    """SURVEY section 8-e for the streaming Reinhard passes: how the chunks of a tile fall onto CTAs depends on the batch around it;
+    the statistics are integer sums and histograms, so a tile's bytes and statistics do not."""
+    x = torch.from_numpy(synth_batch(4300, 37, 256, 304)).cuda()
+    r = sb.ReinhardStainNormalizer()
+    r.fit(synth_tile(1, 128, kind="target"))
+    full = r.transform(x, mask_background=True)
+    lum = sb.LuminosityStandardizer.standardize(x)
+    for lo, hi in ((0, 1), (5, 6), (36, 37), (10, 23)):
+        assert torch.equal(r.transform(x[lo:hi].contiguous(), mask_background=True), full[lo:hi])
+        assert torch.equal(sb.LuminosityStandardizer.standardize(x[lo:hi].contiguous()), lum[lo:hi])
+    from stainlib_b200.utils.stain_utils import get_mean_std
+    m_all, s_all = get_mean_std(x)
+    m_one, s_one = get_mean_std(x[7:8].contiguous())
+    assert torch.equal(m_all[7:8], m_one) and torch.equal(s_all[7:8], s_one)
