@@ -1001,7 +1001,7 @@ __device__ __forceinline__ void load_list(const KeyList& l, const unsigned* src,
 }
 
 // 2: covariance + eigenvectors (macenko_stain_extractor.py:22-27), sample of the angle keys -> brackets (B0 of the fused kernel).
-__global__ void __launch_bounds__(NT) plan_angle_kernel(TileKernelArgs k) {
+__global__ void __launch_bounds__(NT, 3) plan_angle_kernel(TileKernelArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared* ts = reinterpret_cast<TileShared*>(smem_raw);
     PipeShared* sh = &ts->ps;
@@ -1180,7 +1180,7 @@ __device__ __forceinline__ void plan_conc_block(const TileKernelArgs& k, int til
 
 // 4: exact angular percentiles from the bracket lists -> stain matrix (macenko_stain_extractor.py:29-44); then the sample of
 // the concentrations -> brackets (C0 of the fused kernel).
-__global__ void __launch_bounds__(NT) select_angle_kernel(TileKernelArgs k) {
+__global__ void __launch_bounds__(NT, 3) select_angle_kernel(TileKernelArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared* ts = reinterpret_cast<TileShared*>(smem_raw);
     PipeShared* sh = &ts->ps;
@@ -1550,7 +1550,7 @@ __global__ void __launch_bounds__(DL_UPD_THREADS) dl_update_kernel(DictKernelArg
 }
 
 // Vahadane, fit / transform: brackets of the concentration pass from the tile's stain matrix (C0).
-__global__ void __launch_bounds__(NT) vahadane_plan_conc_kernel(TileKernelArgs k) {
+__global__ void __launch_bounds__(NT, 3) vahadane_plan_conc_kernel(TileKernelArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared* ts = reinterpret_cast<TileShared*>(smem_raw);
     PipeShared* sh = &ts->ps;
