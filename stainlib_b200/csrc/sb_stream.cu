@@ -31,7 +31,8 @@
 namespace sb {
 
 constexpr int SLIST_CAP_MAX = 16384;                // entries of a per-tile key list in global memory (full 23-bit keys): 8192 for tiles up
-__host__ __device__ inline int slist_cap(int npx) { return npx > (1 << 20) ? SLIST_CAP_MAX : SLIST_CAP_MAX / 2; }   // to a megapixel, 16384 beyond
+// to a megapixel, 16384 beyond; 4096 for tiles up to 2^17 pixels (their brackets hold < 2000 keys), which lets four select CTAs share an SM
+__host__ __device__ inline int slist_cap(int npx) { return npx > (1 << 20) ? SLIST_CAP_MAX : npx > (1 << 17) ? SLIST_CAP_MAX / 2 : SLIST_CAP_MAX / 4; }
 constexpr int RQ_CAP = 64;                          // entries per warp queue: drained below 32 after every push round
 constexpr int RR_GT = 512;                          // compute threads of a ring-reduce CTA (one 16-pixel group each per chunk)
 constexpr int RR_STAGES = 6;
@@ -1001,7 +1002,7 @@ __device__ __forceinline__ void load_list(const KeyList& l, const unsigned* src,
 }
 
 // 2: covariance + eigenvectors (macenko_stain_extractor.py:22-27), sample of the angle keys -> brackets (B0 of the fused kernel).
-__global__ void __launch_bounds__(NT, 3) plan_angle_kernel(TileKernelArgs k) {
+__global__ void __launch_bounds__(NT, 4) plan_angle_kernel(TileKernelArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared* ts = reinterpret_cast<TileShared*>(smem_raw);
     PipeShared* sh = &ts->ps;
@@ -1180,7 +1181,9 @@ __device__ __forceinline__ void plan_conc_block(const TileKernelArgs& k, int til
 
 // 4: exact angular percentiles from the bracket lists -> stain matrix (macenko_stain_extractor.py:29-44); then the sample of
 // the concentrations -> brackets (C0 of the fused kernel).
-__global__ void __launch_bounds__(NT, 3) select_angle_kernel(TileKernelArgs k) {
+// MINB = resident CTAs per SM the register budget is cut for: 4 for the small-tile lists (52 KB of shared memory per CTA), 3 otherwise
+template <int MINB>
+__global__ void __launch_bounds__(NT, MINB) select_angle_kernel(TileKernelArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared* ts = reinterpret_cast<TileShared*>(smem_raw);
     PipeShared* sh = &ts->ps;
@@ -1646,7 +1649,9 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
     static DeviceOnce once_p, once_a, once_c;
     const int tsm = (int)tile_shared_bytes(SLIST_CAP_MAX), tsm_run = (int)tile_shared_bytes(list_cap);
     if ((e = ensure_dyn_smem(once_p, plan_angle_kernel, tsm)) != cudaSuccess) return (int)e;
-    if ((e = ensure_dyn_smem(once_a, select_angle_kernel, tsm)) != cudaSuccess) return (int)e;
+    static DeviceOnce once_a4;
+    if ((e = ensure_dyn_smem(once_a, select_angle_kernel<3>, tsm)) != cudaSuccess) return (int)e;
+    if ((e = ensure_dyn_smem(once_a4, select_angle_kernel<4>, tsm)) != cudaSuccess) return (int)e;
     if ((e = ensure_dyn_smem(once_c, select_conc_kernel, tsm)) != cudaSuccess) return (int)e;
     const size_t tile_bytes = (size_t)a_all.npx * 3;
     for (int t0 = 0; t0 < a_all.B; t0 += nsub) {
@@ -1693,7 +1698,11 @@ int launch_stream_pipeline(const PipeArgs& a_all, Scratch& scratch) {
             pt.mark("ring_reduce<AngleOp>: angle brackets");
             { NvtxRange r("stream: angle brackets"); if ((rc = launch_ring_reduce<AngleOp>(g, p, num_sms, st)) != 0) return rc; }
             pt.mark("select_angle_kernel");
-            { NvtxRange r("stream: select angle"); select_angle_kernel<<<a.B, NT, tsm_run, st>>>(k); }
+            {
+                NvtxRange r("stream: select angle");
+                if (list_cap <= SLIST_CAP_MAX / 4) select_angle_kernel<4><<<a.B, NT, tsm_run, st>>>(k);
+                else select_angle_kernel<3><<<a.B, NT, tsm_run, st>>>(k);
+            }
             n_launch = 4;
         }
         if (a.mode >= PIPE_FIT) {
