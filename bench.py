@@ -282,18 +282,27 @@ def lib_sha16():
         return None
 
 
+def src_sha16():
+    try:
+        from stainlib_b200.build import source_sha16
+        return source_sha16()
+    except Exception:
+        return None
+
+
 def ncu_traffic(workload, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-    (profiles/traffic.json, written by tools/ncu_summary.py).  A capture only describes the binary it was taken from:
-    the entry carries the sha256 of that libstainb200.so and is reported only while the library on disk is that binary
-    (a CUDA process cannot count its own DRAM bytes without a profiler attached); otherwise null."""
+    (profiles/traffic.json, written by tools/ncu_summary.py).  A capture only describes the code it was taken from: the
+    entry carries the sha256 of the library's SOURCES and flags (nvcc rebuilds of the same sources are not bit-identical, so a
+    hash of the .so would not survive a rebuild) and is reported only while the sources on disk are those (a CUDA process
+    cannot count its own DRAM bytes without a profiler attached); otherwise null."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
     t = json.load(open(p))
     e = t.get(workload, {}).get(kernel)
     if isinstance(e, dict):
-        return e.get("dram_bytes") if e.get("so_sha16") == lib_sha16() else None
+        return e.get("dram_bytes") if e.get("src_sha16") == src_sha16() else None
     return None                                         # legacy entry without a binary stamp: evidence about an older build
 
 
@@ -815,6 +824,7 @@ def main():
         line["hbm_probe_gbs"] = round(2 * probe.numel() / (copy_ms * 1e-3) / 1e9, 1)
         line["cpu_baseline"] = cpu
         line["lib_sha16"] = lib_sha16()
+        line["src_sha16"] = src_sha16()
         if subs:
             line["workloads"] = subs
         print(json.dumps(line), flush=True)

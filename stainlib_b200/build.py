@@ -17,6 +17,19 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
 
+def source_sha16():
+    """sha256 (first 16 hex digits) of the library's sources and compiler flags.  nvcc does not produce bit-identical objects from
+    identical sources, so measurements that describe 'this build' (profiles/traffic.json) are stamped with the SOURCES, which
+    every rebuild of the same code shares."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "stainb200.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def _stale():
     if not os.path.exists(LIB):
         return True

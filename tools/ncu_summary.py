@@ -62,11 +62,10 @@ def main():
                 f.write(f"{h},ratio,{v}\n")
         rd = float(vals[hdr.index("dram__bytes_read.sum")]) * UNIT[units[hdr.index("dram__bytes_read.sum")]]
         wr = float(vals[hdr.index("dram__bytes_write.sum")]) * UNIT[units[hdr.index("dram__bytes_write.sum")]]
-        # stamped with the binary it was captured from: bench.py reports it only while that library is the one on disk
-        import hashlib
-        so = os.path.join(ROOT, "stainlib_b200", "libstainb200.so")
-        sha = hashlib.sha256(open(so, "rb").read()).hexdigest()[:16] if os.path.exists(so) else None
-        traffic.setdefault(workload, {})[kname] = {"dram_bytes": int(rd + wr), "so_sha16": sha, "report": os.path.basename(rep)}
+        # stamped with the sources it was captured from: bench.py reports it only while those are the sources on disk
+        sys.path.insert(0, ROOT)
+        from stainlib_b200.build import source_sha16
+        traffic.setdefault(workload, {})[kname] = {"dram_bytes": int(rd + wr), "src_sha16": source_sha16(), "report": os.path.basename(rep)}
         src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f":::{li + 1}"], capture_output=True, text=True).stdout
         mix = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_opmix.py"), str(npx), "30"], input=src, capture_output=True, text=True).stdout
         with open(base + "_opmix.txt", "w") as f:
