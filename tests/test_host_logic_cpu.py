@@ -62,3 +62,28 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
     # one BLAS/OpenMP thread per worker process (oversubscription used to cost the baseline 5-8x)
     assert d["cpu_baseline"]["threads_per_worker"] == 1 and d["cpu_baseline"]["cores"] == os.cpu_count()
+
+
+def test_traffic_entries_are_tied_to_the_sources(tmp_path, monkeypatch):
+    """bench.py reports an ncu DRAM-traffic figure only while the library's sources are the ones the capture was taken from
+    (profiles/traffic.json carries a hash of csrc/ + the header + the nvcc flags; rebuilding the same sources keeps it)."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from stainlib_b200.build import source_sha16
+    sha = source_sha16()
+    assert isinstance(sha, str) and len(sha) == 16 and sha == source_sha16() == bench.src_sha16()
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    (prof / "traffic.json").write_text(json.dumps({"w": {"k_now": {"dram_bytes": 123, "src_sha16": sha},
+                                                          "k_old": {"dram_bytes": 456, "src_sha16": "0" * 16},
+                                                          "k_legacy": 789}}))
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.ncu_traffic("w", "k_now") == 123
+    assert bench.ncu_traffic("w", "k_old") is None
+    assert bench.ncu_traffic("w", "k_legacy") is None
+    assert bench.ncu_traffic("w", "absent") is None and bench.ncu_traffic("other", "k_now") is None
